@@ -1,0 +1,75 @@
+"""ctypes binding of libdca_b200.so (the C ABI declared in include/dca_b200.h).
+
+There is NO fallback: if the shared library is missing the import of any compute entry point raises.
+Build it with `python <package>/build.py` (or `__graft_entry__.build()`).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdca_b200.so")
+
+_c_int = ctypes.c_int
+_vp = ctypes.c_void_p
+_f = ctypes.c_float
+
+# name -> argtypes (return type is int unless listed in _RESTYPES)
+SIGNATURES = {
+    "dca_version": [],
+    "dca_volume_gwc_concat": [_vp, _vp, _vp, _vp, _vp] + [_c_int] * 9 + [_vp],
+    "dca_build_gwc_volume_f32": [_vp, _vp, _vp] + [_c_int] * 6 + [_vp],
+    "dca_build_concat_volume_f32": [_vp, _vp, _vp] + [_c_int] * 5 + [_vp],
+    "dca_conv3d_direct": [_c_int, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _c_int, _c_int, _c_int]
+                         + [_c_int] * 10 + [_vp],
+    "dca_conv3d_cout1": [_vp, _c_int, _vp, _vp] + [_c_int] * 5 + [_vp],
+    "dca_conv3d_tc": [_c_int, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _c_int, _c_int] + [_c_int] * 9 + [_vp],
+    "dca_pack_weights_tc": [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp],
+    "dca_pack_weights_tc_bytes": [_c_int] * 4,
+    "dca_avgpool3d": [_vp, _vp] + [_c_int] * 6 + [_vp],
+    "dca_class_stats": [_vp, _vp, _vp, _vp] + [_c_int] * 4 + [_vp],
+    "dca_disp_attention": [_vp, _vp, _vp, _vp, _vp, _c_int, _vp] + [_c_int] * 6 + [_vp],
+    "dca_upsample_fuse": [_vp] * 6 + [_c_int] * 6 + [_vp],
+    "dca_softmax_regress": [_vp, _vp] + [_c_int] * 4 + [_vp],
+    "dca_convex_upsample": [_vp, _vp, _vp] + [_c_int] * 3 + [_vp],
+    "dca_planes_from_ncdhw": [_vp, _vp] + [_c_int] * 7 + [_vp],
+    "dca_planes_to_ncdhw": [_vp, _c_int, _vp] + [_c_int] * 6 + [_vp],
+    "dca_pack_weights": [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp],
+    "dca_fold_bn": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _c_int, _c_int, _vp],
+}
+_RESTYPES = {"dca_pack_weights_tc_bytes": ctypes.c_longlong}
+
+ERRORS = {-1: "DCA_ERR_ARG (bad pointer/shape)", -2: "DCA_ERR_LAUNCH (CUDA launch failed)",
+          -3: "DCA_ERR_UNSUPPORTED (shape outside what the kernels support)"}
+
+_lib = None
+LAUNCHES = 0   # kernels launched through this binding (bench.py reports it as gpu_launches)
+
+
+class DcaError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once) and declare every prototype.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DcaError(f"{LIB_PATH} not found: the CUDA extension is not built and there is no CPU fallback. "
+                       f"Run `python {os.path.join(_HERE, 'build.py')}`.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
+        fn.argtypes = args
+        fn.restype = _RESTYPES.get(name, ctypes.c_int)
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Invoke an entry point; non-zero status raises DcaError (the reference raises on its asserts)."""
+    global LAUNCHES
+    LAUNCHES += 8 if (name in ("dca_conv3d_direct", "dca_conv3d_tc") and args[0] == 2) else 1
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        raise DcaError(f"{name} failed: {ERRORS.get(rc, rc)}")

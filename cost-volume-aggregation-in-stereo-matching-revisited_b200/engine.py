@@ -1,0 +1,348 @@
+"""Host-side driver of the hot path: parameter packing and the kernel sequence.
+
+torch is used for device memory (torch.empty on the current device), the current CUDA stream and
+nothing else: every arithmetic step below is a call into libdca_b200.so.  No ATen compute op, no
+cuDNN/cuBLAS, no CPU fallback.
+
+Data layout in HBM ("cost planes"): channels-last bf16 `[planes][B][D][H][W][C]`;
+planes=2 ("parity": hi + lo bf16, ~16-bit significand) or planes=1 ("fast": plain bf16).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+K3S1, K3S2, T3S2, K1, C2D3 = 0, 1, 2, 3, 4
+BN_EPS = 1e-5
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.DcaError("dcanet_b200 has no CPU path: tensors must live on a CUDA device")
+
+
+class Planes:
+    """A cost tensor in the kernels' layout."""
+    __slots__ = ("t", "B", "D", "H", "W", "C", "planes")
+
+    def __init__(self, B, D, H, W, C, planes, device, t=None):
+        self.B, self.D, self.H, self.W, self.C, self.planes = B, D, H, W, C, planes
+        self.t = t if t is not None else torch.empty((planes, B, D, H, W, C), dtype=torch.bfloat16, device=device)
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr()
+
+    @classmethod
+    def from_ncdhw(cls, x, planes=2, cpad=None):
+        """fp32 [B,C,D,H,W] (or [B,C,H,W]) -> planes."""
+        _require_cuda(x)
+        if x.dim() == 4:
+            x = x.unsqueeze(2)
+        x = x.contiguous().float()
+        B, C, D, H, W = x.shape
+        Cp = cpad or ((C + 7) // 8 * 8)
+        out = cls(B, D, H, W, Cp, planes, x.device)
+        _lib.call("dca_planes_from_ncdhw", x.data_ptr(), out.ptr, planes, B, C, Cp, D, H, W, _stream())
+        return out
+
+    def to_ncdhw(self, channels=None):
+        C = channels or self.C
+        y = torch.empty((self.B, C, self.D, self.H, self.W), dtype=torch.float32, device=self.t.device)
+        _lib.call("dca_planes_to_ncdhw", self.ptr, self.planes, y.data_ptr(), self.B, C, self.C, self.D, self.H,
+                  self.W, _stream())
+        return y
+
+
+# --------------------------------------------------------------------------------------------
+# parameter packing (load time)
+# --------------------------------------------------------------------------------------------
+class PackedConv:
+    """Conv weight repacked to [taps][Cin][CoutPad] fp32 + folded BN scale/shift (fp32, CoutPad)."""
+
+    def __init__(self, weight, bn=None, transposed=False):
+        _require_cuda(weight)
+        w = weight.detach().contiguous().float()
+        if transposed:
+            ci, co = w.shape[0], w.shape[1]
+        else:
+            co, ci = w.shape[0], w.shape[1]
+        taps = int(w[0, 0].numel())
+        self.cin, self.cout, self.taps = ci, co, taps
+        self.cout_pad = (co + 31) // 32 * 32
+        dev = w.device
+        self.w = torch.empty((taps, ci, self.cout_pad), dtype=torch.float32, device=dev)
+        _lib.call("dca_pack_weights", w.data_ptr(), int(transposed), co, ci, taps, self.w.data_ptr(), self.cout_pad,
+                  _stream())
+        self.scale = self.shift = None
+        if bn is not None:
+            self.scale = torch.empty(self.cout_pad, dtype=torch.float32, device=dev)
+            self.shift = torch.empty(self.cout_pad, dtype=torch.float32, device=dev)
+            g, b = bn.weight.detach().float().contiguous(), bn.bias.detach().float().contiguous()
+            m, v = bn.running_mean.detach().float().contiguous(), bn.running_var.detach().float().contiguous()
+            _lib.call("dca_fold_bn", g.data_ptr(), b.data_ptr(), m.data_ptr(), v.data_ptr(), float(bn.eps),
+                      self.scale.data_ptr(), self.shift.data_ptr(), co, self.cout_pad, _stream())
+        self.w_tc = None     # bf16 operand pack for the tcgen05 kernels (filled by pack_tc)
+        self.tc_planes = 0
+        self._keep = (w,)
+
+    def pack_tc(self, planes, transposed=False):
+        nbytes = _lib.load().dca_pack_weights_tc_bytes(self.cout, self.cin, self.taps, planes)
+        if nbytes <= 0:
+            return False
+        self.w_tc = torch.empty(nbytes, dtype=torch.uint8, device=self.w.device)
+        _lib.call("dca_pack_weights_tc", self._keep[0].data_ptr(), int(transposed), self.cout, self.cin, self.taps,
+                  self.w_tc.data_ptr(), planes, _stream())
+        self.tc_planes = planes
+        return True
+
+
+def pack_convbn(seq, transposed=False):
+    """seq = Sequential(Conv3d/ConvTranspose3d/Conv2d, BatchNorm) as built by convbn_3d / convbn."""
+    return PackedConv(seq[0].weight, seq[1], transposed)
+
+
+# --------------------------------------------------------------------------------------------
+# operators on planes
+# --------------------------------------------------------------------------------------------
+class Options:
+    use_tc = True      # route eligible convs to the tcgen05 kernels
+
+
+def conv(x: Planes, pc: PackedConv, mode=K3S1, act=ACT_NONE, res_pre: Planes = None, res_post: Planes = None,
+         planes_out=None, out_fp32=False):
+    """y = act(scale*conv(x)+shift + res_pre) + res_post.  Returns Planes, or an fp32 channels-last
+    tensor [B,D,H,W,Cout] when out_fp32."""
+    assert x.C == pc.cin, (x.C, pc.cin)
+    if mode == K3S2:
+        Do, Ho, Wo = (x.D + 1) // 2, (x.H + 1) // 2, (x.W + 1) // 2
+    elif mode == T3S2:
+        Do, Ho, Wo = 2 * x.D, 2 * x.H, 2 * x.W
+    else:
+        Do, Ho, Wo = x.D, x.H, x.W
+    planes_out = planes_out or x.planes
+    dev = x.t.device
+    res = res_pre if res_pre is not None else res_post
+    planes_res = res.planes if res is not None else 1
+    if res_pre is not None and res_post is not None:
+        assert res_pre.planes == res_post.planes
+    if out_fp32:
+        y = torch.empty((x.B, Do, Ho, Wo, pc.cout), dtype=torch.float32, device=dev)
+        yptr = y.data_ptr()
+    else:
+        y = Planes(x.B, Do, Ho, Wo, pc.cout, planes_out, dev)
+        yptr = y.ptr
+    if (Options.use_tc and not out_fp32 and pc.w_tc is not None and pc.tc_planes == x.planes
+            and tc_supported(mode, pc.cin, pc.cout)):
+        _lib.call("dca_conv3d_tc", mode, x.ptr, x.planes, pc.w_tc.data_ptr(), _ptr(pc.scale), _ptr(pc.shift),
+                  res_pre.ptr if res_pre is not None else 0, res_post.ptr if res_post is not None else 0, planes_res,
+                  yptr, planes_out, act, x.B, pc.cin, pc.cout, x.D, x.H, x.W, Do, Ho, Wo, _stream())
+        return y
+    _lib.call("dca_conv3d_direct", mode, x.ptr, x.planes, pc.w.data_ptr(), _ptr(pc.scale), _ptr(pc.shift),
+              res_pre.ptr if res_pre is not None else 0, res_post.ptr if res_post is not None else 0, planes_res,
+              yptr, planes_out, 1 if out_fp32 else 0, act, x.B, pc.cin, pc.cout, pc.cout_pad, x.D, x.H, x.W, Do, Ho,
+              Wo, _stream())
+    return y
+
+
+def tc_supported(mode, cin, cout):
+    return False
+
+
+def conv_cout1(x: Planes, w27: torch.Tensor):
+    """Conv3d k3 s1 p1 to one channel -> fp32 logits [B,D,H,W]."""
+    y = torch.empty((x.B, x.D, x.H, x.W), dtype=torch.float32, device=x.t.device)
+    _lib.call("dca_conv3d_cout1", x.ptr, x.planes, w27.data_ptr(), y.data_ptr(), x.B, x.C, x.D, x.H, x.W, _stream())
+    return y
+
+
+def pack_cout1(weight):
+    """[1,Cin,3,3,3] -> [27][Cin] fp32 (uses the generic packer: taps x Cin x CoutPad with CoutPad=1)."""
+    w = weight.detach().contiguous().float()
+    ci = w.shape[1]
+    out = torch.empty((27, ci), dtype=torch.float32, device=w.device)
+    _lib.call("dca_pack_weights", w.data_ptr(), 0, 1, ci, 27, out.data_ptr(), 1, _stream())
+    return out
+
+
+def avgpool(x: Planes):
+    y = Planes(x.B, (x.D + 1) // 2, (x.H + 1) // 2, (x.W + 1) // 2, x.C, x.planes, x.t.device)
+    _lib.call("dca_avgpool3d", x.ptr, y.ptr, x.planes, x.B, x.C, x.D, x.H, x.W, _stream())
+    return y
+
+
+def class_stats(logits):
+    B, D, H, W = logits.shape
+    dev = logits.device
+    cls = torch.empty((B, H, W), dtype=torch.int32, device=dev)
+    e = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    S = torch.empty((B, D), dtype=torch.float32, device=dev)
+    _lib.call("dca_class_stats", logits.data_ptr(), cls.data_ptr(), e.data_ptr(), S.data_ptr(), B, D, H, W, _stream())
+    return cls, e, S
+
+
+def disp_attention(x: Planes, cls, e, S, weights, has_wa):
+    y = Planes(x.B, x.D, x.H, x.W, x.C, x.planes, x.t.device)
+    _lib.call("dca_disp_attention", x.ptr, cls.data_ptr(), e.data_ptr(), S.data_ptr(), weights.data_ptr(),
+              int(has_wa), y.ptr, x.planes, x.B, x.C, x.D, x.H, x.W, _stream())
+    return y
+
+
+def upsample_fuse(t: Planes, cost: Planes, wcT, scale, shift):
+    assert cost.D == 2 * t.D and cost.H == 2 * t.H and cost.W == 2 * t.W, "cva needs even D/4, H/4, W/4"
+    y = Planes(cost.B, cost.D, cost.H, cost.W, cost.C, cost.planes, cost.t.device)
+    _lib.call("dca_upsample_fuse", t.ptr, cost.ptr, wcT.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.ptr,
+              cost.planes, cost.B, cost.C, t.D, t.H, t.W, _stream())
+    return y
+
+
+def softmax_regress(logits):
+    B, D, H, W = logits.shape
+    pred = torch.empty((B, 1, H, W), dtype=torch.float32, device=logits.device)
+    _lib.call("dca_softmax_regress", logits.data_ptr(), pred.data_ptr(), B, D, H, W, _stream())
+    return pred
+
+
+def convex_upsample(mask, disp):
+    B, _, H, W = disp.shape
+    out = torch.empty((B, 1, 4 * H, 4 * W), dtype=torch.float32, device=disp.device)
+    _lib.call("dca_convex_upsample", mask.data_ptr(), disp.data_ptr(), out.data_ptr(), B, H, W, _stream())
+    return out
+
+
+def fused_volume(gwc_l, gwc_r, cat_l, cat_r, D, G, planes, Cv=None):
+    _require_cuda(gwc_l, gwc_r, cat_l, cat_r)
+    B, C, H, W = gwc_l.shape
+    Cc = 0 if cat_l is None else cat_l.shape[1]
+    Cv = Cv or ((G + 2 * Cc + 7) // 8 * 8)
+    vol = Planes(B, D, H, W, Cv, planes, gwc_l.device)
+    _lib.call("dca_volume_gwc_concat", gwc_l.data_ptr(), gwc_r.data_ptr(), _ptr(cat_l), _ptr(cat_r), vol.ptr, B, C, G,
+              Cc, D, H, W, Cv, planes, _stream())
+    return vol
+
+
+def _f32c(t):
+    return t.contiguous().float()
+
+
+# --------------------------------------------------------------------------------------------
+# packed parameter sets for the composite blocks
+# --------------------------------------------------------------------------------------------
+class PackedAttention:
+    """7 transposed 32x32 matrices (q0,q1,k0,k1,v,o,Wa) + 6 x (scale,shift), one flat fp32 buffer."""
+
+    def __init__(self, attn, fuse_conv_weight=None):
+        convs = [attn.query_project[0], attn.query_project[1], attn.key_project[0], attn.key_project[1],
+                 attn.value_project, attn.out_project]
+        dev = convs[0][0].weight.device
+        self.buf = torch.zeros(7 * 1024 + 6 * 64, dtype=torch.float32, device=dev)
+        for i, seq in enumerate(convs):
+            pc = PackedConv(seq[0].weight, seq[1])
+            assert pc.cin == 32 and pc.cout == 32 and pc.taps == 1
+            self.buf[i * 1024:(i + 1) * 1024].copy_(pc.w.view(-1))
+            o = 7 * 1024 + i * 64
+            self.buf[o:o + 32].copy_(pc.scale[:32])
+            self.buf[o + 32:o + 64].copy_(pc.shift[:32])
+        self.has_wa = fuse_conv_weight is not None
+        if self.has_wa:
+            wa = fuse_conv_weight.detach()[:, :32].contiguous()
+            pc = PackedConv(wa)
+            self.buf[6 * 1024:7 * 1024].copy_(pc.w.view(-1))
+
+
+class PackedCva:
+    def __init__(self, m, planes):
+        self.down = pack_convbn(m.downsample[1])
+        self.cls0 = pack_convbn(m.classify[0])
+        self.cls2 = pack_cout1(m.classify[2].weight)
+        fuse_w = m.fuse[0][0].weight                      # [32, 64, 1,1,1]: in = cat(aug, cost)
+        self.attn = PackedAttention(m.slc_net.cross_attention, fuse_w)
+        pc_c = PackedConv(fuse_w.detach()[:, 32:].contiguous(), m.fuse[0][1])
+        self.fuse_wcT = pc_c.w.view(32, 32).contiguous()  # [ci][co]
+        self.fuse_scale, self.fuse_shift = pc_c.scale, pc_c.shift
+        agg = m.cost_agg
+        self.conv1 = pack_convbn(agg.conv1[0])
+        self.conv2 = pack_convbn(agg.conv2[0])
+        self.conv3 = PackedConv(agg.conv3[0].weight, agg.conv3[1], transposed=True)
+        self.redir = pack_convbn(agg.redir)
+        for pc in (self.down, self.cls0, self.conv1, self.conv2):
+            pc.pack_tc(planes)
+        self.conv3.pack_tc(planes, transposed=True)
+
+
+def cva_forward(pk: PackedCva, cost: Planes, res_post: Planes = None, keep=None):
+    """cva.forward(downsample=True): returns (logits fp32 [B,D8,H8,W8], augmented cost Planes)."""
+    pooled = avgpool(cost)
+    cost_down = conv(pooled, pk.down, K3S1, ACT_RELU)
+    h = conv(cost_down, pk.cls0, K3S1, ACT_RELU)
+    logits = conv_cout1(h, pk.cls2)
+    cls, e, S = class_stats(logits)
+    t = disp_attention(cost_down, cls, e, S, pk.attn.buf, pk.attn.has_wa)
+    fused = upsample_fuse(t, cost, pk.fuse_wcT, pk.fuse_scale, pk.fuse_shift)
+    c1 = conv(fused, pk.conv1, K3S2, ACT_RELU)
+    c2 = conv(c1, pk.conv2, K3S1, ACT_RELU)
+    redir = conv(fused, pk.redir, K1, ACT_NONE)
+    out = conv(c2, pk.conv3, T3S2, ACT_RELU, res_pre=redir, res_post=res_post)
+    if keep is not None:
+        keep.update(cost_down=cost_down, logits=logits, class_map=cls, e=e, S=S, t=t, fused=fused, out=out)
+    return logits, out
+
+
+class PackedHotPath:
+    """All hot-path parameters of a GwcNet, packed for the kernels."""
+
+    def __init__(self, net, planes):
+        self.planes = planes
+        self.maxdisp = net.maxdisp
+        self.num_groups = net.num_groups
+        self.dres0_0 = pack_convbn(net.dres0[0]); self.dres0_2 = pack_convbn(net.dres0[2])
+        self.dres1_0 = pack_convbn(net.dres1[0]); self.dres1_2 = pack_convbn(net.dres1[2])
+        self.cva = [PackedCva(m, planes) for m in (net.cva1, net.cva2, net.cva3)]
+        self.cls3_0 = pack_convbn(net.classif3[0])
+        self.cls3_2 = pack_cout1(net.classif3[2].weight)
+        self.prop0 = pack_convbn(net.prop.conv[0])
+        self.prop2 = PackedConv(net.prop.conv[2].weight)
+        for pc in (self.dres0_0, self.dres0_2, self.dres1_0, self.dres1_2, self.cls3_0):
+            pc.pack_tc(planes)
+
+
+def hot_path_forward(pk: PackedHotPath, gwc_l, gwc_r, cat_l, cat_r, g, keep=None):
+    """Feature maps -> (pred4 [B,1,H,W], prob_volume2 logits [B,D8,H8,W8]).
+    Mirrors GwcNet.forward (eval) of the reference, models/gwcnet_dca_g.py:216-240,282."""
+    _require_cuda(gwc_l, gwc_r, cat_l, cat_r, g)
+    P = pk.planes
+    D4 = pk.maxdisp // 4
+    vol = fused_volume(_f32c(gwc_l), _f32c(gwc_r), _f32c(cat_l) if cat_l is not None else None,
+                       _f32c(cat_r) if cat_r is not None else None, D4, pk.num_groups, P)
+    c = conv(vol, pk.dres0_0, K3S1, ACT_RELU)
+    c = conv(c, pk.dres0_2, K3S1, ACT_RELU)
+    r = conv(c, pk.dres1_0, K3S1, ACT_RELU)
+    cost0 = conv(r, pk.dres1_2, K3S1, ACT_NONE, res_post=c)
+    k1 = {} if keep is not None else None
+    k2 = {} if keep is not None else None
+    k3 = {} if keep is not None else None
+    _, out1 = cva_forward(pk.cva[0], cost0, res_post=cost0, keep=k1)
+    logits2, out2 = cva_forward(pk.cva[1], out1, keep=k2)
+    _, out3 = cva_forward(pk.cva[2], out2, keep=k3)
+    h = conv(out3, pk.cls3_0, K3S1, ACT_RELU)
+    logits = conv_cout1(h, pk.cls3_2)
+    pred_q = softmax_regress(logits)
+    gp = Planes.from_ncdhw(_f32c(g), planes=P)
+    m1 = conv(gp, pk.prop0, C2D3, ACT_RELU)
+    mask = conv(m1, pk.prop2, C2D3, ACT_NONE, out_fp32=True)
+    pred4 = convex_upsample(mask, pred_q)
+    if keep is not None:
+        keep.update(volume=vol, dres0=c, cost0=cost0, out1=out1, cva1=k1, cva2=k2, cva3=k3,
+                    classif3_logits=logits, pred_quarter=pred_q, mask=mask)
+    return pred4, logits2

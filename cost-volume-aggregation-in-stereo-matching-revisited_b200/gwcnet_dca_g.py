@@ -1,0 +1,164 @@
+"""GwcNet (DCANet, 3 cva stages) mirror of the reference's models/gwcnet_dca_g.py: same ctor, same
+forward signature, same 726-key state_dict layout, so reference checkpoints load unchanged.
+The hot path (feature maps -> disparity) runs entirely in the sm_100a kernels; the 2-D front end
+(feature_extraction, Guidance) is ordinary torch (out of scope)."""
+import torch
+import torch.nn as nn
+
+from . import engine
+from .cva import cva
+from .submodule import BasicBlock, Guidance, PropgationNet_4x, convbn, convbn_3d
+
+
+class feature_extraction(nn.Module):
+    def __init__(self, concat_feature=False, concat_feature_channel=12):
+        super().__init__()
+        self.concat_feature = concat_feature
+        self.inplanes = 32
+        self.firstconv = nn.Sequential(convbn(3, 32, 3, 2, 1, 1), nn.ReLU(inplace=True),
+                                       convbn(32, 32, 3, 1, 1, 1), nn.ReLU(inplace=True),
+                                       convbn(32, 32, 3, 1, 1, 1), nn.ReLU(inplace=True))
+        self.layer1 = self._make_layer(BasicBlock, 32, 3, 1, 1, 1)
+        self.layer2 = self._make_layer(BasicBlock, 64, 16, 2, 1, 1)
+        self.layer3 = self._make_layer(BasicBlock, 128, 3, 1, 1, 1)
+        self.layer4 = self._make_layer(BasicBlock, 128, 3, 1, 1, 2)
+        if self.concat_feature:
+            self.lastconv = nn.Sequential(convbn(320, 128, 3, 1, 1, 1), nn.ReLU(inplace=True),
+                                          nn.Conv2d(128, concat_feature_channel, kernel_size=1, padding=0, stride=1,
+                                                    bias=False))
+
+    def _make_layer(self, block, planes, blocks, stride, pad, dilation):
+        downsample = None
+        if stride != 1 or self.inplanes != planes * block.expansion:
+            downsample = nn.Sequential(nn.Conv2d(self.inplanes, planes * block.expansion, kernel_size=1,
+                                                 stride=stride, bias=False),
+                                       nn.BatchNorm2d(planes * block.expansion))
+        layers = [block(self.inplanes, planes, stride, downsample, pad, dilation)]
+        self.inplanes = planes * block.expansion
+        layers += [block(self.inplanes, planes, 1, None, pad, dilation) for _ in range(1, blocks)]
+        return nn.Sequential(*layers)
+
+    def forward(self, x):
+        x = self.layer1(self.firstconv(x))
+        l2 = self.layer2(x)
+        l3 = self.layer3(l2)
+        l4 = self.layer4(l3)
+        gwc_feature = torch.cat((l2, l3, l4), dim=1)
+        if not self.concat_feature:
+            return {"gwc_feature": gwc_feature}
+        return {"gwc_feature": gwc_feature, "concat_feature": self.lastconv(gwc_feature)}
+
+
+class hourglass(nn.Module):
+    """Full GwcNet hourglass (reference gwcnet_dca_g.py:69-106): defined but never instantiated by
+    GwcNet, so it adds no state_dict keys.  Runs on the same conv kernels."""
+
+    def __init__(self, in_channels):
+        super().__init__()
+        c = in_channels
+        self.conv1 = nn.Sequential(convbn_3d(c, c * 2, 3, 2, 1), nn.ReLU(inplace=True))
+        self.conv2 = nn.Sequential(convbn_3d(c * 2, c * 2, 3, 1, 1), nn.ReLU(inplace=True))
+        self.conv3 = nn.Sequential(convbn_3d(c * 2, c * 4, 3, 2, 1), nn.ReLU(inplace=True))
+        self.conv4 = nn.Sequential(convbn_3d(c * 4, c * 4, 3, 1, 1), nn.ReLU(inplace=True))
+        self.conv5 = nn.Sequential(nn.ConvTranspose3d(c * 4, c * 2, 3, padding=1, output_padding=1, stride=2,
+                                                      bias=False), nn.BatchNorm3d(c * 2))
+        self.conv6 = nn.Sequential(nn.ConvTranspose3d(c * 2, c, 3, padding=1, output_padding=1, stride=2,
+                                                      bias=False), nn.BatchNorm3d(c))
+        self.redir1 = convbn_3d(c, c, kernel_size=1, stride=1, pad=0)
+        self.redir2 = convbn_3d(c * 2, c * 2, kernel_size=1, stride=1, pad=0)
+        self.precision_planes = 2
+
+    def forward(self, x):
+        E = engine
+        xp = E.Planes.from_ncdhw(x, self.precision_planes)
+        c1 = E.conv(xp, E.pack_convbn(self.conv1[0]), E.K3S2, E.ACT_RELU)
+        c2 = E.conv(c1, E.pack_convbn(self.conv2[0]), E.K3S1, E.ACT_RELU)
+        c3 = E.conv(c2, E.pack_convbn(self.conv3[0]), E.K3S2, E.ACT_RELU)
+        c4 = E.conv(c3, E.pack_convbn(self.conv4[0]), E.K3S1, E.ACT_RELU)
+        r2 = E.conv(c2, E.pack_convbn(self.redir2), E.K1, E.ACT_NONE)
+        c5 = E.conv(c4, E.PackedConv(self.conv5[0].weight, self.conv5[1], True), E.T3S2, E.ACT_RELU, res_pre=r2)
+        r1 = E.conv(xp, E.pack_convbn(self.redir1), E.K1, E.ACT_NONE)
+        c6 = E.conv(c5, E.PackedConv(self.conv6[0].weight, self.conv6[1], True), E.T3S2, E.ACT_RELU, res_pre=r1)
+        return c6.to_ncdhw()
+
+
+class GwcNet(nn.Module):
+    """precision: "parity" (hi+lo bf16 planes, meets |d disp| <= 0.05 px) or "fast" (single bf16)."""
+
+    def __init__(self, maxdisp, use_concat_volume=True, precision="parity"):
+        super().__init__()
+        assert maxdisp % 8 == 0, "maxdisp must be a multiple of 8 (1/4 volume, 1/8 DCA stage)"
+        self.maxdisp = maxdisp
+        self.use_concat_volume = use_concat_volume
+        self.num_groups = 40
+        if self.use_concat_volume:
+            self.concat_channels = 12
+            self.feature_extraction = feature_extraction(concat_feature=True,
+                                                         concat_feature_channel=self.concat_channels)
+        else:
+            self.concat_channels = 0
+            self.feature_extraction = feature_extraction(concat_feature=False)
+        self.dres0 = nn.Sequential(convbn_3d(self.num_groups + self.concat_channels * 2, 32, 3, 1, 1),
+                                   nn.ReLU(inplace=True), convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True))
+        self.dres1 = nn.Sequential(convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True), convbn_3d(32, 32, 3, 1, 1))
+        self.cva1 = cva(self.maxdisp, 32, downsample=True)
+        self.cva2 = cva(self.maxdisp, 32, downsample=True)
+        self.cva3 = cva(self.maxdisp, 32, downsample=True)
+        for i in range(4):   # classif0..2 are training-only heads; kept for the state_dict layout
+            setattr(self, f"classif{i}", nn.Sequential(
+                convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True),
+                nn.Conv3d(32, 1, kernel_size=3, padding=1, stride=1, bias=False)))
+        self.guidance = Guidance(64)
+        self.prop = PropgationNet_4x(64)
+        self.set_precision(precision)
+        self._packed = None
+
+    # ---- precision / packing -------------------------------------------------------------
+    def set_precision(self, precision):
+        assert precision in ("parity", "fast")
+        self.precision = precision
+        self._planes = 2 if precision == "parity" else 1
+        for m in self.modules():
+            if hasattr(m, "precision_planes"):
+                m.precision_planes = self._planes
+        self._packed = None
+
+    def invalidate(self):
+        """Drop the packed kernel parameters (call after mutating weights in place)."""
+        self._packed = None
+
+    def _apply(self, fn, *a, **kw):        # .cuda() / .to() / .float() move the weights -> repack
+        self._packed = None
+        return super()._apply(fn, *a, **kw)
+
+    def packed(self):
+        """Pack (once per load) every hot-path parameter for the kernels: BN folded to fp32 scale/shift,
+        conv weights to [tap][Cin][Cout] (+ the bf16 operand packs of the tcgen05 kernels)."""
+        if self._packed is None or self._packed.planes != self._planes:
+            self._packed = engine.PackedHotPath(self, self._planes)
+        return self._packed
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """Accepts reference checkpoints as saved from nn.DataParallel (`module.` prefix, main_dca.py:277-281)
+        and the {'state_dict': ...} wrapper."""
+        if "state_dict" in state_dict and not any(k.startswith(("dres0", "module.dres0")) for k in state_dict):
+            state_dict = state_dict["state_dict"]
+        if any(k.startswith("module.") for k in state_dict):
+            state_dict = {(k[7:] if k.startswith("module.") else k): v for k, v in state_dict.items()}
+        self._packed = None
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    # ---- forward -------------------------------------------------------------------------
+    def hot_path(self, gwc_l, gwc_r, cat_l, cat_r, g, keep=None):
+        """feature maps -> (pred4 [B,1,H,W], prob_volume2 [B,D8,H8,W8]); the graded path."""
+        return engine.hot_path_forward(self.packed(), gwc_l, gwc_r, cat_l, cat_r, g, keep)
+
+    def forward(self, left, right, disp_true=None):
+        if self.training:
+            raise NotImplementedError("dcanet_b200 is an inference engine: call .eval() (training-mode heads "
+                                      "classif0-2 exist only so checkpoints load)")
+        fl = self.feature_extraction(left)
+        fr = self.feature_extraction(right)
+        g = self.guidance(left)["g"]
+        return self.hot_path(fl["gwc_feature"], fr["gwc_feature"], fl.get("concat_feature"),
+                             fr.get("concat_feature"), g)

@@ -1,0 +1,99 @@
+/* dca_b200.h -- C ABI of the B200 (sm_100a) DCANet cost-volume hot path.
+ *
+ * Drop-in boundary for everything between the 1/4-resolution feature maps and the final disparity
+ * of the reference model (cocowy1/Cost-Volume-Aggregation-in-Stereo-Matching-Revisited,
+ * models/gwcnet_dca_g.py:216-240).  The reference has no native code on this path (pure PyTorch
+ * eager); its own precedent for this shape of boundary is models/libs/GANet/src/GANet_cuda.cpp:5-64
+ * (`extern "C" int f(...)`).  Every entry point here
+ *   - takes raw DEVICE pointers, sizes and a cudaStream_t (passed as void*),
+ *   - never allocates, never synchronises, never throws,
+ *   - returns DCA_OK (0) or a negative error code.
+ * The caller (Python via ctypes) owns all buffers.
+ *
+ * "cost planes" = channels-last bf16 tensor [planes][B][D][H][W][C]; plane 0 = bf16(x),
+ * plane 1 = bf16(x - plane0) (only when planes == 2, the parity precision mode).
+ */
+#ifndef DCA_B200_H
+#define DCA_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCA_OK 0
+#define DCA_ERR_ARG (-1)         /* bad pointer / shape */
+#define DCA_ERR_LAUNCH (-2)      /* CUDA launch failed */
+#define DCA_ERR_UNSUPPORTED (-3) /* shape outside what the kernels were built for */
+
+#define DCA_ACT_NONE 0
+#define DCA_ACT_RELU 1
+#define DCA_ACT_LEAKY 2 /* LeakyReLU(0.1) */
+
+#define DCA_CONV_K3S1 0  /* Conv3d k3 s1 p1          (submodule.py:121-124) */
+#define DCA_CONV_K3S2 1  /* Conv3d k3 s2 p1          (cva.py:16)            */
+#define DCA_CONV_T3S2 2  /* ConvTranspose3d k3 s2 p1 op1 (cva.py:20-22)     */
+#define DCA_CONV_K1 3    /* Conv3d 1x1x1             (cva.py:24,55)         */
+#define DCA_CONV_2D3 4   /* Conv2d 3x3 s1 p1, Di==1  (gwcnet_dca_g.py:112-115) */
+
+int dca_version(void);
+
+/* (1) volume construction -------------------------------------------------------------------- */
+/* Fused replacement of build_gwc_volume (submodule.py:157-167) + build_concat_volume (:134-145)
+ * + torch.cat (gwcnet_dca_g.py:220).  gwc_* [B,C,H,W] fp32, cat_* [B,Cc,H,W] fp32 (NCHW, as the
+ * extractor emits them); vol = cost planes [planes][B][D][H][W][Cv], channels = G groups, Cc left,
+ * Cc right, zero pad up to Cv (multiple of 8, <= 64). */
+int dca_volume_gwc_concat(const float* gwc_l, const float* gwc_r, const float* cat_l, const float* cat_r, void* vol,
+                          int B, int C, int G, int Cc, int D, int H, int W, int Cv, int planes, void* stream);
+/* Reference-API forms: fp32 NCDHW outputs [B,G,D,H,W] / [B,2C,D,H,W]. */
+int dca_build_gwc_volume_f32(const float* l, const float* r, float* vol, int B, int C, int G, int D, int H, int W,
+                             void* stream);
+int dca_build_concat_volume_f32(const float* l, const float* r, float* vol, int B, int C, int D, int H, int W,
+                                void* stream);
+
+/* (3) convolution family ----------------------------------------------------------------------- */
+/* y = act(scale * conv(x, w) + shift + res_pre) + res_post.   CUDA-core fp32 kernel, any mode.
+ * w_packed fp32 [taps][Cin][CoutPad] (dca_pack_weights); scale/shift [CoutPad] or NULL;
+ * res_* cost planes shaped like y or NULL; out_kind 0 = cost planes, 1 = fp32 channels-last. */
+int dca_conv3d_direct(int mode, const void* x, int planes_in, const float* w_packed, const float* scale,
+                      const float* shift, const void* res_pre, const void* res_post, int planes_res, void* y,
+                      int planes_out, int out_kind, int act, int B, int Cin, int Cout, int CoutPad, int Di, int Hi,
+                      int Wi, int Do, int Ho, int Wo, void* stream);
+/* Conv3d k3 s1 p1, Cin=32 -> 1 channel, no BN: fp32 logits [B,D,H,W] (cva.py:53, gwcnet_dca_g.py:168).
+ * w fp32 [27][Cin]. */
+int dca_conv3d_cout1(const void* x, int planes_in, const float* w, float* y, int B, int Cin, int D, int H, int W,
+                     void* stream);
+/* tcgen05/TMEM implicit-GEMM member of the family (conv_tc.cu): Conv3d k3 s1 p1 + BN + act (+ residuals).
+ * w_tc = bf16 operand pack from dca_pack_weights_tc.  Same epilogue contract as dca_conv3d_direct. */
+int dca_conv3d_tc(int mode, const void* x, int planes_in, const void* w_tc, const float* scale, const float* shift,
+                  const void* res_pre, const void* res_post, int planes_res, void* y, int planes_out, int act, int B,
+                  int Cin, int Cout, int Di, int Hi, int Wi, int Do, int Ho, int Wo, void* stream);
+int dca_pack_weights_tc(const float* w, int transposed, int Co, int Ci, int taps, void* out, int planes, void* stream);
+long long dca_pack_weights_tc_bytes(int Co, int Ci, int taps, int planes);
+
+/* (2) DCA module ------------------------------------------------------------------------------- */
+int dca_avgpool3d(const void* x, void* y, int planes, int B, int C, int Di, int Hi, int Wi, void* stream);
+/* logits fp32 [B,D,H,W] -> class map int32 [B,H,W], e = exp(P[k_p]) [B,H,W], S [B,D] (zeroed here). */
+int dca_class_stats(const float* logits, int* cls, float* e, float* S, int B, int D, int H, int W, void* stream);
+/* weights: 7 x [32][32] transposed (q0,q1,k0,k1,v,o,Wa) then 6 x (scale[32],shift[32]). */
+int dca_disp_attention(const void* x, const int* cls, const float* e, const float* S, const float* weights,
+                       int has_wa, void* y, int planes, int B, int C, int D, int H, int W, void* stream);
+/* y = scale * (trilinear_x2(t) + WcT^T cost) + shift ; t at (Dl,Hl,Wl), cost / y at twice that. */
+int dca_upsample_fuse(const void* t, const void* cost, const float* WcT, const float* scale, const float* shift,
+                      void* y, int planes, int B, int C, int Dl, int Hl, int Wl, void* stream);
+
+/* (4) regression + convex upsampling ------------------------------------------------------------ */
+int dca_softmax_regress(const float* logits, float* pred, int B, int D, int H, int W, void* stream);
+int dca_convex_upsample(const float* mask, const float* disp, float* out, int B, int H, int W, void* stream);
+
+/* layout + parameter preparation ---------------------------------------------------------------- */
+int dca_planes_from_ncdhw(const float* x, void* y, int planes, int B, int C, int Cp, int D, int H, int W,
+                          void* stream);
+int dca_planes_to_ncdhw(const void* x, int planes, float* y, int B, int C, int Cp, int D, int H, int W, void* stream);
+int dca_pack_weights(const float* w, int transposed, int Co, int Ci, int taps, float* out, int CoPad, void* stream);
+int dca_fold_bn(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale,
+                float* shift, int C, int Cpad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCA_B200_H */

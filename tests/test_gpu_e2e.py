@@ -1,0 +1,93 @@
+"""GPU parity of the whole hot path: reference golden vectors (64x128) and the live oracle at config 1
+(256x512, maxdisp 192).  Tolerance from BASELINE.json north_star: per-pixel |d disp| <= 0.05 px,
+mean |d disp| <= 0.01 px, DCA class maps identical (parity precision mode)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL_MAX, TOL_MEAN = 0.05, 0.01
+
+
+def _load_into(model, sd):
+    own = model.state_dict()
+    own.update({k: v for k, v in sd.items()})
+    model.load_state_dict(own)
+    return model
+
+
+def test_hot_path_matches_reference_golden():
+    import dcanet_b200 as d
+    from _util import load_e2e
+    z, sd, maxdisp = load_e2e()
+    net = _load_into(d.GwcNet(maxdisp), sd).cuda().eval()
+    keep = {}
+    cu = lambda k: torch.from_numpy(z[k]).cuda()
+    with torch.no_grad():
+        pred4, pv2 = net.hot_path(cu("gwc_l"), cu("gwc_r"), cu("cat_l"), cu("cat_r"), cu("g"), keep=keep)
+    for s in (1, 2, 3):
+        got = keep[f"cva{s}"]["class_map"].cpu().numpy()
+        assert np.array_equal(got, z[f"cva{s}.class_map"]), f"cva{s} class map differs"
+    dd = (pred4.cpu() - torch.from_numpy(z["pred4"])).abs()
+    assert float(dd.max()) <= TOL_MAX and float(dd.mean()) <= TOL_MEAN, (float(dd.max()), float(dd.mean()))
+    e = (pv2.cpu() - torch.from_numpy(z["prob_volume2"])).abs().max()
+    assert float(e) < 1e-2 * float(np.abs(z["prob_volume2"]).max())
+
+
+def _config1(H4=64, W4=128, maxdisp=192, seed=0):
+    from oracle import dcanet_oracle as O
+    feats = O.synth_features(seed, 1, H4, W4, shift=3)
+    sd = O.calibrate_state_dict(O.synth_state_dict(seed), feats, maxdisp)
+    return O, feats, sd
+
+
+def test_hot_path_config1_matches_oracle():
+    """config 1: one 256x512 pair, maxdisp 192, groups 40 -- oracle run live on the host CPU."""
+    import dcanet_b200 as d
+    O, feats, sd = _config1()
+    col = {}
+    with torch.no_grad():
+        ref4, refpv = O.hot_path(sd, *feats, maxdisp=192, collect=col)
+    net = _load_into(d.GwcNet(192), sd).cuda().eval()
+    keep = {}
+    with torch.no_grad():
+        pred4, pv2 = net.hot_path(*[f.cuda() for f in feats], keep=keep)
+    for s in (1, 2, 3):
+        assert torch.equal(keep[f"cva{s}"]["class_map"].cpu().long(), col[f"cva{s}.class_map"]), f"cva{s} mask"
+    dd = (pred4.cpu() - ref4).abs()
+    print("config1 parity: max %.4f mean %.5f px" % (float(dd.max()), float(dd.mean())))
+    assert float(dd.max()) <= TOL_MAX and float(dd.mean()) <= TOL_MEAN
+    assert float((pv2.cpu() - refpv).abs().max()) < 1e-2 * float(refpv.abs().max())
+
+
+def test_fast_mode_tracks_bf16_emulated_oracle():
+    """precision="fast" (single bf16 operands) is judged against the oracle run with bf16-rounded conv
+    operands (SURVEY 7 hard part 2): same rounding points, so only summation order differs."""
+    import dcanet_b200 as d
+    O, feats, sd = _config1(H4=32, W4=64, maxdisp=96, seed=1)
+    with torch.no_grad():
+        ref4, _ = O.hot_path(sd, *feats, maxdisp=96, operand_bits=7)
+        full4, _ = O.hot_path(sd, *feats, maxdisp=96)
+    net = _load_into(d.GwcNet(96, precision="fast"), sd).cuda().eval()
+    with torch.no_grad():
+        pred4, _ = net.hot_path(*[f.cuda() for f in feats])
+    d_emul = float((pred4.cpu() - ref4).abs().mean())
+    d_full = float((ref4 - full4).abs().mean())
+    print("fast mode: mean |d| vs bf16-emulated oracle %.4f px; bf16 emulation vs fp32 %.4f px" % (d_emul, d_full))
+    assert d_emul < max(0.25, 1.5 * d_full)
+
+
+def test_module_forward_from_images_runs():
+    """Drop-in call: GwcNet(maxdisp)(left, right) with the reference's 2-argument callers (my_img.py:101)."""
+    import dcanet_b200 as d
+    torch.manual_seed(0)
+    import workloads
+    net = workloads.init_bench_weights_(d.GwcNet(48), 0).cuda().eval()
+    left = torch.randn(1, 3, 64, 128, device="cuda")
+    with torch.no_grad():
+        pred4, pv2 = net(left, torch.roll(left, -4, 3))
+    assert pred4.shape == (1, 1, 64, 128) and pv2.shape == (1, 6, 8, 16)
+    assert torch.isfinite(pred4).all()

@@ -1,0 +1,211 @@
+"""GPU parity of every kernel against the CPU oracle (through the C ABI via the Python host layer)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _mods():
+    import dcanet_b200 as d
+    from oracle import dcanet_oracle as O
+    return d, d.engine, O
+
+
+def close(got, ref, rel=2e-4, what=""):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    err = float((got - ref).abs().max())
+    scale = float(ref.abs().max()) + 1e-12
+    assert err <= rel * scale + 1e-7, f"{what}: max err {err:.3e} vs scale {scale:.3e}"
+
+
+def rnd(*shape, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g)
+
+
+@pytest.mark.parametrize("B,C,G,Cc,H,W,D,planes", [
+    (2, 320, 40, 12, 3, 37, 12, 2), (1, 320, 40, 12, 2, 64, 48, 2), (1, 320, 40, 12, 2, 50, 60, 1),
+    (1, 320, 8, 12, 2, 33, 24, 2), (1, 320, 20, 12, 2, 20, 7, 2), (1, 64, 8, 0, 2, 16, 4, 2)])
+def test_fused_volume(B, C, G, Cc, H, W, D, planes):
+    d, E, O = _mods()
+    L, R = rnd(B, C, H, W, seed=1), rnd(B, C, H, W, seed=2)
+    cl = rnd(B, Cc, H, W, seed=3) if Cc else None
+    cr = rnd(B, Cc, H, W, seed=4) if Cc else None
+    ref = O.build_gwc_volume(L, R, D, G)
+    if Cc:
+        ref = torch.cat([ref, O.build_concat_volume(cl, cr, D)], 1)
+    vol = E.fused_volume(L.cuda(), R.cuda(), cl.cuda() if Cc else None, cr.cuda() if Cc else None, D, G, planes)
+    got = vol.to_ncdhw()
+    assert vol.C % 8 == 0 and vol.C >= G + 2 * Cc
+    close(got[:, :G + 2 * Cc], ref, 2e-5 if planes == 2 else 5e-3, "volume")
+    if vol.C > G + 2 * Cc:
+        assert float(got[:, G + 2 * Cc:].abs().max()) == 0.0
+
+
+def test_volume_api_matches_reference_golden():
+    d, E, O = _mods()
+    z = np.load(os.path.join(GOLD, "ops_small.npz"))
+    for tag in "abc":
+        L, R = torch.from_numpy(z[f"gwc_{tag}_L"]), torch.from_numpy(z[f"gwc_{tag}_R"])
+        D, G = [int(v) for v in z[f"gwc_{tag}_meta"]]
+        close(d.build_gwc_volume(L.cuda(), R.cuda(), D, G), torch.from_numpy(z[f"gwc_{tag}_out"]), 1e-6, "gwc")
+        got = d.build_concat_volume(L[:, :12].cuda(), R[:, :12].cuda(), D)
+        assert torch.equal(got.cpu(), torch.from_numpy(z[f"cat_{tag}_out"]))
+    x = torch.from_numpy(z["regress_in"])
+    close(d.softmax_disparity_regression(x.cuda(), 12), torch.from_numpy(z["regress_out"]), 1e-5, "regress")
+    close(d.disparity_regression(torch.softmax(x, 1).cuda(), 12), torch.from_numpy(z["regress_out"]), 1e-4, "regress-p")
+
+
+def _bn(c, seed):
+    bn = torch.nn.BatchNorm3d(c)
+    g = torch.Generator().manual_seed(seed)
+    bn.weight.data = torch.rand(c, generator=g) * 0.5 + 0.75
+    bn.bias.data = torch.randn(c, generator=g) * 0.1
+    bn.running_mean = torch.randn(c, generator=g) * 0.1
+    bn.running_var = torch.rand(c, generator=g) * 0.5 + 0.5
+    return bn.eval()
+
+
+@pytest.mark.parametrize("mode,ci,co,shape", [
+    ("k3s1", 32, 32, (2, 6, 9, 37)), ("k3s1", 64, 32, (1, 4, 6, 34)), ("k3s1", 64, 64, (1, 3, 5, 33)),
+    ("k3s2", 32, 64, (1, 6, 10, 38)), ("k3s2", 32, 64, (1, 5, 7, 35)), ("t3s2", 64, 32, (1, 3, 5, 19)),
+    ("k1", 32, 32, (1, 4, 6, 40)), ("k1", 64, 32, (1, 2, 5, 33))])
+@pytest.mark.parametrize("planes", [2, 1])
+def test_conv_family_direct(mode, ci, co, shape, planes):
+    d, E, O = _mods()
+    E.Options.use_tc = False
+    B, D, H, W = shape
+    x = rnd(B, ci, D, H, W, seed=5)
+    bn = _bn(co, 6)
+    if mode == "t3s2":
+        conv = torch.nn.ConvTranspose3d(ci, co, 3, stride=2, padding=1, output_padding=1, bias=False)
+    else:
+        k, s = (1, 1) if mode == "k1" else (3, 1 if mode == "k3s1" else 2)
+        conv = torch.nn.Conv3d(ci, co, k, stride=s, padding=k // 2, bias=False)
+    xin = x
+    if planes == 1:   # compare like with like: fast mode sees bf16-rounded activations
+        xin = x.to(torch.bfloat16).float()
+    with torch.no_grad():
+        ref0 = bn(conv(xin))
+    res1, res2 = rnd(*ref0.shape, seed=7), rnd(*ref0.shape, seed=8)
+    if planes == 1:
+        res1, res2 = res1.to(torch.bfloat16).float(), res2.to(torch.bfloat16).float()
+    ref = F.relu(ref0 + res1) + res2
+    emode = {"k3s1": E.K3S1, "k3s2": E.K3S2, "t3s2": E.T3S2, "k1": E.K1}[mode]
+    pc = E.PackedConv(conv.weight.cuda(), bn.cuda(), transposed=(mode == "t3s2"))
+    y = E.conv(E.Planes.from_ncdhw(x.cuda(), planes), pc, emode, E.ACT_RELU,
+               res_pre=E.Planes.from_ncdhw(res1.cuda(), planes), res_post=E.Planes.from_ncdhw(res2.cuda(), planes))
+    close(y.to_ncdhw(), ref, 1e-4 if planes == 2 else 1e-2, f"conv {mode}")
+    E.Options.use_tc = True
+
+
+def test_conv_cout1_and_2d():
+    d, E, O = _mods()
+    x = rnd(2, 32, 5, 7, 37, seed=9)
+    conv = torch.nn.Conv3d(32, 1, 3, padding=1, bias=False)
+    with torch.no_grad():
+        ref = conv(x).squeeze(1)
+    got = E.conv_cout1(E.Planes.from_ncdhw(x.cuda(), 2), E.pack_cout1(conv.weight.cuda()))
+    close(got, ref, 3e-5, "cout1")
+    # 2-D 3x3 convs of the propagation net, fp32 channels-last output with 144 channels
+    g = rnd(1, 64, 9, 35, seed=10)
+    c1 = torch.nn.Conv2d(64, 128, 3, padding=1, bias=False)
+    c2 = torch.nn.Conv2d(128, 144, 3, padding=1, bias=False)
+    bn = torch.nn.BatchNorm2d(128).eval()
+    bn.running_mean.normal_(0, 0.1, generator=torch.Generator().manual_seed(3)); bn.running_var.uniform_(0.5, 1.0)
+    with torch.no_grad():
+        ref = c2(F.relu(bn(c1(g))))
+    gp = E.Planes.from_ncdhw(g.cuda(), 2)
+    m1 = E.conv(gp, E.pack_convbn(torch.nn.Sequential(c1, bn).cuda()), E.C2D3, E.ACT_RELU)
+    mask = E.conv(m1, E.PackedConv(c2.weight.cuda()), E.C2D3, E.ACT_NONE, out_fp32=True)
+    close(mask[:, 0].permute(0, 3, 1, 2), ref, 5e-5, "prop convs")
+
+
+def test_avgpool_and_planes_roundtrip():
+    d, E, O = _mods()
+    x = rnd(2, 32, 6, 9, 21, seed=11)
+    xp = E.Planes.from_ncdhw(x.cuda(), 2)
+    close(xp.to_ncdhw(), x, 2e-5, "roundtrip")
+    close(E.avgpool(xp).to_ncdhw(), F.avg_pool3d(x, 3, 2, 1), 3e-5, "avgpool")
+    close(E.Planes.from_ncdhw(x.cuda(), 1).to_ncdhw(), x.to(torch.bfloat16).float(), 1e-7, "bf16 roundtrip")
+
+
+def test_class_stats_exact_mask():
+    d, E, O = _mods()
+    logits = rnd(3, 24, 13, 29, seed=12) * 2.0
+    logits[0, 5, 2, 3] = logits[0, 9, 2, 3] = 50.0       # exact tie -> first index wins
+    P, k, e, S, w = O.class_stats(logits)
+    cls, ee, SS = E.class_stats(logits.cuda())
+    assert torch.equal(cls.cpu().long(), k)
+    assert int(cls[0, 2, 3]) == 5
+    close(ee, e, 1e-6, "e")
+    close(SS, S, 1e-5, "S")
+
+
+def _attn_modules(seed):
+    d, E, O = _mods()
+    torch.manual_seed(seed)
+    m = d.cva(192, 32)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm3d):
+            mod.weight.data.uniform_(0.75, 1.25); mod.bias.data.normal_(0, 0.1)
+            mod.running_mean.normal_(0, 0.1); mod.running_var.uniform_(0.5, 1.5)
+        if isinstance(mod, (torch.nn.Conv3d, torch.nn.ConvTranspose3d)):
+            mod.weight.data.normal_(0, (2.0 / (mod.weight[0].numel())) ** 0.5)
+    return m.eval()
+
+
+@pytest.mark.parametrize("D", [24, 6, 30])
+def test_semantic_level_attention(D):
+    d, E, O = _mods()
+    m = _attn_modules(1)
+    x = rnd(2, 32, D, 5, 11, seed=13)
+    logits = rnd(2, D, 5, 11, seed=14) * 3
+    sd = {"cva." + k: v for k, v in m.state_dict().items()}
+    ctx = O._Ctx(sd)
+    key, kmap = O.semantic_level_key(x, logits)
+    ref = O.disparity_attention(ctx, "cva.slc_net.cross_attention", x, key)
+    m = m.cuda()
+    got = m.slc_net(x.cuda(), logits.cuda())
+    assert torch.equal(m.slc_net.last_class_map.cpu().long(), kmap)
+    close(got, ref, 1e-4, "attention")
+
+
+def test_cva_block_matches_oracle():
+    d, E, O = _mods()
+    m = _attn_modules(2)
+    cost = rnd(1, 32, 12, 10, 22, seed=15)
+    sd = {"cva." + k: v for k, v in m.state_dict().items()}
+    col = {}
+    with torch.no_grad():
+        ref_logits, ref_out = O.cva_forward(O._Ctx(sd), "cva", cost, col)
+    m = m.cuda()
+    logits, out = m(cost.cuda())
+    close(logits, ref_logits, 1e-4, "cva logits")
+    close(m.last["cost_down"].to_ncdhw(), col["cva.cost_down"], 1e-4, "cost_down")
+    close(m.last["fused"].to_ncdhw(), col["cva.fused"], 1e-4, "fused")
+    close(out, ref_out, 2e-4, "cva out")
+    assert torch.equal(m.last["class_map"].cpu().long(), col["cva.class_map"])
+
+
+def test_convex_upsample_and_regression():
+    d, E, O = _mods()
+    mask = rnd(2, 144, 7, 13, seed=16)
+    disp = rnd(2, 1, 7, 13, seed=17).abs() * 10
+    m = F.softmax(mask.view(2, 9, 4, 4, 7, 13), dim=1)
+    dp = F.pad(4.0 * disp[:, 0], (1, 1, 1, 1))
+    ref = torch.zeros(2, 4, 4, 7, 13)
+    for n in range(9):
+        ref = ref + m[:, n] * dp[:, None, None, n // 3:n // 3 + 7, n % 3:n % 3 + 13]
+    ref = ref.permute(0, 3, 1, 4, 2).reshape(2, 1, 28, 52)
+    got = E.convex_upsample(mask.permute(0, 2, 3, 1).contiguous().cuda(), disp.cuda())
+    close(got, ref, 1e-5, "convex")
+    logits = rnd(2, 48, 6, 17, seed=18) * 4
+    close(E.softmax_regress(logits.cuda()), O.disparity_regression(F.softmax(logits, 1), 48), 1e-5, "regress")
