@@ -225,7 +225,7 @@ extern "C" int dca_volume_gwc_concat(const float* gwc_l, const float* gwc_r, con
   if (Cv < G + 2 * Cc || Cv > 64 || (Cv % 8) != 0 || (planes != 1 && planes != 2)) return DCA_ERR_ARG;
   const int cpg = C / G, gp = G + 1, UW = VOL_TW + VOL_DC - 1;
   size_t smem = ((size_t)cpg * (VOL_TW + UW) * gp + (size_t)Cc * (VOL_TW + UW)) * sizeof(float);
-  if (smem > 113 * 1024) return DCA_ERR_UNSUPPORTED;
+  if (smem > 220 * 1024) return DCA_ERR_UNSUPPORTED;
   const int wtiles = (W + VOL_TW - 1) / VOL_TW, dchunks = (D + VOL_DC - 1) / VOL_DC;
   dim3 grid(wtiles * dchunks, H, B);
   cudaStream_t st = (cudaStream_t)stream;
