@@ -117,7 +117,8 @@ def pack_convbn(seq, transposed=False):
 # operators on planes
 # --------------------------------------------------------------------------------------------
 class Options:
-    use_tc = True      # route eligible convs to the tcgen05 kernels
+    use_tc = True                 # route eligible convs to the tcgen05 kernels
+    tc_modes = {0, 1, 2, 3}       # conv modes the tcgen05 kernel takes (K3S1, K3S2, T3S2, K1)
 
 
 def conv(x: Planes, pc: PackedConv, mode=K3S1, act=ACT_NONE, res_pre: Planes = None, res_post: Planes = None,
@@ -157,7 +158,7 @@ def conv(x: Planes, pc: PackedConv, mode=K3S1, act=ACT_NONE, res_pre: Planes = N
 
 
 def tc_supported(mode, cin, cout):
-    return False
+    return mode in Options.tc_modes and cin in (32, 64) and cout in (32, 64)
 
 
 def conv_cout1(x: Planes, w27: torch.Tensor):
@@ -276,7 +277,7 @@ class PackedCva:
         self.conv2 = pack_convbn(agg.conv2[0])
         self.conv3 = PackedConv(agg.conv3[0].weight, agg.conv3[1], transposed=True)
         self.redir = pack_convbn(agg.redir)
-        for pc in (self.down, self.cls0, self.conv1, self.conv2):
+        for pc in (self.down, self.cls0, self.conv1, self.conv2, self.redir):
             pc.pack_tc(planes)
         self.conv3.pack_tc(planes, transposed=True)
 

@@ -106,6 +106,49 @@ def test_conv_family_direct(mode, ci, co, shape, planes):
     E.Options.use_tc = True
 
 
+@pytest.mark.parametrize("mode,ci,co,shape", [
+    ("k3s1", 32, 32, (2, 6, 16, 8)), ("k3s1", 32, 32, (1, 5, 19, 37)), ("k3s1", 64, 32, (1, 4, 18, 34)),
+    ("k3s1", 64, 64, (1, 3, 17, 33)), ("k1", 32, 32, (1, 4, 6, 40)),
+    ("k3s2", 32, 64, (1, 6, 10, 38)), ("k3s2", 32, 64, (1, 5, 7, 35)), ("t3s2", 64, 32, (1, 3, 5, 19))])
+@pytest.mark.parametrize("planes", [2, 1])
+def test_conv_family_tcgen05(mode, ci, co, shape, planes):
+    """tcgen05 implicit-GEMM kernels vs the fp32 oracle conv (and, implicitly, vs the CUDA-core kernel)."""
+    d, E, O = _mods()
+    B, D, H, W = shape
+    x = rnd(B, ci, D, H, W, seed=25)
+    bn = _bn(co, 26)
+    if mode == "t3s2":
+        conv = torch.nn.ConvTranspose3d(ci, co, 3, stride=2, padding=1, output_padding=1, bias=False)
+    else:
+        k, s = (1, 1) if mode == "k1" else (3, 1 if mode == "k3s1" else 2)
+        conv = torch.nn.Conv3d(ci, co, k, stride=s, padding=k // 2, bias=False)
+    w = conv.weight.data
+    xin = x
+    if planes == 1:   # fast mode: bf16 operands on both sides
+        xin = x.to(torch.bfloat16).float()
+        conv.weight.data = w.to(torch.bfloat16).float()
+    with torch.no_grad():
+        ref0 = bn(conv(xin))
+    conv.weight.data = w
+    res1, res2 = rnd(*ref0.shape, seed=27), rnd(*ref0.shape, seed=28)
+    if planes == 1:
+        res1, res2 = res1.to(torch.bfloat16).float(), res2.to(torch.bfloat16).float()
+    ref = F.relu(ref0 + res1) + res2
+    emode = {"k3s1": E.K3S1, "k3s2": E.K3S2, "t3s2": E.T3S2, "k1": E.K1}[mode]
+    pc = E.PackedConv(conv.weight.cuda(), bn.cuda(), transposed=(mode == "t3s2"))
+    assert pc.pack_tc(planes, transposed=(mode == "t3s2"))
+    E.Options.use_tc = True
+    saved = set(E.Options.tc_modes)
+    E.Options.tc_modes = {0, 1, 2, 3}
+    try:
+        y = E.conv(E.Planes.from_ncdhw(x.cuda(), planes), pc, emode, E.ACT_RELU,
+                   res_pre=E.Planes.from_ncdhw(res1.cuda(), planes), res_post=E.Planes.from_ncdhw(res2.cuda(), planes))
+        torch.cuda.synchronize()
+    finally:
+        E.Options.tc_modes = saved
+    close(y.to_ncdhw(), ref, 1e-4 if planes == 2 else 1e-2, f"tc conv {mode}")
+
+
 def test_conv_cout1_and_2d():
     d, E, O = _mods()
     x = rnd(2, 32, 5, 7, 37, seed=9)
