@@ -25,6 +25,8 @@ SIGNATURES = {
     "dca_conv3d_tc": [_c_int, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _c_int, _c_int] + [_c_int] * 9 + [_vp],
     "dca_pack_weights_tc": [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp],
     "dca_pack_weights_tc_bytes": [_c_int] * 4,
+    "dca_tc_set_halo": [_c_int],
+    "dca_tc_set_tuning": [_c_int, _c_int],
     "dca_avgpool3d": [_vp, _vp] + [_c_int] * 6 + [_vp],
     "dca_class_stats": [_vp, _vp, _vp, _vp] + [_c_int] * 4 + [_vp],
     "dca_disp_attention": [_vp, _vp, _vp, _vp, _vp, _c_int, _vp] + [_c_int] * 6 + [_vp],

@@ -47,6 +47,10 @@ struct TcParams {
   const float* scale; const float* shift;
   const __nv_bfloat16* res_pre; const __nv_bfloat16* res_post; size_t res_plane; int planes_res;
   __nv_bfloat16* y; size_t y_plane; int planes_out; int act;
+  int dbg;       // diagnostics: bit0 = skip epilogue stores, bit1 = skip MMAs (timing experiments only)
+  int npart;     // accumulator column blocks (each Cout wide) the epilogue sums
+  int ngrp;      // halo kernel: taps are interleaved over ngrp independent accumulator groups
+  int lo_sep;    // halo kernel, parity: lo*Whi goes to its own column block
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -102,6 +106,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -128,9 +137,91 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)((ROWB * 8) >> 4) << 32) | (1ull << 46) |
          (layout << 61);
 }
+// descriptor with the start-address field left zero: desc(addr) = desc_hi_const<ROWB>(sbo) + (addr >> 4)
+template <int ROWB>
+__host__ __device__ constexpr uint64_t desc_const(uint32_t sbo_bytes) {
+  return (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | ((ROWB == 128 ? 2ull : 4ull) << 61);
+}
 // instruction descriptor, kind::f16: D=f32 (bit4), A=B=bf16 (bits 7,10), K-major both, N>>3 @17, M>>4 @24
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ shared epilogue (warps 2..5)
+// TMEM accumulator -> registers -> (+lo half) -> BN scale/shift -> +res_pre -> act -> +res_post -> bf16 planes
+template <int COUT, int PLANES>
+__device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, uint32_t tmem_base, uint64_t* tfull,
+                                            uint64_t* tempty, const float* s_scale, const float* s_shift, int warp,
+                                            int lane) {
+    const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) are reachable from this warp
+    const int row = quarter * 32 + lane;          // tile row = voxel
+    const int hh = row / TC_TW, ww = row % TC_TW;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      int r = tile;
+      const int tw = r % p.tiles_w; r /= p.tiles_w;
+      const int th = r % p.tiles_h; r /= p.tiles_h;
+      const int td = r % p.Dt;
+      const int b = r / p.Dt;
+      const uint32_t acc = it & 1;
+      mbar_wait(&tfull[acc], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)(PLANES * COUT);
+      const int tz = td, ty = th * TC_TH + hh, tx = tw * TC_TW + ww;
+      const int oz = tz * p.out_stride + p.out_off[0], oy = ty * p.out_stride + p.out_off[1],
+                ox = tx * p.out_stride + p.out_off[2];
+      const bool valid = (ty < p.Ht) && (tx < p.Wt) && (oz < p.Do) && (oy < p.Ho) && (ox < p.Wo);
+      const size_t vox = (((size_t)b * p.Do + oz) * p.Ho + oy) * p.Wo + ox;
+#pragma unroll 1
+      for (int c0 = 0; c0 < COUT; c0 += 32) {
+        uint32_t rh[32];
+        float v[32];
+        tmem_ld32(taddr + c0, rh);
+        if (PLANES == 2) {
+          uint32_t rl[32];
+          tmem_ld32(taddr + COUT + c0, rl);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rh[j]) + __uint_as_float(rl[j]);
+        } else {
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rh[j]);
+        }
+        if (c0 + 32 >= COUT) {           // all TMEM reads of this tile are done: hand the buffer back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+        if (valid && !(p.dbg & 1)) {
+          const size_t off = vox * COUT + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = v[j] * s_scale[c0 + j] + s_shift[c0 + j];
+          if (p.res_pre) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float f[8];
+              load8_rt(p.res_pre, p.res_plane, p.planes_res, off + q * 8, f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[q * 8 + j] += f[j];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+          if (p.res_post) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float f[8];
+              load8_rt(p.res_post, p.res_plane, p.planes_res, off + q * 8, f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[q * 8 + j] += f[j];
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) store8_rt(p.y, p.y_plane, p.planes_out, off + q * 8, v + q * 8);
+        }
+      }
+    }
 }
 
 template <int CIN, int COUT, int PLANES>
@@ -212,10 +303,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc_full = make_idesc(TC_M, Cfg::NACC);
       constexpr uint32_t idesc_half = make_idesc(TC_M, COUT);
+      constexpr uint64_t DAB = desc_const<Cfg::ROWB>(8 * Cfg::ROWB);
+      const uint32_t stage_u32 = smem_u32(stage_base);
       uint32_t s = 0, ph = 0, it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const uint32_t acc = it & 1;
@@ -225,95 +319,219 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         for (int t = 0; t < p.ntaps; ++t) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t a0 = smem_u32(stage_base + (size_t)s * Cfg::STAGE_BYTES);
-          const uint32_t b0 = a0 + PLANES * Cfg::A_BYTES;
+          const uint32_t a0 = stage_u32 + s * Cfg::STAGE_BYTES;
+          const uint64_t da0 = DAB + (a0 >> 4);
+          const uint64_t db0 = DAB + ((a0 + PLANES * Cfg::A_BYTES) >> 4);
 #pragma unroll
           for (int k = 0; k < CIN / 16; ++k) {
-            const uint64_t da = make_desc<Cfg::ROWB>(a0 + k * 32);
-            const uint64_t db = make_desc<Cfg::ROWB>(b0 + k * 32);
-            umma_bf16(d_addr, da, db, idesc_full, (t > 0 || k > 0) ? 1u : 0u);
-            if (PLANES == 2) {
-              const uint64_t dl = make_desc<Cfg::ROWB>(a0 + Cfg::A_BYTES + k * 32);
-              umma_bf16(d_addr, dl, db, idesc_half, 1u);
+            if (leader) {
+              umma_bf16(d_addr, da0 + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc_full, (t > 0 || k > 0) ? 1u : 0u);
+              if (PLANES == 2)
+                umma_bf16(d_addr, da0 + (uint64_t)((Cfg::A_BYTES >> 4) + k * 2), db0 + (uint64_t)(k * 2), idesc_half, 1u);
             }
           }
-          umma_commit(&empty[s]);
+          __syncwarp();
+          if (leader) umma_commit(&empty[s]);
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull[acc]);
+        if (leader) umma_commit(&tfull[acc]);
+        __syncwarp();
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) are reachable from this warp
-    const int row = quarter * 32 + lane;          // tile row = voxel
-    const int hh = row / TC_TW, ww = row % TC_TW;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      int r = tile;
-      const int tw = r % p.tiles_w; r /= p.tiles_w;
-      const int th = r % p.tiles_h; r /= p.tiles_h;
-      const int td = r % p.Dt;
-      const int b = r / p.Dt;
-      const uint32_t acc = it & 1;
-      mbar_wait(&tfull[acc], (it >> 1) & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * Cfg::NACC;
-      const int tz = td, ty = th * TC_TH + hh, tx = tw * TC_TW + ww;
-      const int oz = tz * p.out_stride + p.out_off[0], oy = ty * p.out_stride + p.out_off[1],
-                ox = tx * p.out_stride + p.out_off[2];
-      const bool valid = (ty < p.Ht) && (tx < p.Wt) && (oz < p.Do) && (oy < p.Ho) && (ox < p.Wo);
-      const size_t vox = (((size_t)b * p.Do + oz) * p.Ho + oy) * p.Wo + ox;
-#pragma unroll 1
-      for (int c0 = 0; c0 < COUT; c0 += 32) {
-        uint32_t rh[32];
-        float v[32];
-        tmem_ld32(taddr + c0, rh);
-        if (PLANES == 2) {
-          uint32_t rl[32];
-          tmem_ld32(taddr + COUT + c0, rl);
-          tmem_ld_wait();
+    tc_epilogue<COUT, PLANES>(p, total_tiles, tmem_base, tfull, tempty, s_scale, s_shift, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+
+// =====================================================================================================
+// v2 main loop for 3x3x3 stride-1 convs: halo'd slab reuse.
+// Instead of one shifted 128-row box per tap (27 TMA boxes / tile), ONE halo'd box [Cin, 10 w, 18 h] is
+// loaded per depth slab kd (3 boxes / tile / plane) and the nine (kh,kw) taps of that slab read it through
+// shifted UMMA descriptors: start = slab + (kh*10 + kw)*ROWB, 8-row groups (one h row of 8 voxels) are
+// 10*ROWB apart (SBO).  TMA and UMMA both derive the 64B/128B swizzle XOR from absolute smem address
+// bits, so any row-aligned start inside the slab addresses the right 16-byte chunks.
+// Weights: resident in smem for the whole persistent CTA when 27 taps fit (WRES), else streamed in
+// chunks of 3 taps (one (kd,kh) row) through their own mbarrier ring.
+// =====================================================================================================
+constexpr int HB_W = TC_TW + 2, HB_H = TC_TH + 2;     // halo box 10 x 18
+
+template <int CIN, int COUT, int PLANES>
+struct HaloCfg {
+  static constexpr int ROWB = CIN * 2;
+  static constexpr int SLAB_BYTES = HB_W * HB_H * ROWB;                        // one plane of one slab
+  static constexpr int SLAB_PITCH = (SLAB_BYTES + 1023) / 1024 * 1024;
+  static constexpr int A_SLOT = PLANES * SLAB_PITCH;
+  static constexpr int B_ROWS = PLANES * COUT;
+  static constexpr int B_BYTES = B_ROWS * ROWB;                                // one tap
+  static constexpr int BUDGET = 200 * 1024;
+  static constexpr bool WRES = (27 * B_BYTES + 2 * A_SLOT) <= BUDGET;
+  static constexpr int W_CHUNK = 3 * B_BYTES;
+  static constexpr int A_SLOTS_RES = ((BUDGET - 27 * B_BYTES) / A_SLOT) > 4 ? 4 : ((BUDGET - 27 * B_BYTES) / A_SLOT);
+  static constexpr int A_SLOTS = WRES ? A_SLOTS_RES : 2;
+  static constexpr int W_SLOTS_STR = ((BUDGET - 2 * A_SLOT) / W_CHUNK) > 4 ? 4 : ((BUDGET - 2 * A_SLOT) / W_CHUNK);
+  static constexpr int W_SLOTS = WRES ? 1 : W_SLOTS_STR;
+  static constexpr int W_BYTES_TOTAL = WRES ? 27 * B_BYTES : W_SLOTS * W_CHUNK;
+  static constexpr int TMEM_COLS = 2 * PLANES * COUT < 32 ? 32 : 2 * PLANES * COUT;
+  static constexpr int SMEM_BYTES = A_SLOTS * A_SLOT + W_BYTES_TOTAL + 1024 + 256 + 2 * COUT * 4;
+};
+
+template <int ROWB>
+__device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+  constexpr uint64_t layout = (ROWB == 128) ? 2ull : 4ull;
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
+         (layout << 61);
+}
+
+template <int CIN, int COUT, int PLANES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+  using Cfg = HaloCfg<CIN, COUT, PLANES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_base = smem;
+  uint8_t* w_base = smem + Cfg::A_SLOTS * Cfg::A_SLOT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_base + Cfg::W_BYTES_TOTAL);
+  uint64_t* afull = bars;                       // [A_SLOTS]
+  uint64_t* aempty = afull + Cfg::A_SLOTS;      // [A_SLOTS]
+  uint64_t* wfull = aempty + Cfg::A_SLOTS;      // [W_SLOTS]
+  uint64_t* wempty = wfull + Cfg::W_SLOTS;      // [W_SLOTS]
+  uint64_t* tfull = wempty + Cfg::W_SLOTS;      // [2]
+  uint64_t* tempty = tfull + 2;                 // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_scale = reinterpret_cast<float*>(w_base + Cfg::W_BYTES_TOTAL + 256);
+  float* s_shift = s_scale + COUT;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.B * p.Dt * p.tiles_h * p.tiles_w;
+
+  if (threadIdx.x < COUT) {
+    s_scale[threadIdx.x] = p.scale ? p.scale[threadIdx.x] : 1.f;
+    s_shift[threadIdx.x] = p.shift ? p.shift[threadIdx.x] : 0.f;
+  }
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
+    for (int i = 0; i < Cfg::W_SLOTS; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&maps.a[0]);
+    prefetch_tmap(&maps.w);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      if (Cfg::WRES) {
+        mbar_expect_tx(&wfull[0], 27 * Cfg::B_BYTES);
+        for (int t = 0; t < 27; ++t) tma_load_2d(w_base + t * Cfg::B_BYTES, &maps.w, &wfull[0], 0, t * Cfg::B_ROWS);
+      }
+      uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int r = tile;
+        const int tw = r % p.tiles_w; r /= p.tiles_w;
+        const int th = r % p.tiles_h; r /= p.tiles_h;
+        const int td = r % p.Dt;
+        const int b = r / p.Dt;
+        for (int kd = 0; kd < 3; ++kd) {
+          mbar_wait(&aempty[sa], pa ^ 1);
+          mbar_expect_tx(&afull[sa], PLANES * Cfg::SLAB_BYTES);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rh[j]) + __uint_as_float(rl[j]);
-        } else {
-          tmem_ld_wait();
+          for (int pl = 0; pl < PLANES; ++pl)
+            tma_load_5d(a_base + sa * Cfg::A_SLOT + pl * Cfg::SLAB_PITCH, &maps.a[0], &afull[sa], 0, tw * TC_TW - 1,
+                        th * TC_TH - 1, td + kd - 1, pl * p.B + b);
+          if (++sa == Cfg::A_SLOTS) { sa = 0; pa ^= 1; }
+          if (!Cfg::WRES) {
+            for (int kh = 0; kh < 3; ++kh) {
+              mbar_wait(&wempty[sw], pw ^ 1);
+              mbar_expect_tx(&wfull[sw], Cfg::W_CHUNK);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rh[j]);
-        }
-        if (c0 + 32 >= COUT) {           // all TMEM reads of this tile are done: hand the buffer back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
-        }
-        if (valid) {
-          const size_t off = vox * COUT + c0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = v[j] * s_scale[c0 + j] + s_shift[c0 + j];
-          if (p.res_pre) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float f[8];
-              load8_rt(p.res_pre, p.res_plane, p.planes_res, off + q * 8, f);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[q * 8 + j] += f[j];
+              for (int kw = 0; kw < 3; ++kw)
+                tma_load_2d(w_base + sw * Cfg::W_CHUNK + kw * Cfg::B_BYTES, &maps.w, &wfull[sw], 0,
+                            ((kd * 3 + kh) * 3 + kw) * Cfg::B_ROWS);
+              if (++sw == Cfg::W_SLOTS) { sw = 0; pw ^= 1; }
             }
           }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-          if (p.res_post) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float f[8];
-              load8_rt(p.res_post, p.res_plane, p.planes_res, off + q * 8, f);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[q * 8 + j] += f[j];
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) store8_rt(p.y, p.y_plane, p.planes_out, off + q * 8, v + q * 8);
         }
       }
     }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+    {
+      const bool leader = elect_one();
+      constexpr uint32_t idesc_full = make_idesc(TC_M, PLANES * COUT);
+      constexpr uint32_t idesc_half = make_idesc(TC_M, COUT);
+      constexpr uint64_t DA = desc_const<Cfg::ROWB>(HB_W * Cfg::ROWB);     // activation slab: 8-row groups 10 rows apart
+      constexpr uint64_t DB = desc_const<Cfg::ROWB>(8 * Cfg::ROWB);        // weights: dense
+      constexpr uint32_t NACC = PLANES * COUT;
+      if (Cfg::WRES) { mbar_wait(&wfull[0], 0); tc_fence_after(); }
+      const uint32_t a_u32 = smem_u32(a_base), w_u32 = smem_u32(w_base);
+      uint32_t sa = 0, pa = 0, sw = 0, pw = 0, it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1;
+        mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + acc * NACC;
+#pragma unroll 1
+        for (int kd = 0; kd < 3; ++kd) {
+          mbar_wait(&afull[sa], pa);
+          tc_fence_after();
+          const uint64_t da_slab = DA + ((a_u32 + sa * Cfg::A_SLOT) >> 4);
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            uint64_t db_row;
+            if (Cfg::WRES) {
+              db_row = DB + ((w_u32 + (uint32_t)((kd * 3 + kh) * 3) * Cfg::B_BYTES) >> 4);
+            } else {
+              mbar_wait(&wfull[sw], pw);
+              tc_fence_after();
+              db_row = DB + ((w_u32 + sw * Cfg::W_CHUNK) >> 4);
+            }
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+              for (int k = 0; k < CIN / 16; ++k) {
+                const uint64_t da = da_slab + (uint64_t)(((kh * HB_W + kw) * Cfg::ROWB + k * 32) >> 4);
+                const uint64_t db = db_row + (uint64_t)((kw * Cfg::B_BYTES + k * 32) >> 4);
+                const uint32_t accum = (kh == 0 && kw == 0 && k == 0) ? (kd != 0 ? 1u : 0u) : 1u;
+                if (leader && !(p.dbg & 2)) {
+                  umma_bf16(d_addr, da, db, idesc_full, accum);
+                  if (PLANES == 2) umma_bf16(d_addr, da + (uint64_t)(Cfg::SLAB_PITCH >> 4), db, idesc_half, 1u);
+                }
+              }
+            }
+            if (!Cfg::WRES) {
+              __syncwarp();
+              if (leader) umma_commit(&wempty[sw]);
+              if (++sw == Cfg::W_SLOTS) { sw = 0; pw ^= 1; }
+            }
+          }
+          __syncwarp();
+          if (leader) umma_commit(&aempty[sa]);
+          if (++sa == Cfg::A_SLOTS) { sa = 0; pa ^= 1; }
+        }
+        if (leader) umma_commit(&tfull[acc]);
+        __syncwarp();
+      }
+    }
+  } else {
+    tc_epilogue<COUT, PLANES>(p, total_tiles, tmem_base, tfull, tempty, s_scale, s_shift, warp, lane);
   }
 
   tc_fence_before();
@@ -357,12 +575,12 @@ static EncodeTiledFn get_encode() {
 
 // 5-D view of cost planes: dims (C, W, H, D, planes*B) with arbitrary element strides per axis
 static bool make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int D, int NB, size_t sW, size_t sH,
-                         size_t sD, size_t sB) {
+                         size_t sD, size_t sB, int box_w = TC_TW, int box_h = TC_TH) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)NB};
   cuuint64_t strides[4] = {sW * 2, sH * 2, sD * 2, sB * 2};
-  cuuint32_t box[5] = {(cuuint32_t)C, TC_TW, TC_TH, 1, 1};
+  cuuint32_t box[5] = {(cuuint32_t)C, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   CUtensorMapSwizzle sw = (C * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
@@ -384,6 +602,9 @@ static bool make_w_map(CUtensorMap* m, const void* base, int Cin, int rows, int 
 }
 
 static int g_num_sms = 0;
+static int g_use_halo = 1;
+static int g_ngrp = 1, g_lo_sep = 0;
+static int g_dbg = 0;
 
 template <int CIN, int COUT, int PLANES>
 static int launch_tc(const TcMaps& maps, const TcParams& p, cudaStream_t st) {
@@ -404,9 +625,39 @@ static int launch_tc(const TcMaps& maps, const TcParams& p, cudaStream_t st) {
   return DCA_OK;
 }
 
+template <int CIN, int COUT, int PLANES>
+static int launch_tc_halo(const TcMaps& maps, const TcParams& p, cudaStream_t st) {
+  using Cfg = HaloCfg<CIN, COUT, PLANES>;
+  static_assert(Cfg::A_SLOTS >= 2 && Cfg::W_SLOTS >= 1, "smem plan");
+  static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "smem plan");
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  cudaFuncSetAttribute(conv_tc_halo_kernel<CIN, COUT, PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       Cfg::SMEM_BYTES);
+  const int total = p.B * p.Dt * p.tiles_h * p.tiles_w;
+  const int grid = total < g_num_sms ? total : g_num_sms;
+  conv_tc_halo_kernel<CIN, COUT, PLANES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);
+  DCA_RETURN_IF_LAUNCH_FAILED();
+  return DCA_OK;
+}
+
 }  // namespace dca
 
 using namespace dca;
+
+// 1 = halo-slab main loop for k3 s1 (default), 0 = one TMA box per tap (v1)
+extern "C" int dca_tc_set_halo(int on) { g_use_halo = on ? 1 : 0; return DCA_OK; }
+// accumulator interleave (1,2,4) and separate lo block (0/1) of the halo kernel
+extern "C" int dca_tc_set_tuning(int ngrp, int lo_sep) {
+  if (ngrp != 1 && ngrp != 2 && ngrp != 4) return DCA_ERR_ARG;
+  g_ngrp = ngrp; g_lo_sep = lo_sep ? 1 : 0;
+  g_dbg = lo_sep >> 4;   // timing experiments: (lo_sep >> 4) & 1 skip stores, & 2 skip MMAs
+  return DCA_OK;
+}
 
 extern "C" long long dca_pack_weights_tc_bytes(int Co, int Ci, int taps, int planes) {
   if (Co <= 0 || Ci <= 0 || taps <= 0 || planes < 1 || planes > 2) return 0;
@@ -445,6 +696,7 @@ extern "C" int dca_conv3d_tc(int mode, const void* x, int planes_in, const void*
   p.res_pre = (const __nv_bfloat16*)res_pre; p.res_post = (const __nv_bfloat16*)res_post;
   p.res_plane = (size_t)B * Do * Ho * Wo * Cout; p.planes_res = planes_res;
   p.y = (__nv_bfloat16*)y; p.y_plane = p.res_plane; p.planes_out = planes_out; p.act = act;
+  p.npart = P; p.ngrp = 1; p.lo_sep = 0; p.dbg = g_dbg;
   const size_t sW = Cin, sH = (size_t)Wi * Cin, sD = (size_t)Hi * Wi * Cin, sB = (size_t)Di * Hi * Wi * Cin;
   const int ntaps_total = (mode == 3) ? 1 : 27;
   if (!make_w_map(&maps.w, w_tc, Cin, ntaps_total * P * Cout, P * Cout)) return DCA_ERR_LAUNCH;
@@ -463,6 +715,21 @@ extern "C" int dca_conv3d_tc(int mode, const void* x, int planes_in, const void*
     return DCA_ERR_UNSUPPORTED;
   };
 
+  if (mode == 0 && g_use_halo && !(Cin == 32 && Cout == 64)) {
+    if (!make_act_map(&maps.a[0], x, Cin, Wi, Hi, Di, P * B, sW, sH, sD, sB, HB_W, HB_H)) return DCA_ERR_LAUNCH;
+    for (int i = 1; i < 8; ++i) maps.a[i] = maps.a[0];
+    p.Dt = Do; p.Ht = Ho; p.Wt = Wo; p.out_stride = 1; p.ntaps = 27;
+    p.tiles_w = (p.Wt + TC_TW - 1) / TC_TW;
+    p.tiles_h = (p.Ht + TC_TH - 1) / TC_TH;
+#define DCA_TCH_CASE(CI, CO)                                                       \
+  if (Cin == CI && Cout == CO)                                                     \
+    return P == 2 ? launch_tc_halo<CI, CO, 2>(maps, p, st) : launch_tc_halo<CI, CO, 1>(maps, p, st);
+    DCA_TCH_CASE(32, 32)
+    DCA_TCH_CASE(64, 32)
+    DCA_TCH_CASE(64, 64)
+#undef DCA_TCH_CASE
+    return DCA_ERR_UNSUPPORTED;
+  }
   if (mode == 0 || mode == 3) {
     if (!make_act_map(&maps.a[0], x, Cin, Wi, Hi, Di, P * B, sW, sH, sD, sB)) return DCA_ERR_LAUNCH;
     for (int i = 1; i < 8; ++i) maps.a[i] = maps.a[0];

@@ -69,6 +69,10 @@ int dca_conv3d_tc(int mode, const void* x, int planes_in, const void* w_tc, cons
                   int Cin, int Cout, int Di, int Hi, int Wi, int Do, int Ho, int Wo, void* stream);
 int dca_pack_weights_tc(const float* w, int transposed, int Co, int Ci, int taps, void* out, int planes, void* stream);
 long long dca_pack_weights_tc_bytes(int Co, int Ci, int taps, int planes);
+/* k3 s1 main loop selector: 1 = halo'd slab reuse (default), 0 = one TMA box per tap. */
+int dca_tc_set_halo(int on);
+/* halo kernel tuning: taps interleaved over ngrp (1,2,4) independent TMEM accumulator groups; lo_sep = own block for lo*Whi. */
+int dca_tc_set_tuning(int ngrp, int lo_sep);
 
 /* (2) DCA module ------------------------------------------------------------------------------- */
 int dca_avgpool3d(const void* x, void* y, int planes, int B, int C, int Di, int Hi, int Wi, void* stream);
