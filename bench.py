@@ -118,6 +118,7 @@ def main():
     ap.add_argument("--precision", default="parity", choices=["parity", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tc", action="store_true", help="force the CUDA-core conv kernels")
+    ap.add_argument("--breakdown", action="store_true", help="print per-entry-point GPU time of one forward and exit")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -166,6 +167,23 @@ def main():
         if dist is not None:
             dist.barrier()
             torch.cuda.synchronize()
+
+    if args.breakdown:
+        with torch.no_grad():
+            for i in range(3):
+                net.hot_path(*dev_sets[i % nsets])
+            torch.cuda.synchronize()
+            d._lib.PROFILE = []
+            n_rep = 5
+            for i in range(n_rep):
+                net.hot_path(*dev_sets[i % nsets])
+            agg = d._lib.profile_summary()
+            d._lib.PROFILE = None
+        tot = sum(v[1] for v in agg.values())
+        print(f"per-forward GPU time by entry point ({args.config}, {args.precision}); total {tot / n_rep:.3f} ms")
+        for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            print(f"{ms / n_rep:8.3f} ms  {n // n_rep:3d}x  {100 * ms / tot:5.1f}%  {k}")
+        return 0
 
     # ---------------- device-resident throughput ----------------
     with torch.no_grad():

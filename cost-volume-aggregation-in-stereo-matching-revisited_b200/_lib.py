@@ -22,7 +22,8 @@ SIGNATURES = {
     "dca_conv3d_direct": [_c_int, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _c_int, _c_int, _c_int]
                          + [_c_int] * 10 + [_vp],
     "dca_conv3d_cout1": [_vp, _c_int, _vp, _vp] + [_c_int] * 5 + [_vp],
-    "dca_conv3d_tc": [_c_int, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _c_int, _c_int] + [_c_int] * 9 + [_vp],
+    "dca_conv3d_tc": [_c_int, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _c_int, _vp, _c_int, _c_int]
+                     + [_c_int] * 9 + [_vp],
     "dca_pack_weights_tc": [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp],
     "dca_pack_weights_tc_bytes": [_c_int] * 4,
     "dca_tc_set_halo": [_c_int],
@@ -68,10 +69,38 @@ def load():
     return lib
 
 
+PROFILE = None   # set to a list to record (label, start_event, end_event) around every call (diagnostics)
+
+
+def profile_summary():
+    """Aggregate PROFILE records -> {label: (count, total_ms)} (synchronises)."""
+    import torch
+    torch.cuda.synchronize()
+    agg = {}
+    for label, a, b in PROFILE or []:
+        n, tot = agg.get(label, (0, 0.0))
+        agg[label] = (n + 1, tot + a.elapsed_time(b))
+    return agg
+
+
 def call(name, *args):
     """Invoke an entry point; non-zero status raises DcaError (the reference raises on its asserts)."""
     global LAUNCHES
-    LAUNCHES += 8 if (name in ("dca_conv3d_direct", "dca_conv3d_tc") and args[0] == 2) else 1
+    if PROFILE is not None:
+        import torch
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = getattr(load(), name)(*args)
+        b.record()
+        label = name
+        if name in ("dca_conv3d_tc", "dca_conv3d_direct"):
+            ints = [x for x in args if isinstance(x, int) and 0 < x < 4096]
+            label = f"{name} mode={args[0]} dims={args[-10:-1] if name == 'dca_conv3d_tc' else args[-11:-1]}"
+        PROFILE.append((label, a, b))
+        if rc != 0:
+            raise DcaError(f"{name} failed: {ERRORS.get(rc, rc)}")
+        return
+    LAUNCHES += 8 if (name == "dca_conv3d_direct" and args[0] == 2) else 1
     rc = getattr(load(), name)(*args)
     if rc != 0:
         raise DcaError(f"{name} failed: {ERRORS.get(rc, rc)}")

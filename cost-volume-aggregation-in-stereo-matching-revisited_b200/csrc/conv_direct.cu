@@ -16,6 +16,8 @@
 //               offset (p+1-k)/2  in {0,1}          (o = 2i - 1 + k)
 // CTA = 256 threads, tile 1 x 4 x 32 points x NT output channels; Cin is consumed in chunks of CK
 // through shared memory (input halo tile + the chunk's weights for all taps).
+#include <cstring>
+
 #include "dca_common.cuh"
 
 namespace dca {
@@ -204,61 +206,76 @@ conv_direct_kernel(const ConvDirectParams p) {
 
 // ---------------------------------------------------------------------------------------------
 // 3x3x3 stride-1 conv to ONE output channel, fp32 logits out [B,D,H,W]
-// (cva.classify.2 cva.py:53 and classif3.2 gwcnet_dca_g.py:168).  One thread per output voxel;
-// halo tile of all Cin channels staged in smem as fp32; weights in smem (broadcast reads).
+// (cva.classify.2 cva.py:53 and classif3.2 gwcnet_dca_g.py:168).
+// Marching formulation: the CTA owns an 8h x 32w tile and walks a chunk of depth planes.  For every
+// input plane each thread computes, for ONE (halo) voxel, the 27 dot products <x[v,:], w[tap,:]>
+// (weights are kernel parameters, i.e. constant-bank FFMA operands: no load per FMA), parks them in
+// shared memory, and the output threads gather the 9 in-plane neighbours per kd into a 3-deep ring of
+// running sums.  Every activation is read once (plus the 1-voxel halo).
 // ---------------------------------------------------------------------------------------------
-constexpr int C1_TH = 4, C1_TW = 32;
-template <int CIN>
-__global__ void __launch_bounds__(C1_TH * C1_TW)
-conv3d_cout1_kernel(const __nv_bfloat16* __restrict__ x, size_t x_plane, int planes, const float* __restrict__ w,
-                    float* __restrict__ y, int B, int D, int H, int W) {
-  constexpr int PITCH = CIN + 4;
-  constexpr int EH = C1_TH + 2, EW = C1_TW + 2;
-  extern __shared__ __align__(16) float smem[];
-  float* xs = smem;                        // [3][EH][EW][PITCH]
-  float* ws = smem + 3 * EH * EW * PITCH;  // [27][CIN]
+constexpr int C1_TH = 8, C1_TW = 32, C1_EH = C1_TH + 2, C1_EW = C1_TW + 2;
+constexpr int C1_THREADS = 352;           // >= C1_EH * C1_EW = 340
+struct Cout1Weights { float w[27 * 32]; };
+
+__global__ void __launch_bounds__(C1_THREADS)
+conv3d_cout1_kernel(const __nv_bfloat16* __restrict__ x, size_t x_plane, int planes, const Cout1Weights wp,
+                    float* __restrict__ y, int B, int D, int H, int W, int DC) {
+  constexpr int CIN = 32;
+  __shared__ float P[C1_EH * C1_EW * 27];
   const int wtiles = (W + C1_TW - 1) / C1_TW;
   const int w0 = (blockIdx.x % wtiles) * C1_TW, h0 = (blockIdx.x / wtiles) * C1_TH;
-  const int d = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
-  for (int it = tid; it < 3 * EH * EW * (CIN / 8); it += C1_TH * C1_TW) {
-    int vox = it / (CIN / 8), ch8 = it % (CIN / 8);
-    int dx = vox % EW, r = vox / EW;
-    int dy = r % EH, dz = r / EH;
-    int iz = d - 1 + dz, iy = h0 - 1 + dy, ix = w0 - 1 + dx;
-    float f[8];
-    if (iz >= 0 && iz < D && iy >= 0 && iy < H && ix >= 0 && ix < W) {
-      size_t off = ((((size_t)b * D + iz) * H + iy) * W + ix) * CIN + ch8 * 8;
-      load8_rt(x, x_plane, planes, off, f);
-    } else {
+  const int d0 = blockIdx.y * DC, b = blockIdx.z, tid = threadIdx.x;
+  const int d_end = min(d0 + DC, D);
+  const bool producer = tid < C1_EH * C1_EW;
+  const int ih = h0 - 1 + tid / C1_EW, iw = w0 - 1 + tid % C1_EW;
+  const bool in_hw = producer && ih >= 0 && ih < H && iw >= 0 && iw < W;
+  const bool consumer = tid < C1_TH * C1_TW;
+  const int oh = tid / C1_TW, ow = tid % C1_TW;
+  float r0 = 0.f, r1 = 0.f, r2 = 0.f;       // running sums of output planes d_in-1, d_in, d_in+1
+  for (int d_in = d0 - 1; d_in <= d_end; ++d_in) {
+    const bool plane_ok = d_in >= 0 && d_in < D;
+    if (producer) {
+      float acc[27];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = 0.f;
-    }
-    float4* dst = reinterpret_cast<float4*>(xs + (size_t)vox * PITCH + ch8 * 8);
-    dst[0] = make_float4(f[0], f[1], f[2], f[3]);
-    dst[1] = make_float4(f[4], f[5], f[6], f[7]);
-  }
-  for (int it = tid; it < 27 * CIN; it += C1_TH * C1_TW) ws[it] = __ldg(w + it);
-  __syncthreads();
-  const int hh = tid / C1_TW, ww = tid % C1_TW;
-  float acc = 0.f;
-#pragma unroll 1
-  for (int kd = 0; kd < 3; ++kd)
-#pragma unroll 1
-    for (int kh = 0; kh < 3; ++kh)
+      for (int t = 0; t < 27; ++t) acc[t] = 0.f;
+      if (plane_ok && in_hw) {
+        const size_t off = ((((size_t)b * D + d_in) * H + ih) * W + iw) * CIN;
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const float* xp = xs + (size_t)((kd * EH + hh + kh) * EW + ww + kw) * PITCH;
-        const float* wp = ws + ((kd * 3 + kh) * 3 + kw) * CIN;
+        for (int c8 = 0; c8 < CIN; c8 += 8) {
+          float f[8];
+          load8_rt(x, x_plane, planes, off + c8, f);
 #pragma unroll
-        for (int c = 0; c < CIN; c += 4) {
-          float4 xv = *reinterpret_cast<const float4*>(xp + c);
-          float4 wv = *reinterpret_cast<const float4*>(wp + c);
-          acc = fmaf(xv.x, wv.x, acc); acc = fmaf(xv.y, wv.y, acc);
-          acc = fmaf(xv.z, wv.z, acc); acc = fmaf(xv.w, wv.w, acc);
+          for (int t = 0; t < 27; ++t)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[t] = fmaf(f[j], wp.w[t * CIN + c8 + j], acc[t]);
         }
       }
-  const int oh = h0 + hh, ow = w0 + ww;
-  if (oh < H && ow < W) y[(((size_t)b * D + d) * H + oh) * W + ow] = acc;
+#pragma unroll
+      for (int t = 0; t < 27; ++t) P[tid * 27 + t] = acc[t];
+    }
+    __syncthreads();
+    if (consumer) {
+      float s[3] = {0.f, 0.f, 0.f};
+      if (plane_ok) {
+#pragma unroll
+        for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw)
+              s[kd] += P[((oh + kh) * C1_EW + ow + kw) * 27 + (kd * 3 + kh) * 3 + kw];
+      }
+      // input plane d_in feeds output d_in+1 through kd=0, d_in through kd=1, d_in-1 through kd=2
+      r0 += s[2];
+      const int od = d_in - 1;
+      if (od >= d0 && od < d_end && h0 + oh < H && w0 + ow < W)
+        y[(((size_t)b * D + od) * H + h0 + oh) * W + w0 + ow] = r0;
+      r0 = r1 + s[1];
+      r1 = s[0];
+      (void)r2;
+    }
+    __syncthreads();
+  }
 }
 
 static void fill_taps(ConvDirectParams& p, int mode, const int parity[3]) {
@@ -359,15 +376,17 @@ extern "C" int dca_conv3d_direct(int mode, const void* x, int planes_in, const f
   return run(p);
 }
 
-extern "C" int dca_conv3d_cout1(const void* x, int planes_in, const float* w, float* y, int B, int Cin, int D, int H,
-                                int W, void* stream) {
-  if (!x || !w || !y || B <= 0 || D <= 0 || H <= 0 || W <= 0) return DCA_ERR_ARG;
+extern "C" int dca_conv3d_cout1(const void* x, int planes_in, const float* w_host, float* y, int B, int Cin, int D,
+                                int H, int W, void* stream) {
+  // w_host: HOST pointer [27][Cin] fp32; copied into the launch parameters (constant bank operands).
+  if (!x || !w_host || !y || B <= 0 || D <= 0 || H <= 0 || W <= 0) return DCA_ERR_ARG;
   if (Cin != 32) return DCA_ERR_UNSUPPORTED;
-  size_t smem = ((size_t)3 * (C1_TH + 2) * (C1_TW + 2) * (32 + 4) + 27 * 32) * sizeof(float);
-  cudaFuncSetAttribute(conv3d_cout1_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  dim3 grid(((W + C1_TW - 1) / C1_TW) * ((H + C1_TH - 1) / C1_TH), D, B);
-  conv3d_cout1_kernel<32><<<grid, C1_TH * C1_TW, smem, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, (size_t)B * D * H * W * Cin, planes_in, w, y, B, D, H, W);
+  Cout1Weights wp;
+  memcpy(wp.w, w_host, sizeof(wp.w));
+  const int DC = D <= 16 ? D : 16;
+  dim3 grid(((W + C1_TW - 1) / C1_TW) * ((H + C1_TH - 1) / C1_TH), (D + DC - 1) / DC, B);
+  conv3d_cout1_kernel<<<grid, C1_THREADS, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, (size_t)B * D * H * W * Cin, planes_in, wp, y, B, D, H, W, DC);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }

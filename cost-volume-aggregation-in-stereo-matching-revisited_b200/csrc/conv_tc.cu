@@ -16,8 +16,9 @@
 //        MMA#2  A=lo, B=[Whi]     (N = Cout)    -> cols [0,Cout) += lo*Whi
 //     and the epilogue adds the two column halves: ~16-bit operand significand, fp32 accumulate.
 //   planes == 1 ("fast"): one MMA, plain bf16 operands.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected lane),
-//   warps 2-5 = epilogue (TMEM -> registers -> BN scale/shift, residuals, activation -> bf16 planes).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected lane),
+//   warps 2-9 = epilogue (TMEM -> registers -> [+ fused trilinear x2 term] -> BN scale/shift, residuals,
+//   activation -> bf16 planes).
 // Persistent CTAs (grid = #SMs) walk output tiles round-robin.
 #include <cuda.h>
 #include <cstring>
@@ -27,7 +28,7 @@
 namespace dca {
 
 constexpr int TC_TW = 8, TC_TH = 16, TC_M = 128;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;       // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int TC_MAX_TAPS = 27;
 
 struct TcMaps {
@@ -40,6 +41,9 @@ struct TcParams {
   int Dt, Ht, Wt;                 // tile-space extent
   int tiles_w, tiles_h;
   int out_stride, out_off[3];
+  int ncls;                        // output classes sharing one launch (8 parity classes of a transposed conv, else 1)
+  unsigned char cls_tap0[9];       // taps [cls_tap0[c], cls_tap0[c+1]) belong to class c
+  signed char cls_off[8][3];       // output offset of class c
   int ntaps;
   signed char tap_off[TC_MAX_TAPS][3];
   signed char tap_map[TC_MAX_TAPS];
@@ -47,6 +51,9 @@ struct TcParams {
   const float* scale; const float* shift;
   const __nv_bfloat16* res_pre; const __nv_bfloat16* res_post; size_t res_plane; int planes_res;
   __nv_bfloat16* y; size_t y_plane; int planes_out; int act;
+  const __nv_bfloat16* up; int planes_up;   // optional half-resolution tensor added (trilinear x2) before BN
+  int linear;                      // 1x1x1 convs: tiles are 128 CONSECUTIVE voxels (8 KB bursts); rB/rD/rH/rW = real dims
+  int rB, rD, rH, rW;
   int dbg;       // diagnostics: bit0 = skip epilogue stores, bit1 = skip MMAs (timing experiments only)
   int npart;     // accumulator column blocks (each Cout wide) the epilogue sums
   int ngrp;      // halo kernel: taps are interleaved over ngrp independent accumulator groups
@@ -147,81 +154,169 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// ------------------------------------------------------------------ shared epilogue (warps 2..5)
-// TMEM accumulator -> registers -> (+lo half) -> BN scale/shift -> +res_pre -> act -> +res_post -> bf16 planes
+// ------------------------------------------------------------------ shared epilogue (warps 2..9)
+// TMEM accumulator -> registers -> (+lo half) -> [+ trilinear x2 of `up`] -> BN scale/shift -> +res_pre -> act
+// -> +res_post -> bf16 planes.  Eight warps: warp w reads TMEM lanes [32*(w%4), +32) (hardware restriction) and
+// the 16-column half (w-2)/4 of every 32-channel chunk, so a thread finishes 16 channels of one voxel.
+// Residual / upsample source rows are fetched BEFORE waiting for the accumulator (latency overlaps the MMAs).
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// (a, b) -> packed bf16x2 hi and bf16x2 lo (= bf16 of the remainders)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void add_raw16(float* v, const uint4* raw, int planes) {   // raw[0..1] hi, raw[2..3] lo
+  float f[8];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    unpack8(raw[q], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[q * 8 + j] += f[j];
+    if (planes == 2) {
+      unpack8(raw[2 + q], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[q * 8 + j] += f[j];
+    }
+  }
+}
+__device__ __forceinline__ void load_raw16(uint4* raw, const __nv_bfloat16* base, size_t plane, int planes, size_t off) {
+  raw[0] = *reinterpret_cast<const uint4*>(base + off);
+  raw[1] = *reinterpret_cast<const uint4*>(base + off + 8);
+  if (planes == 2) {
+    raw[2] = *reinterpret_cast<const uint4*>(base + plane + off);
+    raw[3] = *reinterpret_cast<const uint4*>(base + plane + off + 8);
+  }
+}
+
 template <int COUT, int PLANES>
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, uint32_t tmem_base, uint64_t* tfull,
                                             uint64_t* tempty, const float* s_scale, const float* s_shift, int warp,
                                             int lane) {
-    const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) are reachable from this warp
-    const int row = quarter * 32 + lane;          // tile row = voxel
-    const int hh = row / TC_TW, ww = row % TC_TW;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      int r = tile;
-      const int tw = r % p.tiles_w; r /= p.tiles_w;
-      const int th = r % p.tiles_h; r /= p.tiles_h;
-      const int td = r % p.Dt;
-      const int b = r / p.Dt;
-      const uint32_t acc = it & 1;
-      mbar_wait(&tfull[acc], (it >> 1) & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)(PLANES * COUT);
-      const int tz = td, ty = th * TC_TH + hh, tx = tw * TC_TW + ww;
-      const int oz = tz * p.out_stride + p.out_off[0], oy = ty * p.out_stride + p.out_off[1],
-                ox = tx * p.out_stride + p.out_off[2];
-      const bool valid = (ty < p.Ht) && (tx < p.Wt) && (oz < p.Do) && (oy < p.Ho) && (ox < p.Wo);
-      const size_t vox = (((size_t)b * p.Do + oz) * p.Ho + oy) * p.Wo + ox;
+  const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) are reachable from this warp
+  const int half = (warp - 2) >> 2;             // which 16 columns of each 32-channel chunk
+  const int row = quarter * 32 + lane;          // tile row = voxel
+  const int hh = row / TC_TW, ww = row % TC_TW;
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    int r = tile;
+    const int cls = r % p.ncls; r /= p.ncls;
+    const int tw = r % p.tiles_w; r /= p.tiles_w;
+    const int th = r % p.tiles_h; r /= p.tiles_h;
+    const int td = r % p.Dt;
+    const int b = r / p.Dt;
+    const uint32_t acc = it & 1;
+    const int ty = th * TC_TH + hh, tx = tw * TC_TW + ww;
+    int oz = td * p.out_stride + p.cls_off[cls][0], oy = ty * p.out_stride + p.cls_off[cls][1],
+        ox = tx * p.out_stride + p.cls_off[cls][2];
+    const bool valid = (ty < p.Ht) && (tx < p.Wt) && (oz < p.Do) && (oy < p.Ho) && (ox < p.Wo);
+    const size_t vox = (((size_t)b * p.Do + oz) * p.Ho + oy) * p.Wo + ox;
+    int bb = b, uD = p.Do, uH = p.Ho, uW = p.Wo;
+    if (p.linear) {                   // recover the real voxel coordinates from the linear index
+      size_t r2 = vox;
+      ox = (int)(r2 % p.rW); r2 /= p.rW;
+      oy = (int)(r2 % p.rH); r2 /= p.rH;
+      oz = (int)(r2 % p.rD);
+      bb = (int)(r2 / p.rD);
+      uD = p.rD; uH = p.rH; uW = p.rW;
+    }
+    const size_t off0 = vox * COUT + half * 16;          // first chunk's 16 channels of this thread
+    uint4 pre_raw[4], post_raw[4];
+    const bool has_pre = valid && p.res_pre != nullptr, has_post = valid && p.res_post != nullptr;
+    if (has_pre) load_raw16(pre_raw, p.res_pre, p.res_plane, p.planes_res, off0);
+    if (has_post) load_raw16(post_raw, p.res_post, p.res_plane, p.planes_res, off0);
+    // fused trilinear x2 (align_corners=False) of a half-resolution tensor `up` with COUT channels
+    float upv[16];
+    const bool has_up = valid && p.up != nullptr;
+    if (has_up) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) upv[j] = 0.f;
+      const int Dl = uD >> 1, Hl = uH >> 1, Wl = uW >> 1;
+      // even o = 2i: .25*in[i-1] + .75*in[i];  odd o = 2i+1: .75*in[i] + .25*in[i+1]   (indices clamped)
+      const int z0 = (oz >> 1) - ((oz & 1) ? 0 : 1), y0 = (oy >> 1) - ((oy & 1) ? 0 : 1), x0 = (ox >> 1) - ((ox & 1) ? 0 : 1);
+      const float wz = (oz & 1) ? 0.75f : 0.25f, wy = (oy & 1) ? 0.75f : 0.25f, wx = (ox & 1) ? 0.75f : 0.25f;
+      const size_t uplane = (size_t)(p.linear ? p.rB : p.B) * Dl * Hl * Wl * COUT;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int iz = min(max(z0 + (k >> 2), 0), Dl - 1), iy = min(max(y0 + ((k >> 1) & 1), 0), Hl - 1),
+                  ix = min(max(x0 + (k & 1), 0), Wl - 1);
+        const float wgt = ((k >> 2) ? 1.f - wz : wz) * (((k >> 1) & 1) ? 1.f - wy : wy) * ((k & 1) ? 1.f - wx : wx);
+        uint4 raw[4];
+        load_raw16(raw, p.up, uplane, p.planes_up, ((((size_t)bb * Dl + iz) * Hl + iy) * Wl + ix) * COUT + half * 16);
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = 0.f;
+        add_raw16(f, raw, p.planes_up);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) upv[j] = fmaf(wgt, f[j], upv[j]);
+      }
+    }
+    mbar_wait(&tfull[acc], (it >> 1) & 1);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)(PLANES * COUT) + half * 16;
 #pragma unroll 1
-      for (int c0 = 0; c0 < COUT; c0 += 32) {
-        uint32_t rh[32];
-        float v[32];
-        tmem_ld32(taddr + c0, rh);
-        if (PLANES == 2) {
-          uint32_t rl[32];
-          tmem_ld32(taddr + COUT + c0, rl);
-          tmem_ld_wait();
+    for (int c0 = 0; c0 < COUT; c0 += 32) {
+      uint32_t rh[16];
+      float v[16];
+      tmem_ld16(taddr + c0, rh);
+      if (PLANES == 2) {
+        uint32_t rl[16];
+        tmem_ld16(taddr + COUT + c0, rl);
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rh[j]) + __uint_as_float(rl[j]);
-        } else {
-          tmem_ld_wait();
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rh[j]) + __uint_as_float(rl[j]);
+      } else {
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rh[j]);
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rh[j]);
+      }
+      if (c0 + 32 >= COUT) {           // all TMEM reads of this tile are done: hand the buffer back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+      }
+      if (valid && !(p.dbg & 1)) {
+        const size_t off = off0 + c0;
+        const int cb = c0 + half * 16;
+        if (has_up) {
+          if (c0 == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += upv[j];
+          }   // (the fused upsample is only used with COUT == 32)
         }
-        if (c0 + 32 >= COUT) {           // all TMEM reads of this tile are done: hand the buffer back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = v[j] * s_scale[cb + j] + s_shift[cb + j];
+        if (p.res_pre) {
+          if (c0 != 0) load_raw16(pre_raw, p.res_pre, p.res_plane, p.planes_res, off);
+          add_raw16(v, pre_raw, p.planes_res);
         }
-        if (valid && !(p.dbg & 1)) {
-          const size_t off = vox * COUT + c0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = v[j] * s_scale[c0 + j] + s_shift[c0 + j];
-          if (p.res_pre) {
+        for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
+        if (p.res_post) {
+          if (c0 != 0) load_raw16(post_raw, p.res_post, p.res_plane, p.planes_res, off);
+          add_raw16(v, post_raw, p.planes_res);
+        }
+        uint32_t hw[8], lw[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float f[8];
-              load8_rt(p.res_pre, p.res_plane, p.planes_res, off + q * 8, f);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[q * 8 + j] += f[j];
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-          if (p.res_post) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float f[8];
-              load8_rt(p.res_post, p.res_plane, p.planes_res, off + q * 8, f);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[q * 8 + j] += f[j];
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) store8_rt(p.y, p.y_plane, p.planes_out, off + q * 8, v + q * 8);
+        for (int j = 0; j < 8; ++j) split2(v[2 * j], v[2 * j + 1], hw[j], lw[j]);
+        *reinterpret_cast<uint4*>(p.y + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(p.y + off + 8) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+        if (p.planes_out == 2) {
+          *reinterpret_cast<uint4*>(p.y + p.y_plane + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          *reinterpret_cast<uint4*>(p.y + p.y_plane + off + 8) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
         }
       }
     }
+  }
 }
 
 template <int CIN, int COUT, int PLANES>
@@ -254,7 +349,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   float* s_shift = s_scale + COUT;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.B * p.Dt * p.tiles_h * p.tiles_w;
+  const int total_tiles = p.B * p.Dt * p.tiles_h * p.tiles_w * p.ncls;
 
   if (threadIdx.x < COUT) {
     s_scale[threadIdx.x] = p.scale ? p.scale[threadIdx.x] : 1.f;
@@ -262,7 +357,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   }
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tmap(&maps.a[0]);
     prefetch_tmap(&maps.w);
@@ -284,11 +379,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       uint32_t s = 0, ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int r = tile;
+        const int cls = r % p.ncls; r /= p.ncls;
         const int tw = r % p.tiles_w; r /= p.tiles_w;
         const int th = r % p.tiles_h; r /= p.tiles_h;
         const int td = r % p.Dt;
         const int b = r / p.Dt;
-        for (int t = 0; t < p.ntaps; ++t) {
+        for (int t = p.cls_tap0[cls]; t < p.cls_tap0[cls + 1]; ++t) {
           mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
           uint8_t* st = stage_base + (size_t)s * Cfg::STAGE_BYTES;
@@ -316,7 +412,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_addr = tmem_base + acc * Cfg::NACC;
-        for (int t = 0; t < p.ntaps; ++t) {
+        const int cls = tile % p.ncls;
+        const int t_first = p.cls_tap0[cls], t_last = p.cls_tap0[cls + 1];
+        for (int t = t_first; t < t_last; ++t) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t a0 = stage_u32 + s * Cfg::STAGE_BYTES;
@@ -325,7 +423,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 #pragma unroll
           for (int k = 0; k < CIN / 16; ++k) {
             if (leader) {
-              umma_bf16(d_addr, da0 + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc_full, (t > 0 || k > 0) ? 1u : 0u);
+              umma_bf16(d_addr, da0 + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc_full, (t > t_first || k > 0) ? 1u : 0u);
               if (PLANES == 2)
                 umma_bf16(d_addr, da0 + (uint64_t)((Cfg::A_BYTES >> 4) + k * 2), db0 + (uint64_t)(k * 2), idesc_half, 1u);
             }
@@ -410,7 +508,7 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   float* s_shift = s_scale + COUT;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.B * p.Dt * p.tiles_h * p.tiles_w;
+  const int total_tiles = p.B * p.Dt * p.tiles_h * p.tiles_w;   // halo kernel: ncls == 1
 
   if (threadIdx.x < COUT) {
     s_scale[threadIdx.x] = p.scale ? p.scale[threadIdx.x] : 1.f;
@@ -419,7 +517,7 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
     for (int i = 0; i < Cfg::W_SLOTS; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tmap(&maps.a[0]);
     prefetch_tmap(&maps.w);
@@ -618,7 +716,7 @@ static int launch_tc(const TcMaps& maps, const TcParams& p, cudaStream_t st) {
   }
   cudaFuncSetAttribute(conv_tc_kernel<CIN, COUT, PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        Cfg::SMEM_BYTES);
-  const int total = p.B * p.Dt * p.tiles_h * p.tiles_w;
+  const int total = p.B * p.Dt * p.tiles_h * p.tiles_w * p.ncls;
   const int grid = total < g_num_sms ? total : g_num_sms;
   conv_tc_kernel<CIN, COUT, PLANES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);
   DCA_RETURN_IF_LAUNCH_FAILED();
@@ -677,9 +775,10 @@ extern "C" int dca_pack_weights_tc(const float* w, int transposed, int Co, int C
 
 // mode: DCA_CONV_K3S1 (0), DCA_CONV_K3S2 (1), DCA_CONV_T3S2 (2), DCA_CONV_K1 (3)
 extern "C" int dca_conv3d_tc(int mode, const void* x, int planes_in, const void* w_tc, const float* scale,
-                             const float* shift, const void* res_pre, const void* res_post, int planes_res, void* y,
-                             int planes_out, int act, int B, int Cin, int Cout, int Di, int Hi, int Wi, int Do, int Ho,
-                             int Wo, void* stream) {
+                             const float* shift, const void* res_pre, const void* res_post, int planes_res,
+                             const void* up, int planes_up, void* y, int planes_out, int act, int B, int Cin, int Cout,
+                             int Di, int Hi, int Wi, int Do, int Ho, int Wo, void* stream) {
+  if (up && (Cout != 32 || (Do & 1) || (Ho & 1) || (Wo & 1) || planes_up < 1 || planes_up > 2)) return DCA_ERR_ARG;
   if (!x || !w_tc || !y || B <= 0 || planes_in < 1 || planes_in > 2 || planes_out < 1 || planes_out > 2)
     return DCA_ERR_ARG;
   if (!((Cin == 32 || Cin == 64) && (Cout == 32 || Cout == 64)) || mode < 0 || mode > 3) return DCA_ERR_UNSUPPORTED;
@@ -697,13 +796,19 @@ extern "C" int dca_conv3d_tc(int mode, const void* x, int planes_in, const void*
   p.res_plane = (size_t)B * Do * Ho * Wo * Cout; p.planes_res = planes_res;
   p.y = (__nv_bfloat16*)y; p.y_plane = p.res_plane; p.planes_out = planes_out; p.act = act;
   p.npart = P; p.ngrp = 1; p.lo_sep = 0; p.dbg = g_dbg;
+  p.up = (const __nv_bfloat16*)up; p.planes_up = planes_up;
   const size_t sW = Cin, sH = (size_t)Wi * Cin, sD = (size_t)Hi * Wi * Cin, sB = (size_t)Di * Hi * Wi * Cin;
   const int ntaps_total = (mode == 3) ? 1 : 27;
   if (!make_w_map(&maps.w, w_tc, Cin, ntaps_total * P * Cout, P * Cout)) return DCA_ERR_LAUNCH;
 
+  p.ncls = 1;
   auto run = [&]() -> int {
     p.tiles_w = (p.Wt + TC_TW - 1) / TC_TW;
     p.tiles_h = (p.Ht + TC_TH - 1) / TC_TH;
+    if (p.ncls == 1) {
+      p.cls_tap0[0] = 0; p.cls_tap0[1] = (unsigned char)p.ntaps;
+      for (int a = 0; a < 3; ++a) p.cls_off[0][a] = (signed char)p.out_off[a];
+    }
 #define DCA_TC_CASE(CI, CO)                                                        \
   if (Cin == CI && Cout == CO)                                                     \
     return P == 2 ? launch_tc<CI, CO, 2>(maps, p, st) : launch_tc<CI, CO, 1>(maps, p, st);
@@ -718,7 +823,8 @@ extern "C" int dca_conv3d_tc(int mode, const void* x, int planes_in, const void*
   if (mode == 0 && g_use_halo && !(Cin == 32 && Cout == 64)) {
     if (!make_act_map(&maps.a[0], x, Cin, Wi, Hi, Di, P * B, sW, sH, sD, sB, HB_W, HB_H)) return DCA_ERR_LAUNCH;
     for (int i = 1; i < 8; ++i) maps.a[i] = maps.a[0];
-    p.Dt = Do; p.Ht = Ho; p.Wt = Wo; p.out_stride = 1; p.ntaps = 27;
+    p.Dt = Do; p.Ht = Ho; p.Wt = Wo; p.out_stride = 1; p.ntaps = 27; p.ncls = 1;
+    p.cls_tap0[0] = 0; p.cls_tap0[1] = 27;
     p.tiles_w = (p.Wt + TC_TW - 1) / TC_TW;
     p.tiles_h = (p.Ht + TC_TH - 1) / TC_TH;
 #define DCA_TCH_CASE(CI, CO)                                                       \
@@ -729,6 +835,21 @@ extern "C" int dca_conv3d_tc(int mode, const void* x, int planes_in, const void*
     DCA_TCH_CASE(64, 64)
 #undef DCA_TCH_CASE
     return DCA_ERR_UNSUPPORTED;
+  }
+  const long long nvox = (long long)B * Di * Hi * Wi;
+  if (mode == 3 && (nvox % 8) == 0 && nvox / 8 < (1ll << 31)) {
+    // 1x1x1 conv: the voxel order is irrelevant, so tile the flat voxel index (8 x nvox/8 view): each tile is 128
+    // consecutive voxels = one contiguous 8/16 KB burst per plane instead of sixteen 512-byte rows
+    const int rows = (int)(nvox / 8);
+    if (!make_act_map(&maps.a[0], x, Cin, 8, rows, 1, P, (size_t)Cin, (size_t)8 * Cin, (size_t)nvox * Cin,
+                      (size_t)nvox * Cin))
+      return DCA_ERR_LAUNCH;
+    for (int i = 1; i < 8; ++i) maps.a[i] = maps.a[0];
+    p.linear = 1; p.rB = B; p.rD = Do; p.rH = Ho; p.rW = Wo;
+    p.B = 1; p.Do = 1; p.Ho = rows; p.Wo = 8;
+    p.Dt = 1; p.Ht = rows; p.Wt = 8; p.out_stride = 1;
+    p.ntaps = 1; p.tap_map[0] = 0; p.tap_w[0] = 0;
+    return run();
   }
   if (mode == 0 || mode == 3) {
     if (!make_act_map(&maps.a[0], x, Cin, Wi, Hi, Di, P * B, sW, sH, sD, sB)) return DCA_ERR_LAUNCH;
@@ -770,10 +891,11 @@ extern "C" int dca_conv3d_tc(int mode, const void* x, int planes_in, const void*
   if (!make_act_map(&maps.a[0], x, Cin, Wi, Hi, Di, P * B, sW, sH, sD, sB)) return DCA_ERR_LAUNCH;
   for (int i = 1; i < 8; ++i) maps.a[i] = maps.a[0];
   p.Dt = Di; p.Ht = Hi; p.Wt = Wi; p.out_stride = 2;
-  for (int pc = 0; pc < 8; ++pc) {
+  p.ncls = 8; p.ntaps = 0;
+  for (int pc = 0; pc < 8; ++pc) {           // the 8 output parity classes partition the 27 taps
     const int par[3] = {(pc >> 2) & 1, (pc >> 1) & 1, pc & 1};
-    p.out_off[0] = par[0]; p.out_off[1] = par[1]; p.out_off[2] = par[2];
-    p.ntaps = 0;
+    p.cls_tap0[pc] = (unsigned char)p.ntaps;
+    for (int a = 0; a < 3; ++a) p.cls_off[pc][a] = (signed char)par[a];
     for (int kd = 0; kd < 3; ++kd) for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw) {
       const int k[3] = {kd, kh, kw};
       int off[3]; bool ok = true;
@@ -783,8 +905,7 @@ extern "C" int dca_conv3d_tc(int mode, const void* x, int planes_in, const void*
       p.tap_off[t][0] = (signed char)off[0]; p.tap_off[t][1] = (signed char)off[1]; p.tap_off[t][2] = (signed char)off[2];
       p.tap_map[t] = 0; p.tap_w[t] = (signed char)((kd * 3 + kh) * 3 + kw);
     }
-    const int rc = run();
-    if (rc != DCA_OK) return rc;
   }
-  return DCA_OK;
+  p.cls_tap0[8] = (unsigned char)p.ntaps;
+  return run();
 }

@@ -230,92 +230,134 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
 // trilinear x2 (align_corners=False) of t [B,Dl,Hl,Wl,32] + Wc . cost [B,2Dl,2Hl,2Wl,32], then BN.
 //   out[v] = scale * (up(t)[v] + Wc cost[v]) + shift
 // A warp owns one 2x2x2 output block whose 8 voxels share the same 8 low-res corners
-// (block index i in [-1, n-1] per axis -> outputs {2i+1, 2i+2} clipped to [0, 2n)); lane = channel.
-// Wc (transposed [ci][co]) sits in 32 registers per lane; the cost vectors are broadcast via smem.
+// (block index i in [-1, n-1] per axis -> outputs {2i+1, 2i+2} clipped to [0, 2n)).
+// lane = (voxel v of the block, channel octet q): every global access is a 16-byte vector, the four
+// lanes of a voxel cover its 64-byte channel row.  The 32x32 matvec reads the block's cost vectors
+// (padded rows) and Wc from shared memory with conflict-free LDS.128.
 // ------------------------------------------------------------------------------------------------
+constexpr int UF_WARPS = 8;
+
+struct UfBlock {            // raw prefetched data of one 2x2x2 block for this lane
+  uint4 c_hi, c_lo;         // cost octet of the lane's voxel
+  uint4 k_hi, k_lo;         // corner (lane>>2), octet (lane&3) of t
+  size_t ooff;
+  bool valid;
+};
+
 template <int PLANES>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void uf_fetch(UfBlock& u, long long blk, const __nv_bfloat16* __restrict__ t,
+                                         const __nv_bfloat16* __restrict__ cost, int Dl, int Hl, int Wl, int nbd,
+                                         int nbh, int nbw, int lane, size_t lplane, size_t hplane) {
+  const int D = 2 * Dl, H = 2 * Hl, W = 2 * Wl;
+  long long r = blk;
+  const int bw = (int)(r % nbw) - 1; r /= nbw;
+  const int bh = (int)(r % nbh) - 1; r /= nbh;
+  const int bd = (int)(r % nbd) - 1;
+  const int b = (int)(r / nbd);
+  const int v = lane >> 2, q = lane & 3;
+  const int a = v >> 2, bb = (v >> 1) & 1, c = v & 1;
+  const int oz = 2 * bd + 1 + a, oy = 2 * bh + 1 + bb, ox = 2 * bw + 1 + c;
+  u.valid = oz >= 0 && oz < D && oy >= 0 && oy < H && ox >= 0 && ox < W;
+  u.ooff = ((((size_t)b * D + (u.valid ? oz : 0)) * H + (u.valid ? oy : 0)) * W + (u.valid ? ox : 0)) * AT_C + q * 8;
+  u.c_hi = u.c_lo = make_uint4(0, 0, 0, 0);
+  if (u.valid) {
+    u.c_hi = *reinterpret_cast<const uint4*>(cost + u.ooff);
+    if (PLANES == 2) u.c_lo = *reinterpret_cast<const uint4*>(cost + hplane + u.ooff);
+  }
+  // corner (a,bb,c) of the block, clamped
+  const int iz = min(max(bd + a, 0), Dl - 1), iy = min(max(bh + bb, 0), Hl - 1), ix = min(max(bw + c, 0), Wl - 1);
+  const size_t koff = ((((size_t)b * Dl + iz) * Hl + iy) * Wl + ix) * AT_C + q * 8;
+  u.k_hi = *reinterpret_cast<const uint4*>(t + koff);
+  u.k_lo = make_uint4(0, 0, 0, 0);
+  if (PLANES == 2) u.k_lo = *reinterpret_cast<const uint4*>(t + lplane + koff);
+}
+
+template <int PLANES>
+__global__ void __launch_bounds__(UF_WARPS * 32, 2)
 upsample_fuse_kernel(const __nv_bfloat16* __restrict__ t, const __nv_bfloat16* __restrict__ cost,
                      const float* __restrict__ WcT, const float* __restrict__ scale, const float* __restrict__ shift,
                      __nv_bfloat16* __restrict__ y, int B, int Dl, int Hl, int Wl) {
-  __shared__ __align__(16) float cs[8][8][AT_C];    // [warp][voxel of the block][channel]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
-  float wreg[AT_C];
-#pragma unroll
-  for (int ci = 0; ci < AT_C; ++ci) wreg[ci] = __ldg(WcT + ci * AT_C + lane);
-  const float sc = __ldg(scale + lane), sh = __ldg(shift + lane);
-  const int D = 2 * Dl, H = 2 * Hl, W = 2 * Wl;
-  const size_t lplane = (size_t)B * Dl * Hl * Wl * AT_C, hplane = (size_t)B * D * H * W * AT_C;
+  __shared__ __align__(16) float ws[AT_C * AT_C];            // Wc transposed [ci][co]
+  __shared__ __align__(16) float cs[UF_WARPS][8][AT_C + 4];  // cost vectors  [warp][voxel][channel] (padded rows)
+  __shared__ __align__(16) float kn[UF_WARPS][8][AT_C + 4];  // corner vectors [warp][corner][channel]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int v = lane >> 2, q = lane & 3;
+  for (int i = threadIdx.x; i < AT_C * AT_C; i += blockDim.x) ws[i] = __ldg(WcT + i);
+  __shared__ __align__(16) float s_sc[AT_C], s_sh[AT_C];
+  if (threadIdx.x < AT_C) { s_sc[threadIdx.x] = __ldg(scale + threadIdx.x); s_sh[threadIdx.x] = __ldg(shift + threadIdx.x); }
+  __syncthreads();
+  const size_t lplane = (size_t)B * Dl * Hl * Wl * AT_C, hplane = lplane * 8;
   const int nbd = Dl + 1, nbh = Hl + 1, nbw = Wl + 1;
   const long long nblocks = (long long)B * nbd * nbh * nbw;
-  for (long long blk = (long long)blockIdx.x * warps + warp; blk < nblocks; blk += (long long)gridDim.x * warps) {
-    long long r = blk;
-    const int bw = (int)(r % nbw) - 1; r /= nbw;
-    const int bh = (int)(r % nbh) - 1; r /= nbh;
-    const int bd = (int)(r % nbd) - 1;
-    const int b = (int)(r / nbd);
-    // 8 low-res corners (clamped), this lane's channel
-    float cnr[2][2][2];
+  const int a = v >> 2, bb = (v >> 1) & 1, c = v & 1;
+  // output 2i+1 (first of the pair): .75*in[i] + .25*in[i+1];  output 2i+2: .25*in[i] + .75*in[i+1]
+  const float wz0 = a ? 0.25f : 0.75f, wy0 = bb ? 0.25f : 0.75f, wx0 = c ? 0.25f : 0.75f;
+  const long long stride = (long long)gridDim.x * UF_WARPS;
+  long long blk = (long long)blockIdx.x * UF_WARPS + warp;
+  UfBlock cur;
+  if (blk < nblocks) uf_fetch<PLANES>(cur, blk, t, cost, Dl, Hl, Wl, nbd, nbh, nbw, lane, lplane, hplane);
+  for (; blk < nblocks; blk += stride) {
+    UfBlock nxt;
+    const bool has_next = blk + stride < nblocks;
+    if (has_next) uf_fetch<PLANES>(nxt, blk + stride, t, cost, Dl, Hl, Wl, nbd, nbh, nbw, lane, lplane, hplane);
+    // ---- stage this block: cost octet of voxel v, corner octet of corner v ----
+    {
+      float f[8], g[8];
+      unpack8(cur.c_hi, f);
+      if (PLANES == 2) { unpack8(cur.c_lo, g);
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+        for (int j = 0; j < 8; ++j) f[j] += g[j]; }
+      float4* crow = reinterpret_cast<float4*>(&cs[warp][v][q * 8]);
+      crow[0] = make_float4(f[0], f[1], f[2], f[3]);
+      crow[1] = make_float4(f[4], f[5], f[6], f[7]);
+      unpack8(cur.k_hi, f);
+      if (PLANES == 2) { unpack8(cur.k_lo, g);
 #pragma unroll
-      for (int bb = 0; bb < 2; ++bb)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int iz = min(max(bd + a, 0), Dl - 1), iy = min(max(bh + bb, 0), Hl - 1),
-                    ix = min(max(bw + c, 0), Wl - 1);
-          const size_t off = ((((size_t)b * Dl + iz) * Hl + iy) * Wl + ix) * AT_C + lane;
-          float v = __bfloat162float(t[off]);
-          if (PLANES == 2) v += __bfloat162float(t[lplane + off]);
-          cnr[a][bb][c] = v;
-        }
-    // stage the 8 cost vectors of the block
-    float cval[8];
-    bool valid[8];
-#pragma unroll
-    for (int v = 0; v < 8; ++v) {
-      const int oz = 2 * bd + 1 + (v >> 2), oy = 2 * bh + 1 + ((v >> 1) & 1), ox = 2 * bw + 1 + (v & 1);
-      valid[v] = oz >= 0 && oz < D && oy >= 0 && oy < H && ox >= 0 && ox < W;
-      float cv = 0.f;
-      if (valid[v]) {
-        const size_t off = ((((size_t)b * D + oz) * H + oy) * W + ox) * AT_C + lane;
-        cv = __bfloat162float(cost[off]);
-        if (PLANES == 2) cv += __bfloat162float(cost[hplane + off]);
-      }
-      cval[v] = cv;
-      cs[warp][v][lane] = cv;
+        for (int j = 0; j < 8; ++j) f[j] += g[j]; }
+      float4* krow = reinterpret_cast<float4*>(&kn[warp][v][q * 8]);
+      krow[0] = make_float4(f[0], f[1], f[2], f[3]);
+      krow[1] = make_float4(f[4], f[5], f[6], f[7]);
     }
     __syncwarp();
+    // ---- trilinear blend of the 8 corners for this lane's voxel / octet ----
+    float up[8];
 #pragma unroll
-    for (int v = 0; v < 8; ++v) {
-      if (!valid[v]) continue;           // warp-uniform
-      const int a = v >> 2, bb = (v >> 1) & 1, c = v & 1;
-      // output 2i+1 (a==0): .75*in[i] + .25*in[i+1];  output 2i+2 (a==1): .25*in[i] + .75*in[i+1]
-      const float wz0 = a ? 0.25f : 0.75f, wy0 = bb ? 0.25f : 0.75f, wx0 = c ? 0.25f : 0.75f;
-      float up = 0.f;
+    for (int j = 0; j < 8; ++j) up[j] = 0.f;
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
+    for (int k = 0; k < 8; ++k) {
+      const float wgt = ((k >> 2) ? 1.f - wz0 : wz0) * (((k >> 1) & 1) ? 1.f - wy0 : wy0) * ((k & 1) ? 1.f - wx0 : wx0);
+      const float4 k0 = *reinterpret_cast<const float4*>(&kn[warp][k][q * 8]);
+      const float4 k1 = *reinterpret_cast<const float4*>(&kn[warp][k][q * 8 + 4]);
+      up[0] = fmaf(wgt, k0.x, up[0]); up[1] = fmaf(wgt, k0.y, up[1]); up[2] = fmaf(wgt, k0.z, up[2]);
+      up[3] = fmaf(wgt, k0.w, up[3]); up[4] = fmaf(wgt, k1.x, up[4]); up[5] = fmaf(wgt, k1.y, up[5]);
+      up[6] = fmaf(wgt, k1.z, up[6]); up[7] = fmaf(wgt, k1.w, up[7]);
+    }
+    // ---- 32x32 matvec: this lane's 8 output channels of its voxel ----
+    float acc[8];
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 #pragma unroll
-          for (int k = 0; k < 2; ++k)
-            up += (i ? 1.f - wz0 : wz0) * (j ? 1.f - wy0 : wy0) * (k ? 1.f - wx0 : wx0) * cnr[i][j][k];
-      float acc = 0.f;
+    for (int c4 = 0; c4 < AT_C; c4 += 4) {
+      const float4 xv = *reinterpret_cast<const float4*>(&cs[warp][v][c4]);
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-      for (int c4 = 0; c4 < AT_C; c4 += 4) {
-        const float4 xv = *reinterpret_cast<const float4*>(&cs[warp][v][c4]);
-        acc = fmaf(xv.x, wreg[c4], acc); acc = fmaf(xv.y, wreg[c4 + 1], acc);
-        acc = fmaf(xv.z, wreg[c4 + 2], acc); acc = fmaf(xv.w, wreg[c4 + 3], acc);
+      for (int u = 0; u < 4; ++u) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&ws[(c4 + u) * AT_C + q * 8]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&ws[(c4 + u) * AT_C + q * 8 + 4]);
+        acc[0] = fmaf(xs[u], w0.x, acc[0]); acc[1] = fmaf(xs[u], w0.y, acc[1]);
+        acc[2] = fmaf(xs[u], w0.z, acc[2]); acc[3] = fmaf(xs[u], w0.w, acc[3]);
+        acc[4] = fmaf(xs[u], w1.x, acc[4]); acc[5] = fmaf(xs[u], w1.y, acc[5]);
+        acc[6] = fmaf(xs[u], w1.z, acc[6]); acc[7] = fmaf(xs[u], w1.w, acc[7]);
       }
-      const float o = (up + acc) * sc + sh;
-      const int oz = 2 * bd + 1 + a, oy = 2 * bh + 1 + bb, ox = 2 * bw + 1 + c;
-      const size_t off = ((((size_t)b * D + oz) * H + oy) * W + ox) * AT_C + lane;
-      uint32_t lo;
-      const uint32_t hi = split_bf16(o, lo);
-      y[off] = __ushort_as_bfloat16((unsigned short)hi);
-      if (PLANES == 2) y[hplane + off] = __ushort_as_bfloat16((unsigned short)lo);
+    }
+    if (cur.valid) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (up[j] + acc[j]) * s_sc[q * 8 + j] + s_sh[q * 8 + j];
+      store8<PLANES>(y, hplane, cur.ooff, o);
     }
     __syncwarp();
+    cur = nxt;
   }
 }
 
@@ -520,7 +562,7 @@ extern "C" int dca_upsample_fuse(const void* t, const void* cost, const float* W
   if (!t || !cost || !WcT || !scale || !shift || !y || planes < 1 || planes > 2 || B <= 0) return DCA_ERR_ARG;
   if (C != AT_C) return DCA_ERR_UNSUPPORTED;
   const long long nblocks = (long long)B * (Dl + 1) * (Hl + 1) * (Wl + 1);
-  int grid = (int)((nblocks + 7) / 8 < 148 * 8 ? (nblocks + 7) / 8 : 148 * 8);
+  int grid = (int)((nblocks + 7) / 8 < 148 * 12 ? (nblocks + 7) / 8 : 148 * 12);
   cudaStream_t st = (cudaStream_t)stream;
   if (planes == 2)
     upsample_fuse_kernel<2><<<grid, 256, 0, st>>>((const __nv_bfloat16*)t, (const __nv_bfloat16*)cost, WcT, scale,

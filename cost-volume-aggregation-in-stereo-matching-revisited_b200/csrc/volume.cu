@@ -25,15 +25,35 @@ constexpr int VOL_TW = 16;   // columns per CTA
 constexpr int VOL_DC = 48;   // disparities per CTA
 constexpr int VOL_THREADS = 256;
 
-template <int PLANES>
+// 4-byte async global->shared copy (LDGSTS); src_size 0 zero-fills the destination (out-of-image columns)
+__device__ __forceinline__ void cp_async4(float* dst, const float* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src),
+               "r"(valid ? 4 : 0)
+               : "memory");
+}
+
+__device__ __forceinline__ void vol_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// CVT = compile-time channel pitch of the volume (64 for DCANet's 40 groups + 2x12 concat); 0 = runtime Cv.
+// GT / CPGT = compile-time group count / channels per group (40 / 8 for DCANet); 0 = runtime.  With them fixed
+// every shared-memory offset of the inner product loop is an immediate and the channel loop unrolls fully.
+template <int PLANES, int CVT, int GT, int CPGT>
 __global__ void __launch_bounds__(VOL_THREADS, 2)
 volume_fused_kernel(const float* __restrict__ gl, const float* __restrict__ gr,
                     const float* __restrict__ cl, const float* __restrict__ cr,
-                    __nv_bfloat16* __restrict__ vol, int B, int C, int G, int Cc, int D, int H, int W, int Cv) {
+                    __nv_bfloat16* __restrict__ vol, int B, int C, int G_rt, int Cc, int D, int H, int W, int Cv_rt) {
   extern __shared__ float smem[];
-  const int cpg = C / G;
+  const int Cv = CVT ? CVT : Cv_rt;
+  const int G = GT ? GT : G_rt;
+  const int cpg = CPGT ? CPGT : C / G;
   const int gp = G + 1;                       // pitch of the group axis (bank-conflict-free transposing stores)
-  const int UW = VOL_TW + VOL_DC - 1;         // right window width
+  constexpr int UW = VOL_TW + VOL_DC - 1;     // right window width (63)
   float* Ls = smem;                           // [cpg][TW][gp]
   float* Rs = Ls + cpg * VOL_TW * gp;         // [cpg][UW][gp]
   float* cLs = Rs + cpg * UW * gp;            // [Cc][TW]
@@ -47,41 +67,46 @@ volume_fused_kernel(const float* __restrict__ gl, const float* __restrict__ gr,
   const int dcount = min(VOL_DC, D - d0);
   const int u0 = w0 - (d0 + VOL_DC - 1);      // image column of window index 0
   const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
   const size_t HW = (size_t)H * W;
 
-  // ---- stage: coalesced along w in global, transposed into [c][w][g] in smem ----
+  // ---- stage: coalesced along w in global, transposed into [c][w][g] in smem (no div/mod in the loops) ----
   {
+    // all copies are asynchronous (no register round trip): every thread has ~100 loads in flight at once
     const float* src = gl + ((size_t)b * C * H + h) * W;   // + ch*HW + w
     for (int i = tid; i < C * VOL_TW; i += VOL_THREADS) {
-      int ch = i / VOL_TW, wl = i % VOL_TW, w = w0 + wl;
-      float v = (w < W) ? __ldg(src + (size_t)ch * HW + w) : 0.f;
-      Ls[((ch % cpg) * VOL_TW + wl) * gp + ch / cpg] = v;
+      const int ch = i / VOL_TW, wl = i % VOL_TW, w = w0 + wl;
+      const bool ok = w < W;
+      cp_async4(&Ls[((ch % cpg) * VOL_TW + wl) * gp + ch / cpg], ok ? src + (size_t)ch * HW + w : src, ok);
     }
     const float* srcr = gr + ((size_t)b * C * H + h) * W;
     for (int i = tid; i < C * UW; i += VOL_THREADS) {
-      int ch = i / UW, ul = i % UW, u = u0 + ul;
-      float v = (u >= 0 && u < W) ? __ldg(srcr + (size_t)ch * HW + u) : 0.f;
-      Rs[((ch % cpg) * UW + ul) * gp + ch / cpg] = v;
+      const int ch = i / UW, ul = i % UW, u = u0 + ul;
+      const bool ok = u >= 0 && u < W;
+      cp_async4(&Rs[((ch % cpg) * UW + ul) * gp + ch / cpg], ok ? srcr + (size_t)ch * HW + u : srcr, ok);
     }
     if (Cc > 0) {
       const float* s2 = cl + ((size_t)b * Cc * H + h) * W;
       for (int i = tid; i < Cc * VOL_TW; i += VOL_THREADS) {
-        int ch = i / VOL_TW, wl = i % VOL_TW, w = w0 + wl;
-        cLs[i] = (w < W) ? __ldg(s2 + (size_t)ch * HW + w) : 0.f;
+        const int ch = i / VOL_TW, wl2 = i % VOL_TW, w = w0 + wl2;
+        const bool ok = w < W;
+        cp_async4(&cLs[i], ok ? s2 + (size_t)ch * HW + w : s2, ok);
       }
       const float* s3 = cr + ((size_t)b * Cc * H + h) * W;
       for (int i = tid; i < Cc * UW; i += VOL_THREADS) {
-        int ch = i / UW, ul = i % UW, u = u0 + ul;
-        cRs[i] = (u >= 0 && u < W) ? __ldg(s3 + (size_t)ch * HW + u) : 0.f;
+        const int ch = i / UW, ul = i % UW, u = u0 + ul;
+        const bool ok = u >= 0 && u < W;
+        cp_async4(&cRs[i], ok ? s3 + (size_t)ch * HW + u : s3, ok);
       }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   }
   __syncthreads();
 
-  const int warp = tid >> 5, lane = tid & 31;
   const float inv_cpg = 1.0f / (float)cpg;
   const size_t plane_stride = (size_t)B * D * H * W * Cv;
   const int n_wt = VOL_TW / 4, n_dt = (dcount + 7) / 8;
+  const int odd = lane & 1;
 
   for (int t = warp; t < n_wt * n_dt; t += VOL_THREADS / 32) {
     const int wt = (t % n_wt) * 4;            // local column of the 4-wide tile
@@ -98,7 +123,8 @@ volume_fused_kernel(const float* __restrict__ gl, const float* __restrict__ gr,
         for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
 
       if (slot < G) {
-        for (int c = 0; c < cpg; ++c) {
+#pragma unroll
+        for (int c = 0; c < (CPGT ? CPGT : cpg); ++c) {
           float l[4], r[11];
           const float* lp = Ls + (c * VOL_TW + wt) * gp + slot;
           const float* rp = Rs + (c * UW + ubase) * gp + slot;
@@ -129,28 +155,27 @@ volume_fused_kernel(const float* __restrict__ gl, const float* __restrict__ gr,
 #pragma unroll
           for (int i = 0; i < 4; ++i) acc[j][i] = cRs[cc * UW + ubase + (i - j + 7)];
       }
-      // ---- bf16 split, pair exchange, 32-bit stores: even lane stores column i of the pair
-      //      (i, i+1) ... we pair voxels (j, i) and (j, i+1) ----
+      // ---- pair exchange (even lane keeps column ip, odd lane column ip+1), packed bf16 split, 32-bit stores ----
+      const int ch = slot & ~1;
+      const bool ch_ok = ch < Cv;
+      // this lane's column inside each pair is ip + odd
+      __nv_bfloat16* colp = vol + ((((size_t)b * D + d0 + dt) * H + h) * W + (w0 + wt + odd)) * Cv + ch;
+      const size_t dstep = HW * Cv;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
+        const bool d_ok = (dt + j) < dcount;
 #pragma unroll
         for (int ip = 0; ip < 4; ip += 2) {
-          float mine_a = acc[j][ip], mine_b = acc[j][ip + 1];
-          float send = (lane & 1) ? mine_a : mine_b;          // odd lanes give away voxel a, even give b
-          float got = __shfl_xor_sync(0xffffffffu, send, 1);
-          // even lane: voxel a, channels (slot, slot+1) = (mine_a, got)
-          // odd  lane: voxel b, channels (slot-1, slot) = (got, mine_b)
-          float lo_ch = (lane & 1) ? got : mine_a;
-          float hi_ch = (lane & 1) ? mine_b : got;
-          const int i = ip + (lane & 1);
-          const int w = w0 + wt + i, d = d0 + dt + j;
-          const int ch = slot & ~1;
-          if (w < W && d < D && (dt + j) < dcount && ch < Cv) {
-            uint32_t l0, l1;
-            uint32_t h0 = split_bf16(lo_ch, l0), h1 = split_bf16(hi_ch, l1);
-            size_t off = ((((size_t)b * D + d) * H + h) * W + w) * Cv + ch;
-            *reinterpret_cast<uint32_t*>(vol + off) = h0 | (h1 << 16);
-            if (PLANES == 2) *reinterpret_cast<uint32_t*>(vol + plane_stride + off) = l0 | (l1 << 16);
+          const float mine_a = acc[j][ip], mine_b = acc[j][ip + 1];
+          const float got = __shfl_xor_sync(0xffffffffu, odd ? mine_a : mine_b, 1);
+          // even lane: voxel a, channels (slot, slot+1) = (mine_a, got); odd lane: voxel b, (slot-1, slot) = (got, mine_b)
+          const float lo_ch = odd ? got : mine_a, hi_ch = odd ? mine_b : got;
+          if (d_ok && ch_ok && (w0 + wt + ip + odd) < W) {
+            uint32_t hw, lw;
+            vol_split2(lo_ch, hi_ch, hw, lw);
+            __nv_bfloat16* dst = colp + (size_t)j * dstep + ip * Cv;
+            *reinterpret_cast<uint32_t*>(dst) = hw;
+            if (PLANES == 2) *reinterpret_cast<uint32_t*>(dst + plane_stride) = lw;
           }
         }
       }
@@ -229,15 +254,24 @@ extern "C" int dca_volume_gwc_concat(const float* gwc_l, const float* gwc_r, con
   const int wtiles = (W + VOL_TW - 1) / VOL_TW, dchunks = (D + VOL_DC - 1) / VOL_DC;
   dim3 grid(wtiles * dchunks, H, B);
   cudaStream_t st = (cudaStream_t)stream;
-  if (planes == 2) {
-    cudaFuncSetAttribute(volume_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    volume_fused_kernel<2><<<grid, VOL_THREADS, smem, st>>>(gwc_l, gwc_r, cat_l, cat_r, (__nv_bfloat16*)vol, B, C, G,
-                                                             Cc, D, H, W, Cv);
-  } else {
-    cudaFuncSetAttribute(volume_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    volume_fused_kernel<1><<<grid, VOL_THREADS, smem, st>>>(gwc_l, gwc_r, cat_l, cat_r, (__nv_bfloat16*)vol, B, C, G,
-                                                             Cc, D, H, W, Cv);
-  }
+#define DCA_VOL_LAUNCH(P, CVT)                                                                                   \
+  do {                                                                                                           \
+    auto kern = volume_fused_kernel<P, CVT, GT_, CPG_>;                                                          \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
+    kern<<<grid, VOL_THREADS, smem, st>>>(gwc_l, gwc_r, cat_l, cat_r, (__nv_bfloat16*)vol, B, C, G, Cc, D, H, W, Cv); \
+  } while (0)
+  const bool dcanet_shape = (Cv == 64 && G == 40 && cpg == 8);
+#define GT_ 40
+#define CPG_ 8
+  if (dcanet_shape) { if (planes == 2) DCA_VOL_LAUNCH(2, 64); else DCA_VOL_LAUNCH(1, 64); }
+#undef GT_
+#undef CPG_
+#define GT_ 0
+#define CPG_ 0
+  else { if (planes == 2) DCA_VOL_LAUNCH(2, 0); else DCA_VOL_LAUNCH(1, 0); }
+#undef GT_
+#undef CPG_
+#undef DCA_VOL_LAUNCH
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }

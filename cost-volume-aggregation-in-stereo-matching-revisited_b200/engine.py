@@ -119,12 +119,13 @@ def pack_convbn(seq, transposed=False):
 class Options:
     use_tc = True                 # route eligible convs to the tcgen05 kernels
     tc_modes = {0, 1, 2, 3}       # conv modes the tcgen05 kernel takes (K3S1, K3S2, T3S2, K1)
+    fuse_upsample_in_conv = True  # cva fuse stage: fold the trilinear upsample into the 1x1x1 conv's epilogue
 
 
 def conv(x: Planes, pc: PackedConv, mode=K3S1, act=ACT_NONE, res_pre: Planes = None, res_post: Planes = None,
-         planes_out=None, out_fp32=False):
-    """y = act(scale*conv(x)+shift + res_pre) + res_post.  Returns Planes, or an fp32 channels-last
-    tensor [B,D,H,W,Cout] when out_fp32."""
+         planes_out=None, out_fp32=False, up: Planes = None):
+    """y = act(scale*(conv(x) + trilinear_x2(up)) + shift + res_pre) + res_post.  Returns Planes, or an fp32
+    channels-last tensor [B,D,H,W,Cout] when out_fp32.  `up` needs the tcgen05 kernel."""
     assert x.C == pc.cin, (x.C, pc.cin)
     if mode == K3S2:
         Do, Ho, Wo = (x.D + 1) // 2, (x.H + 1) // 2, (x.W + 1) // 2
@@ -148,8 +149,11 @@ def conv(x: Planes, pc: PackedConv, mode=K3S1, act=ACT_NONE, res_pre: Planes = N
             and tc_supported(mode, pc.cin, pc.cout)):
         _lib.call("dca_conv3d_tc", mode, x.ptr, x.planes, pc.w_tc.data_ptr(), _ptr(pc.scale), _ptr(pc.shift),
                   res_pre.ptr if res_pre is not None else 0, res_post.ptr if res_post is not None else 0, planes_res,
+                  up.ptr if up is not None else 0, up.planes if up is not None else 1,
                   yptr, planes_out, act, x.B, pc.cin, pc.cout, x.D, x.H, x.W, Do, Ho, Wo, _stream())
         return y
+    if up is not None:
+        raise _lib.DcaError("conv(..., up=) is only implemented by the tcgen05 kernel")
     _lib.call("dca_conv3d_direct", mode, x.ptr, x.planes, pc.w.data_ptr(), _ptr(pc.scale), _ptr(pc.shift),
               res_pre.ptr if res_pre is not None else 0, res_post.ptr if res_post is not None else 0, planes_res,
               yptr, planes_out, 1 if out_fp32 else 0, act, x.B, pc.cin, pc.cout, pc.cout_pad, x.D, x.H, x.W, Do, Ho,
@@ -169,12 +173,13 @@ def conv_cout1(x: Planes, w27: torch.Tensor):
 
 
 def pack_cout1(weight):
-    """[1,Cin,3,3,3] -> [27][Cin] fp32 (uses the generic packer: taps x Cin x CoutPad with CoutPad=1)."""
+    """[1,Cin,3,3,3] -> HOST tensor [27][Cin] fp32 (the kernel takes these 864 weights as launch parameters).
+    Packed on the device by the generic packer (taps x Cin x CoutPad with CoutPad=1), copied back once at load."""
     w = weight.detach().contiguous().float()
     ci = w.shape[1]
     out = torch.empty((27, ci), dtype=torch.float32, device=w.device)
     _lib.call("dca_pack_weights", w.data_ptr(), 0, 1, ci, 27, out.data_ptr(), 1, _stream())
-    return out
+    return out.cpu().contiguous()
 
 
 def avgpool(x: Planes):
@@ -270,6 +275,8 @@ class PackedCva:
         fuse_w = m.fuse[0][0].weight                      # [32, 64, 1,1,1]: in = cat(aug, cost)
         self.attn = PackedAttention(m.slc_net.cross_attention, fuse_w)
         pc_c = PackedConv(fuse_w.detach()[:, 32:].contiguous(), m.fuse[0][1])
+        pc_c.pack_tc(planes)
+        self.fuse_c = pc_c                                # cost half of the fuse conv (+ the fuse BN)
         self.fuse_wcT = pc_c.w.view(32, 32).contiguous()  # [ci][co]
         self.fuse_scale, self.fuse_shift = pc_c.scale, pc_c.shift
         agg = m.cost_agg
@@ -290,7 +297,11 @@ def cva_forward(pk: PackedCva, cost: Planes, res_post: Planes = None, keep=None)
     logits = conv_cout1(h, pk.cls2)
     cls, e, S = class_stats(logits)
     t = disp_attention(cost_down, cls, e, S, pk.attn.buf, pk.attn.has_wa)
-    fused = upsample_fuse(t, cost, pk.fuse_wcT, pk.fuse_scale, pk.fuse_shift)
+    if Options.use_tc and Options.fuse_upsample_in_conv and tc_supported(K1, 32, 32):
+        # trilinear x2 + cat + 1x1x1 fuse + BN as ONE tcgen05 conv: Wc.cost by MMA, up(t) added in the epilogue
+        fused = conv(cost, pk.fuse_c, K1, ACT_NONE, up=t)
+    else:
+        fused = upsample_fuse(t, cost, pk.fuse_wcT, pk.fuse_scale, pk.fuse_shift)
     c1 = conv(fused, pk.conv1, K3S2, ACT_RELU)
     c2 = conv(c1, pk.conv2, K3S1, ACT_RELU)
     redir = conv(fused, pk.redir, K1, ACT_NONE)
