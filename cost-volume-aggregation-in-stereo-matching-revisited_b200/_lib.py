@@ -22,8 +22,8 @@ SIGNATURES = {
     "dca_conv3d_direct": [_c_int, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _c_int, _c_int, _c_int]
                          + [_c_int] * 10 + [_vp],
     "dca_conv3d_cout1": [_vp, _c_int, _vp, _vp] + [_c_int] * 5 + [_vp],
-    "dca_conv3d_tc": [_c_int, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _c_int, _vp, _c_int, _c_int]
-                     + [_c_int] * 9 + [_vp],
+    "dca_conv3d_tc": [_c_int, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _c_int, _vp, _c_int, _vp, _c_int,
+                      _c_int] + [_c_int] * 9 + [_vp],
     "dca_pack_weights_tc": [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp],
     "dca_pack_weights_tc_bytes": [_c_int] * 4,
     "dca_tc_set_halo": [_c_int],
@@ -96,6 +96,8 @@ def call(name, *args):
         if name in ("dca_conv3d_tc", "dca_conv3d_direct"):
             ints = [x for x in args if isinstance(x, int) and 0 < x < 4096]
             label = f"{name} mode={args[0]} dims={args[-10:-1] if name == 'dca_conv3d_tc' else args[-11:-1]}"
+            if name == 'dca_conv3d_tc':
+                label += (' +up' if args[9] else '') + (' +side' if args[11] else '')
         PROFILE.append((label, a, b))
         if rc != 0:
             raise DcaError(f"{name} failed: {ERRORS.get(rc, rc)}")

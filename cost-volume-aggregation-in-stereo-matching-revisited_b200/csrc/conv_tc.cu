@@ -29,10 +29,11 @@ namespace dca {
 
 constexpr int TC_TW = 8, TC_TH = 16, TC_M = 128;
 constexpr int TC_THREADS = 320;       // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int TC_MAX_TAPS = 27;
+constexpr int TC_MAX_TAPS = 36;       // 27 + one fused 1x1x1 side tap per transposed-conv parity class
 
 struct TcMaps {
-  CUtensorMap a[8];   // input views (index = parity class for stride-2 convs, else only [0])
+  CUtensorMap a[9];   // input views: [0..7] parity classes of stride-2 convs (else only [0]); for the transposed conv
+                      // with a fused 1x1x1 side input, [1+c] = parity view c of that side input
   CUtensorMap w;      // packed weights [taps*planes*Cout rows][Cin]
 };
 
@@ -673,14 +674,15 @@ static EncodeTiledFn get_encode() {
 
 // 5-D view of cost planes: dims (C, W, H, D, planes*B) with arbitrary element strides per axis
 static bool make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int D, int NB, size_t sW, size_t sH,
-                         size_t sD, size_t sB, int box_w = TC_TW, int box_h = TC_TH) {
+                         size_t sD, size_t sB, int box_w = TC_TW, int box_h = TC_TH, int box_c = 0) {
+  if (box_c == 0) box_c = C;   // box_c > C: the extra channels are out of bounds -> zero filled
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)NB};
   cuuint64_t strides[4] = {sW * 2, sH * 2, sD * 2, sB * 2};
-  cuuint32_t box[5] = {(cuuint32_t)C, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
+  cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  CUtensorMapSwizzle sw = (C * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMapSwizzle sw = (box_c * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
              CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -776,8 +778,12 @@ extern "C" int dca_pack_weights_tc(const float* w, int transposed, int Co, int C
 // mode: DCA_CONV_K3S1 (0), DCA_CONV_K3S2 (1), DCA_CONV_T3S2 (2), DCA_CONV_K1 (3)
 extern "C" int dca_conv3d_tc(int mode, const void* x, int planes_in, const void* w_tc, const float* scale,
                              const float* shift, const void* res_pre, const void* res_post, int planes_res,
-                             const void* up, int planes_up, void* y, int planes_out, int act, int B, int Cin, int Cout,
-                             int Di, int Hi, int Wi, int Do, int Ho, int Wo, void* stream) {
+                             const void* up, int planes_up, const void* side, int side_c, void* y, int planes_out,
+                             int act, int B, int Cin, int Cout, int Di, int Hi, int Wi, int Do, int Ho, int Wo,
+                             void* stream) {
+  // side (optional, transposed conv only): cost planes [P][B][Do][Ho][Wo][side_c] whose 1x1x1 conv is accumulated into
+  // the same GEMM; its weights are tap 27 of w_tc ([planes][Cout][Cin], zero padded beyond side_c).
+  if (side && (mode != 2 || side_c <= 0 || side_c > Cin || (side_c % 8) != 0)) return DCA_ERR_ARG;
   if (up && (Cout != 32 || (Do & 1) || (Ho & 1) || (Wo & 1) || planes_up < 1 || planes_up > 2)) return DCA_ERR_ARG;
   if (!x || !w_tc || !y || B <= 0 || planes_in < 1 || planes_in > 2 || planes_out < 1 || planes_out > 2)
     return DCA_ERR_ARG;
@@ -798,7 +804,7 @@ extern "C" int dca_conv3d_tc(int mode, const void* x, int planes_in, const void*
   p.npart = P; p.ngrp = 1; p.lo_sep = 0; p.dbg = g_dbg;
   p.up = (const __nv_bfloat16*)up; p.planes_up = planes_up;
   const size_t sW = Cin, sH = (size_t)Wi * Cin, sD = (size_t)Hi * Wi * Cin, sB = (size_t)Di * Hi * Wi * Cin;
-  const int ntaps_total = (mode == 3) ? 1 : 27;
+  const int ntaps_total = (mode == 3) ? 1 : (side ? 28 : 27);
   if (!make_w_map(&maps.w, w_tc, Cin, ntaps_total * P * Cout, P * Cout)) return DCA_ERR_LAUNCH;
 
   p.ncls = 1;
@@ -887,12 +893,21 @@ extern "C" int dca_conv3d_tc(int mode, const void* x, int planes_in, const void*
     }
     return run();
   }
-  // mode 2: transposed conv, one launch per output parity class (o = 2i - 1 + k)
+  // mode 2: transposed conv (o = 2i - 1 + k): the 8 output parity classes partition the 27 taps; one launch
   if (!make_act_map(&maps.a[0], x, Cin, Wi, Hi, Di, P * B, sW, sH, sD, sB)) return DCA_ERR_LAUNCH;
-  for (int i = 1; i < 8; ++i) maps.a[i] = maps.a[0];
+  for (int i = 1; i < 9; ++i) maps.a[i] = maps.a[0];
+  if (side) {   // parity views of the side input at the OUTPUT resolution: class c reads side[2t + parity(c)]
+    const size_t qW = side_c, qH = (size_t)Wo * side_c, qD = (size_t)Ho * Wo * side_c, qB = (size_t)Do * Ho * Wo * side_c;
+    for (int pc = 0; pc < 8; ++pc) {
+      const int pz = (pc >> 2) & 1, py = (pc >> 1) & 1, px = pc & 1;
+      const __nv_bfloat16* base = (const __nv_bfloat16*)side + pz * qD + py * qH + px * qW;
+      if (!make_act_map(&maps.a[1 + pc], base, side_c, Wi, Hi, Di, P * B, 2 * qW, 2 * qH, 2 * qD, qB, TC_TW, TC_TH, Cin))
+        return DCA_ERR_LAUNCH;
+    }
+  }
   p.Dt = Di; p.Ht = Hi; p.Wt = Wi; p.out_stride = 2;
   p.ncls = 8; p.ntaps = 0;
-  for (int pc = 0; pc < 8; ++pc) {           // the 8 output parity classes partition the 27 taps
+  for (int pc = 0; pc < 8; ++pc) {
     const int par[3] = {(pc >> 2) & 1, (pc >> 1) & 1, pc & 1};
     p.cls_tap0[pc] = (unsigned char)p.ntaps;
     for (int a = 0; a < 3; ++a) p.cls_off[pc][a] = (signed char)par[a];
@@ -904,6 +919,11 @@ extern "C" int dca_conv3d_tc(int mode, const void* x, int planes_in, const void*
       const int t = p.ntaps++;
       p.tap_off[t][0] = (signed char)off[0]; p.tap_off[t][1] = (signed char)off[1]; p.tap_off[t][2] = (signed char)off[2];
       p.tap_map[t] = 0; p.tap_w[t] = (signed char)((kd * 3 + kh) * 3 + kw);
+    }
+    if (side) {
+      const int t = p.ntaps++;
+      p.tap_off[t][0] = p.tap_off[t][1] = p.tap_off[t][2] = 0;
+      p.tap_map[t] = (signed char)(1 + pc); p.tap_w[t] = 27;
     }
   }
   p.cls_tap0[8] = (unsigned char)p.ntaps;

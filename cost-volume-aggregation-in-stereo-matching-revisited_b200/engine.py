@@ -120,10 +120,11 @@ class Options:
     use_tc = True                 # route eligible convs to the tcgen05 kernels
     tc_modes = {0, 1, 2, 3}       # conv modes the tcgen05 kernel takes (K3S1, K3S2, T3S2, K1)
     fuse_upsample_in_conv = True  # cva fuse stage: fold the trilinear upsample into the 1x1x1 conv's epilogue
+    fuse_redir_in_deconv = True   # Multi_Aggregation: conv3 (transposed) + redir (1x1x1) as one GEMM
 
 
 def conv(x: Planes, pc: PackedConv, mode=K3S1, act=ACT_NONE, res_pre: Planes = None, res_post: Planes = None,
-         planes_out=None, out_fp32=False, up: Planes = None):
+         planes_out=None, out_fp32=False, up: Planes = None, side: Planes = None):
     """y = act(scale*(conv(x) + trilinear_x2(up)) + shift + res_pre) + res_post.  Returns Planes, or an fp32
     channels-last tensor [B,D,H,W,Cout] when out_fp32.  `up` needs the tcgen05 kernel."""
     assert x.C == pc.cin, (x.C, pc.cin)
@@ -150,10 +151,11 @@ def conv(x: Planes, pc: PackedConv, mode=K3S1, act=ACT_NONE, res_pre: Planes = N
         _lib.call("dca_conv3d_tc", mode, x.ptr, x.planes, pc.w_tc.data_ptr(), _ptr(pc.scale), _ptr(pc.shift),
                   res_pre.ptr if res_pre is not None else 0, res_post.ptr if res_post is not None else 0, planes_res,
                   up.ptr if up is not None else 0, up.planes if up is not None else 1,
+                  side.ptr if side is not None else 0, side.C if side is not None else 0,
                   yptr, planes_out, act, x.B, pc.cin, pc.cout, x.D, x.H, x.W, Do, Ho, Wo, _stream())
         return y
-    if up is not None:
-        raise _lib.DcaError("conv(..., up=) is only implemented by the tcgen05 kernel")
+    if up is not None or side is not None:
+        raise _lib.DcaError("conv(..., up=/side=) is only implemented by the tcgen05 kernel")
     _lib.call("dca_conv3d_direct", mode, x.ptr, x.planes, pc.w.data_ptr(), _ptr(pc.scale), _ptr(pc.shift),
               res_pre.ptr if res_pre is not None else 0, res_post.ptr if res_post is not None else 0, planes_res,
               yptr, planes_out, 1 if out_fp32 else 0, act, x.B, pc.cin, pc.cout, pc.cout_pad, x.D, x.H, x.W, Do, Ho,
@@ -287,6 +289,33 @@ class PackedCva:
         for pc in (self.down, self.cls0, self.conv1, self.conv2, self.redir):
             pc.pack_tc(planes)
         self.conv3.pack_tc(planes, transposed=True)
+        self.conv3_fused = _pack_deconv_with_redir(agg, self.conv3, self.redir, planes)
+
+
+class _FusedDeconv:
+    """conv3 (ConvTranspose3d 64->32 + BN) and redir (1x1x1 32->32 + BN) of Multi_Aggregation as ONE GEMM:
+    s3*deconv + b3 + sr*(Wr x) + br = s3*(deconv + (diag(sr/s3) Wr) x) + (b3 + br): 27 deconv taps + a 28th
+    tap holding diag(sr/s3) Wr zero-padded from 32 to 64 input channels."""
+
+    def __init__(self, w_tc, scale, shift, planes):
+        self.w_tc, self.scale, self.shift, self.tc_planes = w_tc, scale, shift, planes
+        self.cin, self.cout = 64, 32
+
+
+def _pack_deconv_with_redir(agg, pc3, pcr, planes):
+    s3, sr = pc3.scale[:32], pcr.scale[:32]
+    if pc3.w_tc is None or bool((s3.abs() < 1e-12).any()):
+        return None                                   # a zero BN scale cannot be divided out: keep the two kernels
+    lib = _lib.load()
+    per_tap = lib.dca_pack_weights_tc_bytes(32, 64, 1, planes)
+    buf = torch.empty(28 * per_tap, dtype=torch.uint8, device=pc3.w.device)
+    buf[:27 * per_tap].copy_(pc3.w_tc)
+    wr = agg.redir[0].weight.detach().float().view(32, 32) * (sr / s3).view(32, 1)      # [co][ci]
+    wr64 = torch.zeros((32, 64, 1, 1, 1), dtype=torch.float32, device=wr.device)
+    wr64[:, :32, 0, 0, 0] = wr
+    _lib.call("dca_pack_weights_tc", wr64.data_ptr(), 0, 32, 64, 1, buf[27 * per_tap:].data_ptr(), planes, _stream())
+    torch.cuda.current_stream().synchronize()        # wr64 is a temporary
+    return _FusedDeconv(buf, pc3.scale, (pc3.shift + pcr.shift).contiguous(), planes)
 
 
 def cva_forward(pk: PackedCva, cost: Planes, res_post: Planes = None, keep=None):
@@ -304,8 +333,18 @@ def cva_forward(pk: PackedCva, cost: Planes, res_post: Planes = None, keep=None)
         fused = upsample_fuse(t, cost, pk.fuse_wcT, pk.fuse_scale, pk.fuse_shift)
     c1 = conv(fused, pk.conv1, K3S2, ACT_RELU)
     c2 = conv(c1, pk.conv2, K3S1, ACT_RELU)
-    redir = conv(fused, pk.redir, K1, ACT_NONE)
-    out = conv(c2, pk.conv3, T3S2, ACT_RELU, res_pre=redir, res_post=res_post)
+    fd = pk.conv3_fused
+    if Options.use_tc and Options.fuse_redir_in_deconv and fd is not None and fd.tc_planes == c2.planes \
+            and tc_supported(T3S2, 64, 32):
+        # ReLU(BN(deconv(c2)) + BN(redir(fused))) (+ res_post) as one tcgen05 GEMM with a 28th, 1x1x1 tap
+        out = Planes(c2.B, 2 * c2.D, 2 * c2.H, 2 * c2.W, 32, c2.planes, c2.t.device)
+        _lib.call("dca_conv3d_tc", T3S2, c2.ptr, c2.planes, fd.w_tc.data_ptr(), fd.scale.data_ptr(),
+                  fd.shift.data_ptr(), 0, res_post.ptr if res_post is not None else 0,
+                  res_post.planes if res_post is not None else 1, 0, 1, fused.ptr, fused.C, out.ptr, c2.planes,
+                  ACT_RELU, c2.B, 64, 32, c2.D, c2.H, c2.W, out.D, out.H, out.W, _stream())
+    else:
+        redir = conv(fused, pk.redir, K1, ACT_NONE)
+        out = conv(c2, pk.conv3, T3S2, ACT_RELU, res_pre=redir, res_post=res_post)
     if keep is not None:
         keep.update(cost_down=cost_down, logits=logits, class_map=cls, e=e, S=S, t=t, fused=fused, out=out)
     return logits, out

@@ -65,11 +65,13 @@ int dca_conv3d_cout1(const void* x, int planes_in, const float* w_host, float* y
 /* tcgen05/TMEM/TMA implicit-GEMM member of the family (conv_tc.cu), modes K3S1 / K3S2 / T3S2 / K1, Cin,Cout in {32,64}:
  *   y = act(scale * (conv(x, w) + trilinear_x2(up)) + shift + res_pre) + res_post
  * w_tc = bf16 operand pack from dca_pack_weights_tc; `up` (optional, Cout == 32) is a cost-plane tensor at half the
- * output resolution: the trilinear x2 + cat + 1x1x1 fuse of cva.py:64,69 folded into the epilogue. */
+ * output resolution: the trilinear x2 + cat + 1x1x1 fuse of cva.py:64,69 folded into the epilogue.
+ * `side` (optional, T3S2 only) is a cost-plane tensor [.., Do,Ho,Wo, side_c] whose 1x1x1 conv (weights = tap 27 of
+ * w_tc, zero padded to Cin) joins the same GEMM: Multi_Aggregation's conv3 + redir (cva.py:20-29) in one kernel. */
 int dca_conv3d_tc(int mode, const void* x, int planes_in, const void* w_tc, const float* scale, const float* shift,
-                  const void* res_pre, const void* res_post, int planes_res, const void* up, int planes_up, void* y,
-                  int planes_out, int act, int B, int Cin, int Cout, int Di, int Hi, int Wi, int Do, int Ho, int Wo,
-                  void* stream);
+                  const void* res_pre, const void* res_post, int planes_res, const void* up, int planes_up,
+                  const void* side, int side_c, void* y, int planes_out, int act, int B, int Cin, int Cout, int Di,
+                  int Hi, int Wi, int Do, int Ho, int Wo, void* stream);
 int dca_pack_weights_tc(const float* w, int transposed, int Co, int Ci, int taps, void* out, int planes, void* stream);
 long long dca_pack_weights_tc_bytes(int Co, int Ci, int taps, int planes);
 /* k3 s1 main loop selector: 1 = halo'd slab reuse (default), 0 = one TMA box per tap. */
