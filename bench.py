@@ -28,6 +28,19 @@ METRIC = "KITTI 384x1248 pairs/s"
 UNIT = "pairs/s"
 
 
+def ncu_traffic(kernel_key):
+    """DRAM bytes per launch (read+write) of a kernel from the committed `ncu --set full` capture, or None."""
+    best = None
+    for fn in sorted(os.listdir(os.path.join(ROOT, "profiles"))):
+        if fn.endswith("_ncu_traffic.json"):
+            z = json.load(open(os.path.join(ROOT, "profiles", fn)))
+            for k, v in z.items():
+                if kernel_key in k and v:
+                    best = {"bytes": v[0]["dram_read_bytes"] + v[0]["dram_write_bytes"], "source": f"profiles/{fn}",
+                            "tensor_pipe_pct": v[0].get("tensor_pipe_pct"), "dram_pct": v[0].get("dram_pct")}
+    return best
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -254,10 +267,17 @@ def main():
             ach = fl / (conv_ms * 1e-3) / 1e12
             kernel_name = "conv3d_tc" if (E.Options.use_tc and pc.w_tc is not None and E.tc_supported(E.K3S1, 32, 32)) \
                 else "conv_direct_kernel<32,16> (CUDA-core fp32)"
+            tr = ncu_traffic("conv_tc_halo_kernel<32, 32, %d>" % P) if kernel_name == "conv3d_tc" else None
+            issued = 3.0 if (P == 2 and kernel_name == "conv3d_tc") else 1.0
             roof = {"kernel": f"{kernel_name} k3 s1 32->32 @ {maxdisp // 4}x{H4}x{W4}", "bound": "tensor",
-                    "achieved": ach, "peak": tf_sust, "unit": "TFLOP/s", "frac": ach / tf_sust, "traffic": None,
+                    "achieved": ach, "peak": tf_sust, "unit": "TFLOP/s", "frac": ach / tf_sust,
+                    "traffic": tr["bytes"] if tr else None,
                     "peak_source": f"{src} (bf16 sustained; burst {tf_burst})", "ms_per_launch": conv_ms,
-                    "algorithmic_flops_per_launch": fl}
+                    "algorithmic_flops_per_launch": fl,
+                    "issued_tflops": ach * issued,
+                    "note": ("parity precision issues 3 bf16 MMAs per algorithmic MAC (hi*Whi, hi*Wlo, lo*Whi); "
+                             "`achieved` counts algorithmic FLOPs only") if issued > 1 else "",
+                    "ncu": tr}
             # volume kernel (HBM bound)
             fs = dev_sets[0]
             for _ in range(3):
@@ -273,7 +293,8 @@ def main():
             vb = workloads.volume_bytes(H, W, maxdisp, P) * B
             extra["roofline_volume"] = {"kernel": "volume_fused_kernel", "bound": "hbm",
                                         "achieved": vb / (vol_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                                        "frac": vb / (vol_ms * 1e-3) / 1e9 / hbm, "traffic": None,
+                                        "frac": vb / (vol_ms * 1e-3) / 1e9 / hbm,
+                                        "traffic": (ncu_traffic("volume_fused_kernel") or {}).get("bytes"),
                                         "ms_per_launch": vol_ms, "algorithmic_bytes_per_launch": vb,
                                         "peak_source": src}
 
