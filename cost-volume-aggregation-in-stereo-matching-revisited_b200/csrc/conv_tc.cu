@@ -53,6 +53,7 @@ struct TcParams {
   const __nv_bfloat16* res_pre; const __nv_bfloat16* res_post; size_t res_plane; int planes_res;
   __nv_bfloat16* y; size_t y_plane; int planes_out; int act;
   const __nv_bfloat16* up; int planes_up;   // optional half-resolution tensor added (trilinear x2) before BN
+  int cls_inner;                   // epilogue/work order: CTA owns whole tiles, classes inside (up2 kernel)
   int linear;                      // 1x1x1 convs: tiles are 128 CONSECUTIVE voxels (8 KB bursts); rB/rD/rH/rW = real dims
   int rB, rD, rH, rW;
   int dbg;       // diagnostics: bit0 = skip epilogue stores, bit1 = skip MMAs (timing experiments only)
@@ -208,9 +209,16 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
   const int row = quarter * 32 + lane;          // tile row = voxel
   const int hh = row / TC_TW, ww = row % TC_TW;
   uint32_t it = 0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-    int r = tile;
-    const int cls = r % p.ncls; r /= p.ncls;
+  // flat mode: work item = (tile, class) pairs round-robin over CTAs; cls_inner mode: a CTA owns whole tiles and
+  // walks the ncls classes inside each (total_tiles then counts tiles only)
+  const int step = p.cls_inner ? 1 : (int)gridDim.x;
+  const int first = p.cls_inner ? 0 : (int)blockIdx.x;
+  const int my_tiles = p.cls_inner ? ((total_tiles > (int)blockIdx.x) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0) : 0;
+  const int n_items = p.cls_inner ? my_tiles * p.ncls : total_tiles;
+  for (int item = first; item < n_items; item += step, ++it) {
+    int r, cls;
+    if (p.cls_inner) { cls = item % p.ncls; r = (int)blockIdx.x + (item / p.ncls) * (int)gridDim.x; }
+    else { cls = item % p.ncls; r = item / p.ncls; }
     const int tw = r % p.tiles_w; r /= p.tiles_w;
     const int th = r % p.tiles_h; r /= p.tiles_h;
     const int td = r % p.Dt;
@@ -641,6 +649,214 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   }
 }
 
+
+// =====================================================================================================
+// "up2" kernel: outputs at TWICE the resolution of the main input, 8 output parity classes per low-res
+// tile, every class a short list of taps that all read the SAME halo'd slabs of the low-res tile:
+//   kind 0  ConvTranspose3d k3 s2 p1 op1 (o = 2i - 1 + k): slabs dz in {0,1}, tap offsets in {0,1}^3,
+//           1/2/4/8 taps per class, weights = the 27 filter taps        (Multi_Aggregation.conv3, cva.py:20-22)
+//   kind 1  trilinear x2 (align_corners=False) of a border-replicated low-res tensor: slabs dz in {0,1,2},
+//           8 taps per class whose weights are the 4 diagonal matrices {27,9,3,1}/64 * I     (cva.py:64)
+// plus an optional 1x1x1 "side" tap per class on the parity view of a tensor at the OUTPUT resolution
+// (redir of cva.py:24 for kind 0; the cost half of cva.fuse, cva.py:55,69, for kind 1).
+// One slab load per tile feeds all 8 classes (the per-tap kernel reloaded a 128-row box per tap and was
+// L2->SMEM bound).  Weights stream per tap through a small ring; side boxes through a 2-deep ring.
+// =====================================================================================================
+struct Up2Tap { unsigned char slab, dy, dx, widx; };
+struct Up2Params {
+  int nslab; int slab_dz[3];
+  int has_side; int side_widx;
+  unsigned char cls_tap0[9];
+  Up2Tap taps[64];
+};
+
+template <int CIN, int PLANES, int NSLAB>
+struct Up2Cfg {
+  static constexpr int COUT = 32;
+  static constexpr int ROWB = CIN * 2;
+  static constexpr int SLAB_BYTES = HB_W * HB_H * ROWB;
+  static constexpr int SLAB_PITCH = (SLAB_BYTES + 1023) / 1024 * 1024;
+  static constexpr int SLAB_SET = NSLAB * PLANES * SLAB_PITCH;      // slabs x planes
+  static constexpr int A_BYTES = TC_M * ROWB;                        // one plane of a side box
+  static constexpr int SIDE_SLOT = PLANES * A_BYTES;
+  static constexpr int B_ROWS = PLANES * COUT;
+  static constexpr int B_BYTES = B_ROWS * ROWB;
+  static constexpr int W_SLOTS = 6;
+  static constexpr int SIDE_SLOTS = 2;
+  static constexpr int FIXED = SIDE_SLOTS * SIDE_SLOT + W_SLOTS * B_BYTES + 1024 + 512 + 2 * COUT * 4;
+  static constexpr int NBUF = (2 * SLAB_SET + FIXED <= 225 * 1024) ? 2 : 1;
+  static constexpr int TMEM_COLS = 2 * PLANES * COUT < 32 ? 32 : 2 * PLANES * COUT;
+  static constexpr int SMEM_BYTES = NBUF * SLAB_SET + FIXED;
+};
+
+template <int CIN, int PLANES, int NSLAB>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_up2_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const Up2Params u) {
+  using Cfg = Up2Cfg<CIN, PLANES, NSLAB>;
+  constexpr int COUT = Cfg::COUT;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* slab_base = smem;
+  uint8_t* side_base = slab_base + Cfg::NBUF * Cfg::SLAB_SET;
+  uint8_t* w_base = side_base + Cfg::SIDE_SLOTS * Cfg::SIDE_SLOT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_base + Cfg::W_SLOTS * Cfg::B_BYTES);
+  uint64_t* sfull = bars;                          // [NBUF]
+  uint64_t* sempty = sfull + Cfg::NBUF;            // [NBUF]
+  uint64_t* dfull = sempty + Cfg::NBUF;            // [SIDE_SLOTS]
+  uint64_t* dempty = dfull + Cfg::SIDE_SLOTS;      // [SIDE_SLOTS]
+  uint64_t* wfull = dempty + Cfg::SIDE_SLOTS;      // [W_SLOTS]
+  uint64_t* wempty = wfull + Cfg::W_SLOTS;         // [W_SLOTS]
+  uint64_t* tfull = wempty + Cfg::W_SLOTS;         // [2]
+  uint64_t* tempty = tfull + 2;                    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_scale = reinterpret_cast<float*>(w_base + Cfg::W_SLOTS * Cfg::B_BYTES + 512);
+  float* s_shift = s_scale + COUT;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.B * p.Dt * p.tiles_h * p.tiles_w;      // low-res tiles; 8 classes inside each
+
+  if (threadIdx.x < COUT) {
+    s_scale[threadIdx.x] = p.scale ? p.scale[threadIdx.x] : 1.f;
+    s_shift[threadIdx.x] = p.shift ? p.shift[threadIdx.x] : 0.f;
+  }
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < Cfg::NBUF; ++i) { mbar_init(&sfull[i], 1); mbar_init(&sempty[i], 1); }
+    for (int i = 0; i < Cfg::SIDE_SLOTS; ++i) { mbar_init(&dfull[i], 1); mbar_init(&dempty[i], 1); }
+    for (int i = 0; i < Cfg::W_SLOTS; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&maps.a[0]);
+    prefetch_tmap(&maps.w);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t sb = 0, pb = 0, sd = 0, pd = 0, sw = 0, pw = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int r = tile;
+        const int tw = r % p.tiles_w; r /= p.tiles_w;
+        const int th = r % p.tiles_h; r /= p.tiles_h;
+        const int td = r % p.Dt;
+        const int b = r / p.Dt;
+        mbar_wait(&sempty[sb], pb ^ 1);
+        mbar_expect_tx(&sfull[sb], u.nslab * PLANES * Cfg::SLAB_BYTES);
+        for (int sl = 0; sl < u.nslab; ++sl)
+#pragma unroll
+          for (int pl = 0; pl < PLANES; ++pl)
+            tma_load_5d(slab_base + sb * Cfg::SLAB_SET + (sl * PLANES + pl) * Cfg::SLAB_PITCH, &maps.a[0], &sfull[sb], 0,
+                        tw * TC_TW, th * TC_TH, td + u.slab_dz[sl], pl * p.B + b);
+        if (++sb == Cfg::NBUF) { sb = 0; pb ^= 1; }
+        for (int cls = 0; cls < 8; ++cls) {
+          if (u.has_side) {
+            mbar_wait(&dempty[sd], pd ^ 1);
+            mbar_expect_tx(&dfull[sd], PLANES * Cfg::A_BYTES);
+#pragma unroll
+            for (int pl = 0; pl < PLANES; ++pl)
+              tma_load_5d(side_base + sd * Cfg::SIDE_SLOT + pl * Cfg::A_BYTES, &maps.a[1 + cls], &dfull[sd], 0,
+                          tw * TC_TW, th * TC_TH, td, pl * p.B + b);
+            if (++sd == Cfg::SIDE_SLOTS) { sd = 0; pd ^= 1; }
+          }
+          const int nt = u.cls_tap0[cls + 1] - u.cls_tap0[cls] + (u.has_side ? 1 : 0);
+          for (int j = 0; j < nt; ++j) {
+            const int widx = (j < u.cls_tap0[cls + 1] - u.cls_tap0[cls]) ? u.taps[u.cls_tap0[cls] + j].widx : u.side_widx;
+            mbar_wait(&wempty[sw], pw ^ 1);
+            mbar_expect_tx(&wfull[sw], Cfg::B_BYTES);
+            tma_load_2d(w_base + sw * Cfg::B_BYTES, &maps.w, &wfull[sw], 0, widx * Cfg::B_ROWS);
+            if (++sw == Cfg::W_SLOTS) { sw = 0; pw ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    {
+      const bool leader = elect_one();
+      constexpr uint32_t idesc_full = make_idesc(TC_M, PLANES * COUT);
+      constexpr uint32_t idesc_half = make_idesc(TC_M, COUT);
+      constexpr uint64_t DA = desc_const<Cfg::ROWB>(HB_W * Cfg::ROWB);     // slab views: 8-row groups 10 rows apart
+      constexpr uint64_t DD = desc_const<Cfg::ROWB>(8 * Cfg::ROWB);        // dense tiles (side boxes, weights)
+      constexpr uint32_t NACC = PLANES * COUT;
+      const uint32_t slab_u32 = smem_u32(slab_base), side_u32 = smem_u32(side_base), w_u32 = smem_u32(w_base);
+      uint32_t sb = 0, pb = 0, sd = 0, pd = 0, sw = 0, pw = 0, it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&sfull[sb], pb);
+        tc_fence_after();
+        const uint32_t set_u32 = slab_u32 + sb * Cfg::SLAB_SET;
+        for (int cls = 0; cls < 8; ++cls, ++it) {
+          const uint32_t acc = it & 1;
+          mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_addr = tmem_base + acc * NACC;
+          const int t0 = u.cls_tap0[cls], t1 = u.cls_tap0[cls + 1];
+          for (int t = t0; t < t1; ++t) {
+            const Up2Tap tp = u.taps[t];
+            mbar_wait(&wfull[sw], pw);
+            tc_fence_after();
+            const uint32_t a0 = set_u32 + (uint32_t)(tp.slab * PLANES) * Cfg::SLAB_PITCH + (uint32_t)(tp.dy * HB_W + tp.dx) * Cfg::ROWB;
+            const uint64_t da0 = DA + (a0 >> 4);
+            const uint64_t db0 = DD + ((w_u32 + sw * Cfg::B_BYTES) >> 4);
+#pragma unroll
+            for (int k = 0; k < CIN / 16; ++k) {
+              if (leader) {
+                umma_bf16(d_addr, da0 + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc_full, (t > t0 || k > 0) ? 1u : 0u);
+                if (PLANES == 2)
+                  umma_bf16(d_addr, da0 + (uint64_t)((Cfg::SLAB_PITCH >> 4) + k * 2), db0 + (uint64_t)(k * 2), idesc_half, 1u);
+              }
+            }
+            __syncwarp();
+            if (leader) umma_commit(&wempty[sw]);
+            if (++sw == Cfg::W_SLOTS) { sw = 0; pw ^= 1; }
+          }
+          if (u.has_side) {
+            mbar_wait(&dfull[sd], pd);
+            mbar_wait(&wfull[sw], pw);
+            tc_fence_after();
+            const uint64_t da0 = DD + ((side_u32 + sd * Cfg::SIDE_SLOT) >> 4);
+            const uint64_t db0 = DD + ((w_u32 + sw * Cfg::B_BYTES) >> 4);
+#pragma unroll
+            for (int k = 0; k < CIN / 16; ++k) {
+              if (leader) {
+                umma_bf16(d_addr, da0 + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc_full, (t1 > t0 || k > 0) ? 1u : 0u);
+                if (PLANES == 2)
+                  umma_bf16(d_addr, da0 + (uint64_t)((Cfg::A_BYTES >> 4) + k * 2), db0 + (uint64_t)(k * 2), idesc_half, 1u);
+              }
+            }
+            __syncwarp();
+            if (leader) { umma_commit(&wempty[sw]); umma_commit(&dempty[sd]); }
+            if (++sw == Cfg::W_SLOTS) { sw = 0; pw ^= 1; }
+            if (++sd == Cfg::SIDE_SLOTS) { sd = 0; pd ^= 1; }
+          }
+          if (leader) umma_commit(&tfull[acc]);
+          __syncwarp();
+        }
+        if (leader) umma_commit(&sempty[sb]);      // all MMAs reading this slab set have been issued
+        __syncwarp();
+        if (++sb == Cfg::NBUF) { sb = 0; pb ^= 1; }
+      }
+    }
+  } else {
+    tc_epilogue<COUT, PLANES>(p, total_tiles, tmem_base, tfull, tempty, s_scale, s_shift, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ weight pack: [tap][plane][Cout][Cin] bf16
 __global__ void pack_weight_tc_kernel(const float* __restrict__ w, int transposed, int Co, int Ci, int taps,
                                       __nv_bfloat16* __restrict__ out, int planes) {
@@ -745,9 +961,122 @@ static int launch_tc_halo(const TcMaps& maps, const TcParams& p, cudaStream_t st
   return DCA_OK;
 }
 
+
+template <int CIN, int PLANES, int NSLAB>
+static int launch_up2(const TcMaps& maps, const TcParams& p, const Up2Params& u, cudaStream_t st) {
+  using Cfg = Up2Cfg<CIN, PLANES, NSLAB>;
+  static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "smem plan");
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  cudaFuncSetAttribute(conv_tc_up2_kernel<CIN, PLANES, NSLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  const int total = p.B * p.Dt * p.tiles_h * p.tiles_w;
+  const int grid = total < g_num_sms ? total : g_num_sms;
+  conv_tc_up2_kernel<CIN, PLANES, NSLAB><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p, u);
+  DCA_RETURN_IF_LAUNCH_FAILED();
+  return DCA_OK;
+}
+
 }  // namespace dca
 
 using namespace dca;
+
+// kind 0: y = act(scale * (conv_transpose3d_k3s2(x) + side 1x1x1) + shift) + res_post
+//         x [P][B][Dl][Hl][Wl][Cin], w_tc = 27 taps (+ tap 27 = side weights, Cin-padded) of [planes][32][Cin]
+// kind 1: y = act(scale * (trilinear_x2(x) + side 1x1x1) + shift) + res_post
+//         x = BORDER-REPLICATED low-res tensor [P][B][Dl+2][Hl+2][Wl+2][32]; w_tc = 5 taps:
+//         {27,9,3,1}/64 * I and the side weights.
+// side [P][B][2Dl][2Hl][2Wl][side_c] (optional for kind 0), Cout = 32.
+extern "C" int dca_up2_tc(int kind, const void* x, int planes, const void* side, int side_c, const void* w_tc,
+                          const float* scale, const float* shift, const void* res_post, int planes_res, void* y, int act,
+                          int B, int Cin, int Dl, int Hl, int Wl, void* stream) {
+  if (!x || !w_tc || !y || B <= 0 || planes < 1 || planes > 2 || Dl <= 0 || Hl <= 0 || Wl <= 0) return DCA_ERR_ARG;
+  if (kind < 0 || kind > 1 || (kind == 1 && (!side || Cin != 32)) || (Cin != 32 && Cin != 64)) return DCA_ERR_UNSUPPORTED;
+  if (side && (side_c <= 0 || side_c > Cin || (side_c % 8) != 0)) return DCA_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = planes, Cout = 32;
+  const int Do = 2 * Dl, Ho = 2 * Hl, Wo = 2 * Wl;
+  TcMaps maps;
+  TcParams p;
+  Up2Params u;
+  memset(&p, 0, sizeof(p));
+  memset(&u, 0, sizeof(u));
+  p.B = B; p.Do = Do; p.Ho = Ho; p.Wo = Wo;
+  p.scale = scale; p.shift = shift;
+  p.res_post = (const __nv_bfloat16*)res_post;
+  p.res_plane = (size_t)B * Do * Ho * Wo * Cout; p.planes_res = planes_res;
+  p.y = (__nv_bfloat16*)y; p.y_plane = p.res_plane; p.planes_out = P; p.act = act;
+  p.npart = P; p.ngrp = 1; p.dbg = g_dbg;
+  p.Dt = Dl; p.Ht = Hl; p.Wt = Wl; p.out_stride = 2; p.ncls = 8; p.cls_inner = 1;
+  p.tiles_w = (Wl + TC_TW - 1) / TC_TW; p.tiles_h = (Hl + TC_TH - 1) / TC_TH;
+  // main input: halo box 10 x 18 whose origin is the tile origin (kind 1: the +1 of the padding cancels the -1 halo)
+  const int pad = (kind == 1) ? 2 : 0;
+  const int Dx = Dl + pad, Hx = Hl + pad, Wx = Wl + pad;
+  if (!make_act_map(&maps.a[0], x, Cin, Wx, Hx, Dx, P * B, (size_t)Cin, (size_t)Wx * Cin, (size_t)Hx * Wx * Cin,
+                    (size_t)Dx * Hx * Wx * Cin, HB_W, HB_H))
+    return DCA_ERR_LAUNCH;
+  for (int i = 1; i < 9; ++i) maps.a[i] = maps.a[0];
+  if (side) {
+    const size_t qW = side_c, qH = (size_t)Wo * side_c, qD = (size_t)Ho * Wo * side_c, qB = (size_t)Do * Ho * Wo * side_c;
+    for (int pc = 0; pc < 8; ++pc) {
+      const int pz = (pc >> 2) & 1, py = (pc >> 1) & 1, px = pc & 1;
+      const __nv_bfloat16* base = (const __nv_bfloat16*)side + pz * qD + py * qH + px * qW;
+      if (!make_act_map(&maps.a[1 + pc], base, side_c, Wl, Hl, Dl, P * B, 2 * qW, 2 * qH, 2 * qD, qB, TC_TW, TC_TH, Cin))
+        return DCA_ERR_LAUNCH;
+    }
+    u.has_side = 1;
+  }
+  int ntaps = 0;
+  if (kind == 0) {
+    u.nslab = 2; u.slab_dz[0] = 0; u.slab_dz[1] = 1;
+    u.side_widx = 27;
+    for (int pc = 0; pc < 8; ++pc) {
+      const int par[3] = {(pc >> 2) & 1, (pc >> 1) & 1, pc & 1};
+      u.cls_tap0[pc] = (unsigned char)ntaps;
+      for (int a = 0; a < 3; ++a) p.cls_off[pc][a] = (signed char)par[a];
+      for (int kd = 0; kd < 3; ++kd) for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw) {
+        const int k[3] = {kd, kh, kw};
+        int off[3]; bool ok = true;
+        for (int a = 0; a < 3; ++a) { const int n = par[a] + 1 - k[a]; if (n & 1) ok = false; off[a] = n / 2; }
+        if (!ok) continue;
+        Up2Tap& t = u.taps[ntaps++];
+        t.slab = (unsigned char)off[0]; t.dy = (unsigned char)off[1]; t.dx = (unsigned char)off[2];
+        t.widx = (unsigned char)((kd * 3 + kh) * 3 + kw);
+      }
+    }
+  } else {
+    u.nslab = 3; u.slab_dz[0] = 0; u.slab_dz[1] = 1; u.slab_dz[2] = 2;
+    u.side_widx = 4;
+    for (int pc = 0; pc < 8; ++pc) {
+      const int par[3] = {(pc >> 2) & 1, (pc >> 1) & 1, pc & 1};
+      u.cls_tap0[pc] = (unsigned char)ntaps;
+      for (int a = 0; a < 3; ++a) p.cls_off[pc][a] = (signed char)par[a];
+      // per axis: even output 2i: (in[i-1], .25), (in[i], .75); odd 2i+1: (in[i], .75), (in[i+1], .25);
+      // in padded coordinates in[j] sits at j+1, so the two source offsets are (0,1) for even, (1,2) for odd
+      for (int m = 0; m < 8; ++m) {
+        int n75 = 0, off[3];
+        for (int a = 0; a < 3; ++a) {
+          const int second = (m >> (2 - a)) & 1;                 // 0 = first source of the axis, 1 = second
+          off[a] = par[a] + second;
+          const bool is75 = par[a] ? (second == 0) : (second == 1);
+          n75 += is75 ? 1 : 0;
+        }
+        Up2Tap& t = u.taps[ntaps++];
+        t.slab = (unsigned char)off[0]; t.dy = (unsigned char)off[1]; t.dx = (unsigned char)off[2];
+        t.widx = (unsigned char)(3 - n75);                       // 0: 27/64, 1: 9/64, 2: 3/64, 3: 1/64
+      }
+    }
+  }
+  u.cls_tap0[8] = (unsigned char)ntaps;
+  const int wt = (kind == 0) ? (side ? 28 : 27) : 5;
+  if (!make_w_map(&maps.w, w_tc, Cin, wt * P * Cout, P * Cout)) return DCA_ERR_LAUNCH;
+  if (kind == 1) return P == 2 ? launch_up2<32, 2, 3>(maps, p, u, st) : launch_up2<32, 1, 3>(maps, p, u, st);
+  if (Cin == 64) return P == 2 ? launch_up2<64, 2, 2>(maps, p, u, st) : launch_up2<64, 1, 2>(maps, p, u, st);
+  return P == 2 ? launch_up2<32, 2, 2>(maps, p, u, st) : launch_up2<32, 1, 2>(maps, p, u, st);
+}
 
 // 1 = halo-slab main loop for k3 s1 (default), 0 = one TMA box per tap (v1)
 extern "C" int dca_tc_set_halo(int on) { g_use_halo = on ? 1 : 0; return DCA_OK; }

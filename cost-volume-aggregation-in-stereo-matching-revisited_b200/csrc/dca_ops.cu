@@ -136,7 +136,8 @@ template <int PLANES>
 __global__ void __launch_bounds__(256)
 disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ cls, const float* __restrict__ e,
                       const float* __restrict__ S, const float* __restrict__ wts, int has_wa,
-                      __nv_bfloat16* __restrict__ y, int B, int D, int HW) {
+                      __nv_bfloat16* __restrict__ y, int B, int D, int H, int Wd, int pad) {
+  const int HW = H * Wd;
   extern __shared__ __align__(16) float smem[];
   float* W = smem;                                   // AT_WFLOATS
   const int Dp = (D + 7) & ~7;
@@ -211,7 +212,11 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
     warp_project(bB, bC, Wo, ss + 5 * 64, Dp, lane, true);     // aug_down in bC
     const float* res = bC;
     if (has_wa) { warp_project(bC, bD, Wa, nullptr, Dp, lane, false); res = bD; }
-    // ---- store [d][32] rows: lane = (row, chunk) ----
+    // ---- store [d][32] rows: lane = (row, chunk).  pad = 1 writes into a tensor with a replicated 1-voxel border
+    //      ([D+2][H+2][W+2], what the trilinear-x2 "up2" GEMM consumes) ----
+    const int ph = p / Wd, pw = p - ph * Wd;
+    const int Dp2 = D + 2 * pad, Hp2 = H + 2 * pad, Wp2 = Wd + 2 * pad;
+    const size_t oplane = (size_t)B * Dp2 * Hp2 * Wp2 * AT_C;
     for (int d0 = 0; d0 < D; d0 += 8) {
       const int d = d0 + (lane >> 2), q = lane & 3;
       if (d < D) {
@@ -219,7 +224,24 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
         const float4 a = *reinterpret_cast<const float4*>(res + d * AT_C + q * 8);
         const float4 c2 = *reinterpret_cast<const float4*>(res + d * AT_C + q * 8 + 4);
         f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = c2.x; f[5] = c2.y; f[6] = c2.z; f[7] = c2.w;
-        store8<PLANES>(y, plane, (((size_t)b * D + d) * HW + p) * AT_C + q * 8, f);
+        if (!pad) {
+          store8<PLANES>(y, oplane, (((size_t)b * D + d) * HW + p) * AT_C + q * 8, f);
+        } else {
+          // every coordinate x in [0,n) maps to x+1, plus the replicated border copies 0 (x==0) and n+1 (x==n-1)
+          for (int iz = 0; iz < 3; ++iz) {
+            const int zz = iz == 0 ? d + 1 : (iz == 1 ? (d == 0 ? 0 : -1) : (d == D - 1 ? D + 1 : -1));
+            if (zz < 0) continue;
+            for (int iy = 0; iy < 3; ++iy) {
+              const int yy = iy == 0 ? ph + 1 : (iy == 1 ? (ph == 0 ? 0 : -1) : (ph == H - 1 ? H + 1 : -1));
+              if (yy < 0) continue;
+              for (int ix = 0; ix < 3; ++ix) {
+                const int xx = ix == 0 ? pw + 1 : (ix == 1 ? (pw == 0 ? 0 : -1) : (pw == Wd - 1 ? Wd + 1 : -1));
+                if (xx < 0) continue;
+                store8<PLANES>(y, oplane, ((((size_t)b * Dp2 + zz) * Hp2 + yy) * Wp2 + xx) * AT_C + q * 8, f);
+              }
+            }
+          }
+        }
       }
     }
     __syncwarp();
@@ -530,7 +552,9 @@ extern "C" int dca_class_stats(const float* logits, int* cls, float* e, float* S
 }
 
 extern "C" int dca_disp_attention(const void* x, const int* cls, const float* e, const float* S, const float* weights,
-                                  int has_wa, void* y, int planes, int B, int C, int D, int H, int W, void* stream) {
+                                  int has_wa, void* y, int pad, int planes, int B, int C, int D, int H, int W,
+                                  void* stream) {
+  if (pad != 0 && pad != 1) return DCA_ERR_ARG;
   if (!x || !cls || !e || !S || !weights || !y || planes < 1 || planes > 2 || B <= 0 || D <= 0) return DCA_ERR_ARG;
   if (C != AT_C) return DCA_ERR_UNSUPPORTED;
   const int Dp = (D + 7) & ~7;
@@ -546,11 +570,11 @@ extern "C" int dca_disp_attention(const void* x, const int* cls, const float* e,
   if (planes == 2) {
     cudaFuncSetAttribute(disp_attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     disp_attention_kernel<2><<<grid, warps * 32, smem, st>>>((const __nv_bfloat16*)x, cls, e, S, weights, has_wa,
-                                                             (__nv_bfloat16*)y, B, D, HW);
+                                                             (__nv_bfloat16*)y, B, D, H, W, pad);
   } else {
     cudaFuncSetAttribute(disp_attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     disp_attention_kernel<1><<<grid, warps * 32, smem, st>>>((const __nv_bfloat16*)x, cls, e, S, weights, has_wa,
-                                                             (__nv_bfloat16*)y, B, D, HW);
+                                                             (__nv_bfloat16*)y, B, D, H, W, pad);
   }
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;

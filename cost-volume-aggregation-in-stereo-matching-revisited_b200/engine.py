@@ -121,6 +121,7 @@ class Options:
     tc_modes = {0, 1, 2, 3}       # conv modes the tcgen05 kernel takes (K3S1, K3S2, T3S2, K1)
     fuse_upsample_in_conv = True  # cva fuse stage: fold the trilinear upsample into the 1x1x1 conv's epilogue
     fuse_redir_in_deconv = True   # Multi_Aggregation: conv3 (transposed) + redir (1x1x1) as one GEMM
+    use_up2 = True                # class-wise halo-slab kernel for the transposed conv and the trilinear fuse stage
 
 
 def conv(x: Planes, pc: PackedConv, mode=K3S1, act=ACT_NONE, res_pre: Planes = None, res_post: Planes = None,
@@ -200,10 +201,22 @@ def class_stats(logits):
     return cls, e, S
 
 
-def disp_attention(x: Planes, cls, e, S, weights, has_wa):
-    y = Planes(x.B, x.D, x.H, x.W, x.C, x.planes, x.t.device)
+def disp_attention(x: Planes, cls, e, S, weights, has_wa, pad=False):
+    """pad=True: the result gets a replicated 1-voxel border ([D+2][H+2][W+2]) for the up2 (trilinear) GEMM."""
+    k = 2 if pad else 0
+    y = Planes(x.B, x.D + k, x.H + k, x.W + k, x.C, x.planes, x.t.device)
     _lib.call("dca_disp_attention", x.ptr, cls.data_ptr(), e.data_ptr(), S.data_ptr(), weights.data_ptr(),
-              int(has_wa), y.ptr, x.planes, x.B, x.C, x.D, x.H, x.W, _stream())
+              int(has_wa), y.ptr, int(pad), x.planes, x.B, x.C, x.D, x.H, x.W, _stream())
+    return y
+
+
+def up2(kind, x: Planes, side: Planes, w_tc, scale, shift, act, cin, dl, hl, wl, res_post: Planes = None):
+    """dca_up2_tc: kind 0 transposed conv (+side 1x1x1), kind 1 trilinear x2 of a padded tensor + side 1x1x1."""
+    y = Planes(x.B, 2 * dl, 2 * hl, 2 * wl, 32, x.planes, x.t.device)
+    _lib.call("dca_up2_tc", kind, x.ptr, x.planes, side.ptr if side is not None else 0,
+              side.C if side is not None else 0, w_tc.data_ptr(), _ptr(scale), _ptr(shift),
+              res_post.ptr if res_post is not None else 0, res_post.planes if res_post is not None else 1, y.ptr, act,
+              x.B, cin, dl, hl, wl, _stream())
     return y
 
 
@@ -290,6 +303,16 @@ class PackedCva:
             pc.pack_tc(planes)
         self.conv3.pack_tc(planes, transposed=True)
         self.conv3_fused = _pack_deconv_with_redir(agg, self.conv3, self.redir, planes)
+        # trilinear x2 + cat + fuse as a GEMM: 4 diagonal interpolation taps {27,9,3,1}/64 * I and the cost half Wc
+        w5 = torch.zeros((32, 32, 5), dtype=torch.float32, device=fuse_w.device)       # [co][ci][tap]
+        eye = torch.eye(32, device=fuse_w.device)
+        for i, wv in enumerate((27.0, 9.0, 3.0, 1.0)):
+            w5[:, :, i] = eye * (wv / 64.0)
+        w5[:, :, 4] = fuse_w.detach().float()[:, 32:, 0, 0, 0]
+        nb = _lib.load().dca_pack_weights_tc_bytes(32, 32, 5, planes)
+        self.fuse_up2_w = torch.empty(nb, dtype=torch.uint8, device=fuse_w.device)
+        _lib.call("dca_pack_weights_tc", w5.data_ptr(), 0, 32, 32, 5, self.fuse_up2_w.data_ptr(), planes, _stream())
+        torch.cuda.current_stream().synchronize()
 
 
 class _FusedDeconv:
@@ -325,8 +348,13 @@ def cva_forward(pk: PackedCva, cost: Planes, res_post: Planes = None, keep=None)
     h = conv(cost_down, pk.cls0, K3S1, ACT_RELU)
     logits = conv_cout1(h, pk.cls2)
     cls, e, S = class_stats(logits)
-    t = disp_attention(cost_down, cls, e, S, pk.attn.buf, pk.attn.has_wa)
-    if Options.use_tc and Options.fuse_upsample_in_conv and tc_supported(K1, 32, 32):
+    use_up2 = Options.use_tc and Options.use_up2 and pk.attn.has_wa
+    t = disp_attention(cost_down, cls, e, S, pk.attn.buf, pk.attn.has_wa, pad=use_up2)
+    if use_up2:
+        # trilinear x2 + cat + 1x1x1 fuse + BN as ONE class-wise GEMM over halo slabs of the padded low-res tensor
+        fused = up2(1, t, cost, pk.fuse_up2_w, pk.fuse_scale, pk.fuse_shift, ACT_NONE, 32, cost_down.D, cost_down.H,
+                    cost_down.W)
+    elif Options.use_tc and Options.fuse_upsample_in_conv and tc_supported(K1, 32, 32):
         # trilinear x2 + cat + 1x1x1 fuse + BN as ONE tcgen05 conv: Wc.cost by MMA, up(t) added in the epilogue
         fused = conv(cost, pk.fuse_c, K1, ACT_NONE, up=t)
     else:
@@ -334,7 +362,9 @@ def cva_forward(pk: PackedCva, cost: Planes, res_post: Planes = None, keep=None)
     c1 = conv(fused, pk.conv1, K3S2, ACT_RELU)
     c2 = conv(c1, pk.conv2, K3S1, ACT_RELU)
     fd = pk.conv3_fused
-    if Options.use_tc and Options.fuse_redir_in_deconv and fd is not None and fd.tc_planes == c2.planes \
+    if Options.use_tc and Options.use_up2 and fd is not None and fd.tc_planes == c2.planes:
+        out = up2(0, c2, fused, fd.w_tc, fd.scale, fd.shift, ACT_RELU, 64, c2.D, c2.H, c2.W, res_post=res_post)
+    elif Options.use_tc and Options.fuse_redir_in_deconv and fd is not None and fd.tc_planes == c2.planes \
             and tc_supported(T3S2, 64, 32):
         # ReLU(BN(deconv(c2)) + BN(redir(fused))) (+ res_post) as one tcgen05 GEMM with a 28th, 1x1x1 tap
         out = Planes(c2.B, 2 * c2.D, 2 * c2.H, 2 * c2.W, 32, c2.planes, c2.t.device)

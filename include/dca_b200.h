@@ -74,6 +74,15 @@ int dca_conv3d_tc(int mode, const void* x, int planes_in, const void* w_tc, cons
                   int Hi, int Wi, int Do, int Ho, int Wo, void* stream);
 int dca_pack_weights_tc(const float* w, int transposed, int Co, int Ci, int taps, void* out, int planes, void* stream);
 long long dca_pack_weights_tc_bytes(int Co, int Ci, int taps, int planes);
+/* Outputs at twice the input resolution, 8 output parity classes per low-res tile fed from shared halo slabs:
+ *   kind 0: y = act(scale * (ConvTranspose3d_k3s2p1op1(x) + side 1x1x1) + shift) + res_post     (cva.py:20-29)
+ *           x [planes][B][Dl][Hl][Wl][Cin]; w_tc = 27 taps (+ tap 27: side weights zero-padded to Cin)
+ *   kind 1: y = act(scale * (trilinear_x2(x) + side 1x1x1) + shift) + res_post                  (cva.py:64,55,69)
+ *           x = border-replicated [planes][B][Dl+2][Hl+2][Wl+2][32]; w_tc = 5 taps: {27,9,3,1}/64*I, side weights
+ * side [planes][B][2Dl][2Hl][2Wl][side_c]; Cout = 32. */
+int dca_up2_tc(int kind, const void* x, int planes, const void* side, int side_c, const void* w_tc, const float* scale,
+               const float* shift, const void* res_post, int planes_res, void* y, int act, int B, int Cin, int Dl,
+               int Hl, int Wl, void* stream);
 /* k3 s1 main loop selector: 1 = halo'd slab reuse (default), 0 = one TMA box per tap. */
 int dca_tc_set_halo(int on);
 /* halo kernel tuning: taps interleaved over ngrp (1,2,4) independent TMEM accumulator groups; lo_sep = own block for lo*Whi. */
@@ -84,8 +93,9 @@ int dca_avgpool3d(const void* x, void* y, int planes, int B, int C, int Di, int 
 /* logits fp32 [B,D,H,W] -> class map int32 [B,H,W], e = exp(P[k_p]) [B,H,W], S [B,D] (zeroed here). */
 int dca_class_stats(const float* logits, int* cls, float* e, float* S, int B, int D, int H, int W, void* stream);
 /* weights: 7 x [32][32] transposed (q0,q1,k0,k1,v,o,Wa) then 6 x (scale[32],shift[32]). */
+/* pad = 1: y is [planes][B][D+2][H+2][W+2][C] with a replicated 1-voxel border (input of dca_up2_tc kind 1). */
 int dca_disp_attention(const void* x, const int* cls, const float* e, const float* S, const float* weights,
-                       int has_wa, void* y, int planes, int B, int C, int D, int H, int W, void* stream);
+                       int has_wa, void* y, int pad, int planes, int B, int C, int D, int H, int W, void* stream);
 /* y = scale * (trilinear_x2(t) + WcT^T cost) + shift ; t at (Dl,Hl,Wl), cost / y at twice that. */
 int dca_upsample_fuse(const void* t, const void* cost, const float* WcT, const float* scale, const float* shift,
                       void* y, int planes, int B, int C, int Dl, int Hl, int Wl, void* stream);
