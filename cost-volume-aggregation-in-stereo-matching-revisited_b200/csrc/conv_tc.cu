@@ -666,6 +666,8 @@ struct Up2Tap { unsigned char slab, dy, dx, widx; };
 struct Up2Params {
   int nslab; int slab_dz[3];
   int has_side; int side_widx;
+  int wres;      // 1: all weight tiles (<= W_SLOTS) are loaded once and stay resident (kind 1: 5 tiles)
+  int nw;
   unsigned char cls_tap0[9];
   Up2Tap taps[64];
 };
@@ -743,6 +745,10 @@ conv_tc_up2_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const 
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t sb = 0, pb = 0, sd = 0, pd = 0, sw = 0, pw = 0;
+      if (u.wres) {     // resident weights: slot i holds weight tile i for the whole kernel
+        mbar_expect_tx(&wfull[0], u.nw * Cfg::B_BYTES);
+        for (int i = 0; i < u.nw; ++i) tma_load_2d(w_base + i * Cfg::B_BYTES, &maps.w, &wfull[0], 0, i * Cfg::B_ROWS);
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int r = tile;
         const int tw = r % p.tiles_w; r /= p.tiles_w;
@@ -767,7 +773,7 @@ conv_tc_up2_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const 
                           tw * TC_TW, th * TC_TH, td, pl * p.B + b);
             if (++sd == Cfg::SIDE_SLOTS) { sd = 0; pd ^= 1; }
           }
-          const int nt = u.cls_tap0[cls + 1] - u.cls_tap0[cls] + (u.has_side ? 1 : 0);
+          const int nt = u.wres ? 0 : (u.cls_tap0[cls + 1] - u.cls_tap0[cls] + (u.has_side ? 1 : 0));
           for (int j = 0; j < nt; ++j) {
             const int widx = (j < u.cls_tap0[cls + 1] - u.cls_tap0[cls]) ? u.taps[u.cls_tap0[cls] + j].widx : u.side_widx;
             mbar_wait(&wempty[sw], pw ^ 1);
@@ -789,6 +795,7 @@ conv_tc_up2_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const 
       constexpr uint32_t NACC = PLANES * COUT;
       const uint32_t slab_u32 = smem_u32(slab_base), side_u32 = smem_u32(side_base), w_u32 = smem_u32(w_base);
       uint32_t sb = 0, pb = 0, sd = 0, pd = 0, sw = 0, pw = 0, it = 0;
+      if (u.wres) { mbar_wait(&wfull[0], 0); tc_fence_after(); }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(&sfull[sb], pb);
         tc_fence_after();
@@ -801,11 +808,10 @@ conv_tc_up2_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const 
           const int t0 = u.cls_tap0[cls], t1 = u.cls_tap0[cls + 1];
           for (int t = t0; t < t1; ++t) {
             const Up2Tap tp = u.taps[t];
-            mbar_wait(&wfull[sw], pw);
-            tc_fence_after();
+            if (!u.wres) { mbar_wait(&wfull[sw], pw); tc_fence_after(); }
             const uint32_t a0 = set_u32 + (uint32_t)(tp.slab * PLANES) * Cfg::SLAB_PITCH + (uint32_t)(tp.dy * HB_W + tp.dx) * Cfg::ROWB;
             const uint64_t da0 = DA + (a0 >> 4);
-            const uint64_t db0 = DD + ((w_u32 + sw * Cfg::B_BYTES) >> 4);
+            const uint64_t db0 = DD + ((w_u32 + (u.wres ? (uint32_t)tp.widx : sw) * Cfg::B_BYTES) >> 4);
 #pragma unroll
             for (int k = 0; k < CIN / 16; ++k) {
               if (leader) {
@@ -814,16 +820,18 @@ conv_tc_up2_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const 
                   umma_bf16(d_addr, da0 + (uint64_t)((Cfg::SLAB_PITCH >> 4) + k * 2), db0 + (uint64_t)(k * 2), idesc_half, 1u);
               }
             }
-            __syncwarp();
-            if (leader) umma_commit(&wempty[sw]);
-            if (++sw == Cfg::W_SLOTS) { sw = 0; pw ^= 1; }
+            if (!u.wres) {
+              __syncwarp();
+              if (leader) umma_commit(&wempty[sw]);
+              if (++sw == Cfg::W_SLOTS) { sw = 0; pw ^= 1; }
+            }
           }
           if (u.has_side) {
             mbar_wait(&dfull[sd], pd);
-            mbar_wait(&wfull[sw], pw);
+            if (!u.wres) mbar_wait(&wfull[sw], pw);
             tc_fence_after();
             const uint64_t da0 = DD + ((side_u32 + sd * Cfg::SIDE_SLOT) >> 4);
-            const uint64_t db0 = DD + ((w_u32 + sw * Cfg::B_BYTES) >> 4);
+            const uint64_t db0 = DD + ((w_u32 + (u.wres ? (uint32_t)u.side_widx : sw) * Cfg::B_BYTES) >> 4);
 #pragma unroll
             for (int k = 0; k < CIN / 16; ++k) {
               if (leader) {
@@ -833,8 +841,8 @@ conv_tc_up2_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const 
               }
             }
             __syncwarp();
-            if (leader) { umma_commit(&wempty[sw]); umma_commit(&dempty[sd]); }
-            if (++sw == Cfg::W_SLOTS) { sw = 0; pw ^= 1; }
+            if (leader) { if (!u.wres) umma_commit(&wempty[sw]); umma_commit(&dempty[sd]); }
+            if (!u.wres) { if (++sw == Cfg::W_SLOTS) { sw = 0; pw ^= 1; } }
             if (++sd == Cfg::SIDE_SLOTS) { sd = 0; pd ^= 1; }
           }
           if (leader) umma_commit(&tfull[acc]);
@@ -1049,7 +1057,7 @@ extern "C" int dca_up2_tc(int kind, const void* x, int planes, const void* side,
     }
   } else {
     u.nslab = 3; u.slab_dz[0] = 0; u.slab_dz[1] = 1; u.slab_dz[2] = 2;
-    u.side_widx = 4;
+    u.side_widx = 4; u.wres = 1; u.nw = 5;
     for (int pc = 0; pc < 8; ++pc) {
       const int par[3] = {(pc >> 2) & 1, (pc >> 1) & 1, pc & 1};
       u.cls_tap0[pc] = (unsigned char)ntaps;
