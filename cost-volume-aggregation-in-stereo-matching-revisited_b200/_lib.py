@@ -26,6 +26,9 @@ SIGNATURES = {
                       _c_int] + [_c_int] * 9 + [_vp],
     "dca_pack_weights_tc": [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp],
     "dca_pack_weights_tc_bytes": [_c_int] * 4,
+    "dca_conv2d_tc": [_vp, _c_int, _vp, _vp, _vp, _vp, _c_int, _c_int] + [_c_int] * 5 + [_vp],
+    "dca_pack_weights_tc2d": [_vp, _c_int, _c_int, _vp, _c_int, _vp],
+    "dca_pack_weights_tc2d_bytes": [_c_int] * 3,
     "dca_tc_set_halo": [_c_int],
     "dca_tc_set_tuning": [_c_int, _c_int],
     "dca_avgpool3d": [_vp, _vp] + [_c_int] * 6 + [_vp],
@@ -40,7 +43,7 @@ SIGNATURES = {
     "dca_pack_weights": [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp],
     "dca_fold_bn": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _c_int, _c_int, _vp],
 }
-_RESTYPES = {"dca_pack_weights_tc_bytes": ctypes.c_longlong}
+_RESTYPES = {"dca_pack_weights_tc_bytes": ctypes.c_longlong, "dca_pack_weights_tc2d_bytes": ctypes.c_longlong}
 
 ERRORS = {-1: "DCA_ERR_ARG (bad pointer/shape)", -2: "DCA_ERR_LAUNCH (CUDA launch failed)",
           -3: "DCA_ERR_UNSUPPORTED (shape outside what the kernels support)"}

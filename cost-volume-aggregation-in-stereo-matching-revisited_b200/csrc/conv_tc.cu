@@ -53,6 +53,8 @@ struct TcParams {
   const __nv_bfloat16* res_pre; const __nv_bfloat16* res_post; size_t res_plane; int planes_res;
   __nv_bfloat16* y; size_t y_plane; int planes_out; int act;
   const __nv_bfloat16* up; int planes_up;   // optional half-resolution tensor added (trilinear x2) before BN
+  int nslab; int slab_c0[3]; int slab_dz[3];   // halo kernel: slabs per tile (3 depth slabs, or channel halves in 2-D)
+  int ldc, co_base, cout_valid, out_f32;        // output row pitch / first channel / valid channels / fp32 output
   int cls_inner;                   // epilogue/work order: CTA owns whole tiles, classes inside (up2 kernel)
   int linear;                      // 1x1x1 convs: tiles are 128 CONSECUTIVE voxels (8 KB bursts); rB/rD/rH/rW = real dims
   int rB, rD, rH, rW;
@@ -238,7 +240,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
       bb = (int)(r2 / p.rD);
       uD = p.rD; uH = p.rH; uW = p.rW;
     }
-    const size_t off0 = vox * COUT + half * 16;          // first chunk's 16 channels of this thread
+    const size_t off0 = vox * (size_t)p.ldc + p.co_base + half * 16;   // first chunk's 16 channels of this thread
     uint4 pre_raw[4], post_raw[4];
     const bool has_pre = valid && p.res_pre != nullptr, has_post = valid && p.res_post != nullptr;
     if (has_pre) load_raw16(pre_raw, p.res_pre, p.res_plane, p.planes_res, off0);
@@ -314,14 +316,21 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
           if (c0 != 0) load_raw16(post_raw, p.res_post, p.res_plane, p.planes_res, off);
           add_raw16(v, post_raw, p.planes_res);
         }
-        uint32_t hw[8], lw[8];
+        if (p.out_f32) {                      // fp32 channels-last output (mask logits of the propagation net)
+          float* yf = reinterpret_cast<float*>(p.y) + off;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) split2(v[2 * j], v[2 * j + 1], hw[j], lw[j]);
-        *reinterpret_cast<uint4*>(p.y + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        *reinterpret_cast<uint4*>(p.y + off + 8) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-        if (p.planes_out == 2) {
-          *reinterpret_cast<uint4*>(p.y + p.y_plane + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-          *reinterpret_cast<uint4*>(p.y + p.y_plane + off + 8) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+          for (int j = 0; j < 16; ++j)
+            if (p.co_base + cb + j < p.cout_valid) yf[j] = v[j];
+        } else {
+          uint32_t hw[8], lw[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) split2(v[2 * j], v[2 * j + 1], hw[j], lw[j]);
+          *reinterpret_cast<uint4*>(p.y + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(p.y + off + 8) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+          if (p.planes_out == 2) {
+            *reinterpret_cast<uint4*>(p.y + p.y_plane + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            *reinterpret_cast<uint4*>(p.y + p.y_plane + off + 8) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+          }
         }
       }
     }
@@ -546,8 +555,8 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       if (Cfg::WRES) {
-        mbar_expect_tx(&wfull[0], 27 * Cfg::B_BYTES);
-        for (int t = 0; t < 27; ++t) tma_load_2d(w_base + t * Cfg::B_BYTES, &maps.w, &wfull[0], 0, t * Cfg::B_ROWS);
+        mbar_expect_tx(&wfull[0], p.nslab * 9 * Cfg::B_BYTES);
+        for (int t = 0; t < p.nslab * 9; ++t) tma_load_2d(w_base + t * Cfg::B_BYTES, &maps.w, &wfull[0], 0, t * Cfg::B_ROWS);
       }
       uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -556,13 +565,13 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         const int th = r % p.tiles_h; r /= p.tiles_h;
         const int td = r % p.Dt;
         const int b = r / p.Dt;
-        for (int kd = 0; kd < 3; ++kd) {
+        for (int kd = 0; kd < p.nslab; ++kd) {
           mbar_wait(&aempty[sa], pa ^ 1);
           mbar_expect_tx(&afull[sa], PLANES * Cfg::SLAB_BYTES);
 #pragma unroll
           for (int pl = 0; pl < PLANES; ++pl)
-            tma_load_5d(a_base + sa * Cfg::A_SLOT + pl * Cfg::SLAB_PITCH, &maps.a[0], &afull[sa], 0, tw * TC_TW - 1,
-                        th * TC_TH - 1, td + kd - 1, pl * p.B + b);
+            tma_load_5d(a_base + sa * Cfg::A_SLOT + pl * Cfg::SLAB_PITCH, &maps.a[0], &afull[sa], p.slab_c0[kd],
+                        tw * TC_TW - 1, th * TC_TH - 1, td + p.slab_dz[kd], pl * p.B + b);
           if (++sa == Cfg::A_SLOTS) { sa = 0; pa ^= 1; }
           if (!Cfg::WRES) {
             for (int kh = 0; kh < 3; ++kh) {
@@ -596,7 +605,7 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         tc_fence_after();
         const uint32_t d_addr = tmem_base + acc * NACC;
 #pragma unroll 1
-        for (int kd = 0; kd < 3; ++kd) {
+        for (int kd = 0; kd < p.nslab; ++kd) {
           mbar_wait(&afull[sa], pa);
           tc_fence_after();
           const uint64_t da_slab = DA + ((a_u32 + sa * Cfg::A_SLOT) >> 4);
@@ -970,6 +979,23 @@ static int launch_tc_halo(const TcMaps& maps, const TcParams& p, cudaStream_t st
 }
 
 
+// ------------------------------------------------------------------ 2-D 3x3 convs (PropgationNet_4x.conv, gwcnet_dca_g.py:112-115)
+// weight pack for the 2-D path: [Cout chunk of 64][channel slab of 64][tap 9][plane][64][64] bf16 (zero padded)
+__global__ void pack_weight_tc2d_kernel(const float* __restrict__ w, int Co, int Ci, __nv_bfloat16* __restrict__ out,
+                                        int planes, int nchunk, int nslab) {
+  const int total = nchunk * nslab * 9 * 64 * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ci = i % 64, co = (i / 64) % 64, t = (i / 4096) % 9, sl = (i / (4096 * 9)) % nslab, j = i / (4096 * 9 * nslab);
+    const int gco = j * 64 + co, gci = sl * 64 + ci;
+    const float v = (gco < Co && gci < Ci) ? w[((size_t)gco * Ci + gci) * 9 + t] : 0.f;
+    uint32_t lo;
+    const uint32_t hi = split_bf16(v, lo);
+    const size_t tapbase = ((size_t)(j * nslab + sl) * 9 + t) * planes;
+    out[((tapbase + 0) * 64 + co) * 64 + ci] = __ushort_as_bfloat16((unsigned short)hi);
+    if (planes == 2) out[((tapbase + 1) * 64 + co) * 64 + ci] = __ushort_as_bfloat16((unsigned short)lo);
+  }
+}
+
 template <int CIN, int PLANES, int NSLAB>
 static int launch_up2(const TcMaps& maps, const TcParams& p, const Up2Params& u, cudaStream_t st) {
   using Cfg = Up2Cfg<CIN, PLANES, NSLAB>;
@@ -1018,6 +1044,7 @@ extern "C" int dca_up2_tc(int kind, const void* x, int planes, const void* side,
   p.res_plane = (size_t)B * Do * Ho * Wo * Cout; p.planes_res = planes_res;
   p.y = (__nv_bfloat16*)y; p.y_plane = p.res_plane; p.planes_out = P; p.act = act;
   p.npart = P; p.ngrp = 1; p.dbg = g_dbg;
+  p.ldc = Cout; p.cout_valid = Cout;
   p.Dt = Dl; p.Ht = Hl; p.Wt = Wl; p.out_stride = 2; p.ncls = 8; p.cls_inner = 1;
   p.tiles_w = (Wl + TC_TW - 1) / TC_TW; p.tiles_h = (Hl + TC_TH - 1) / TC_TH;
   // main input: halo box 10 x 18 whose origin is the tile origin (kind 1: the +1 of the padding cancels the -1 halo)
@@ -1140,6 +1167,8 @@ extern "C" int dca_conv3d_tc(int mode, const void* x, int planes_in, const void*
   p.y = (__nv_bfloat16*)y; p.y_plane = p.res_plane; p.planes_out = planes_out; p.act = act;
   p.npart = P; p.ngrp = 1; p.lo_sep = 0; p.dbg = g_dbg;
   p.up = (const __nv_bfloat16*)up; p.planes_up = planes_up;
+  p.nslab = 3; p.slab_dz[0] = -1; p.slab_dz[1] = 0; p.slab_dz[2] = 1;
+  p.ldc = Cout; p.cout_valid = Cout;
   const size_t sW = Cin, sH = (size_t)Wi * Cin, sD = (size_t)Hi * Wi * Cin, sB = (size_t)Di * Hi * Wi * Cin;
   const int ntaps_total = (mode == 3) ? 1 : (side ? 28 : 27);
   if (!make_w_map(&maps.w, w_tc, Cin, ntaps_total * P * Cout, P * Cout)) return DCA_ERR_LAUNCH;
@@ -1265,4 +1294,52 @@ extern "C" int dca_conv3d_tc(int mode, const void* x, int planes_in, const void*
   }
   p.cls_tap0[8] = (unsigned char)p.ntaps;
   return run();
+}
+
+extern "C" long long dca_pack_weights_tc2d_bytes(int Co, int Ci, int planes) {
+  if (Co <= 0 || (Ci != 64 && Ci != 128) || planes < 1 || planes > 2) return 0;
+  return (long long)((Co + 63) / 64) * (Ci / 64) * 9 * planes * 64 * 64 * 2;
+}
+
+extern "C" int dca_pack_weights_tc2d(const float* w, int Co, int Ci, void* out, int planes, void* stream) {
+  if (!w || !out || dca_pack_weights_tc2d_bytes(Co, Ci, planes) == 0) return DCA_ERR_ARG;
+  const int nchunk = (Co + 63) / 64, nslab = Ci / 64, total = nchunk * nslab * 9 * 4096;
+  pack_weight_tc2d_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, Co, Ci, (__nv_bfloat16*)out, planes,
+                                                                                 nchunk, nslab);
+  DCA_RETURN_IF_LAUNCH_FAILED();
+  return DCA_OK;
+}
+
+// y = act(scale * conv2d_3x3(x) + shift): x cost planes [P][B][1][H][W][Cin], Cin in {64,128}; y = cost planes
+// [P][B][1][H][W][Cout] (Cout % 64 == 0) or, with out_f32, fp32 channels-last [B][H][W][Cout] (any Cout).
+// Runs the halo-slab tcgen05 kernel once per 64-channel output chunk; Cin = 128 is two channel slabs.
+extern "C" int dca_conv2d_tc(const void* x, int planes, const void* w_tc2d, const float* scale, const float* shift,
+                             void* y, int out_f32, int act, int B, int Cin, int Cout, int H, int W, void* stream) {
+  if (!x || !w_tc2d || !y || B <= 0 || planes < 1 || planes > 2 || H <= 0 || W <= 0) return DCA_ERR_ARG;
+  if ((Cin != 64 && Cin != 128) || Cout <= 0 || (!out_f32 && (Cout % 64) != 0)) return DCA_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = planes, nslab = Cin / 64, nchunk = (Cout + 63) / 64;
+  TcMaps maps;
+  if (!make_act_map(&maps.a[0], x, Cin, W, H, 1, P * B, (size_t)Cin, (size_t)W * Cin, (size_t)H * W * Cin,
+                    (size_t)H * W * Cin, HB_W, HB_H, 64))
+    return DCA_ERR_LAUNCH;
+  for (int i = 1; i < 9; ++i) maps.a[i] = maps.a[0];
+  for (int j = 0; j < nchunk; ++j) {
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.Do = 1; p.Ho = H; p.Wo = W;
+    p.scale = scale ? scale + j * 64 : nullptr; p.shift = shift ? shift + j * 64 : nullptr;
+    p.y = (__nv_bfloat16*)y; p.y_plane = (size_t)B * H * W * Cout; p.res_plane = p.y_plane; p.planes_res = 1;
+    p.planes_out = P; p.act = act; p.npart = P; p.ngrp = 1; p.dbg = g_dbg;
+    p.ldc = Cout; p.co_base = j * 64; p.cout_valid = Cout; p.out_f32 = out_f32;
+    p.nslab = nslab; p.slab_c0[0] = 0; p.slab_c0[1] = 64; p.slab_dz[0] = p.slab_dz[1] = 0;
+    p.Dt = 1; p.Ht = H; p.Wt = W; p.out_stride = 1; p.ntaps = 9 * nslab; p.ncls = 1;
+    p.cls_tap0[0] = 0; p.cls_tap0[1] = (unsigned char)(9 * nslab);
+    p.tiles_w = (W + TC_TW - 1) / TC_TW; p.tiles_h = (H + TC_TH - 1) / TC_TH;
+    const __nv_bfloat16* wj = (const __nv_bfloat16*)w_tc2d + (size_t)j * nslab * 9 * P * 64 * 64;
+    if (!make_w_map(&maps.w, wj, 64, nslab * 9 * P * 64, P * 64)) return DCA_ERR_LAUNCH;
+    const int rc = P == 2 ? launch_tc_halo<64, 64, 2>(maps, p, st) : launch_tc_halo<64, 64, 1>(maps, p, st);
+    if (rc != DCA_OK) return rc;
+  }
+  return DCA_OK;
 }

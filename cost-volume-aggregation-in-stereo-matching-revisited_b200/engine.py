@@ -121,6 +121,7 @@ class Options:
     tc_modes = {0, 1, 2, 3}       # conv modes the tcgen05 kernel takes (K3S1, K3S2, T3S2, K1)
     fuse_upsample_in_conv = True  # cva fuse stage: fold the trilinear upsample into the 1x1x1 conv's epilogue
     fuse_redir_in_deconv = True   # Multi_Aggregation: conv3 (transposed) + redir (1x1x1) as one GEMM
+    prop_on_tc = True             # the two 3x3 Conv2d of PropgationNet_4x on the halo-slab tcgen05 kernel
     use_up2 = True                # class-wise halo-slab kernel for the transposed conv and the trilinear fuse stage
 
 
@@ -161,6 +162,46 @@ def conv(x: Planes, pc: PackedConv, mode=K3S1, act=ACT_NONE, res_pre: Planes = N
               res_pre.ptr if res_pre is not None else 0, res_post.ptr if res_post is not None else 0, planes_res,
               yptr, planes_out, 1 if out_fp32 else 0, act, x.B, pc.cin, pc.cout, pc.cout_pad, x.D, x.H, x.W, Do, Ho,
               Wo, _stream())
+    return y
+
+
+class PackedConv2dTc:
+    """3x3 Conv2d (+ optional BN) packed for dca_conv2d_tc: bf16 hi/lo weights in 64x64 (Cout chunk, Cin slab) tiles,
+    BN folded to fp32 scale/shift padded to a multiple of 64."""
+
+    def __init__(self, weight, bn, planes):
+        w = weight.detach().contiguous().float()
+        self.cout, self.cin = w.shape[0], w.shape[1]
+        dev = w.device
+        nb = _lib.load().dca_pack_weights_tc2d_bytes(self.cout, self.cin, planes)
+        if nb <= 0:
+            raise _lib.DcaError("dca_conv2d_tc supports Cin in {64,128}")
+        self.w = torch.empty(nb, dtype=torch.uint8, device=dev)
+        _lib.call("dca_pack_weights_tc2d", w.data_ptr(), self.cout, self.cin, self.w.data_ptr(), planes, _stream())
+        self.planes = planes
+        self.scale = self.shift = None
+        if bn is not None:
+            cpad = (self.cout + 63) // 64 * 64
+            self.scale = torch.empty(cpad, dtype=torch.float32, device=dev)
+            self.shift = torch.empty(cpad, dtype=torch.float32, device=dev)
+            g, b = bn.weight.detach().float().contiguous(), bn.bias.detach().float().contiguous()
+            m, v = bn.running_mean.detach().float().contiguous(), bn.running_var.detach().float().contiguous()
+            _lib.call("dca_fold_bn", g.data_ptr(), b.data_ptr(), m.data_ptr(), v.data_ptr(), float(bn.eps),
+                      self.scale.data_ptr(), self.shift.data_ptr(), self.cout, cpad, _stream())
+        torch.cuda.current_stream().synchronize()
+
+
+def conv2d_tc(x: Planes, pc: PackedConv2dTc, act=ACT_NONE, out_fp32=False):
+    assert x.D == 1 and x.C == pc.cin and x.planes == pc.planes
+    dev = x.t.device
+    if out_fp32:
+        y = torch.empty((x.B, 1, x.H, x.W, pc.cout), dtype=torch.float32, device=dev)
+        yptr = y.data_ptr()
+    else:
+        y = Planes(x.B, 1, x.H, x.W, pc.cout, x.planes, dev)
+        yptr = y.ptr
+    _lib.call("dca_conv2d_tc", x.ptr, x.planes, pc.w.data_ptr(), _ptr(pc.scale), _ptr(pc.shift), yptr, int(out_fp32),
+              act, x.B, pc.cin, pc.cout, x.H, x.W, _stream())
     return y
 
 
@@ -394,6 +435,8 @@ class PackedHotPath:
         self.cls3_2 = pack_cout1(net.classif3[2].weight)
         self.prop0 = pack_convbn(net.prop.conv[0])
         self.prop2 = PackedConv(net.prop.conv[2].weight)
+        self.prop0_tc = PackedConv2dTc(net.prop.conv[0][0].weight, net.prop.conv[0][1], planes)
+        self.prop2_tc = PackedConv2dTc(net.prop.conv[2].weight, None, planes)
         for pc in (self.dres0_0, self.dres0_2, self.dres1_0, self.dres1_2, self.cls3_0):
             pc.pack_tc(planes)
 
@@ -420,8 +463,12 @@ def hot_path_forward(pk: PackedHotPath, gwc_l, gwc_r, cat_l, cat_r, g, keep=None
     logits = conv_cout1(h, pk.cls3_2)
     pred_q = softmax_regress(logits)
     gp = Planes.from_ncdhw(_f32c(g), planes=P)
-    m1 = conv(gp, pk.prop0, C2D3, ACT_RELU)
-    mask = conv(m1, pk.prop2, C2D3, ACT_NONE, out_fp32=True)
+    if Options.use_tc and Options.prop_on_tc:
+        m1 = conv2d_tc(gp, pk.prop0_tc, ACT_RELU)
+        mask = conv2d_tc(m1, pk.prop2_tc, ACT_NONE, out_fp32=True)
+    else:
+        m1 = conv(gp, pk.prop0, C2D3, ACT_RELU)
+        mask = conv(m1, pk.prop2, C2D3, ACT_NONE, out_fp32=True)
     pred4 = convex_upsample(mask, pred_q)
     if keep is not None:
         keep.update(volume=vol, dres0=c, cost0=cost0, out1=out1, cva1=k1, cva2=k2, cva3=k3,

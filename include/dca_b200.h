@@ -83,6 +83,12 @@ long long dca_pack_weights_tc_bytes(int Co, int Ci, int taps, int planes);
 int dca_up2_tc(int kind, const void* x, int planes, const void* side, int side_c, const void* w_tc, const float* scale,
                const float* shift, const void* res_post, int planes_res, void* y, int act, int B, int Cin, int Dl,
                int Hl, int Wl, void* stream);
+/* 2-D 3x3 s1 p1 convs of the propagation net (gwcnet_dca_g.py:112-115) on the halo-slab tcgen05 kernel.
+ * x [planes][B][1][H][W][Cin] (Cin 64/128); y cost planes (Cout % 64 == 0) or fp32 channels-last [B][H][W][Cout]. */
+int dca_conv2d_tc(const void* x, int planes, const void* w_tc2d, const float* scale, const float* shift, void* y,
+                  int out_f32, int act, int B, int Cin, int Cout, int H, int W, void* stream);
+int dca_pack_weights_tc2d(const float* w, int Co, int Ci, void* out, int planes, void* stream);
+long long dca_pack_weights_tc2d_bytes(int Co, int Ci, int planes);
 /* k3 s1 main loop selector: 1 = halo'd slab reuse (default), 0 = one TMA box per tap. */
 int dca_tc_set_halo(int on);
 /* halo kernel tuning: taps interleaved over ngrp (1,2,4) independent TMEM accumulator groups; lo_sep = own block for lo*Whi. */

@@ -171,6 +171,34 @@ def test_conv_cout1_and_2d():
     close(mask[:, 0].permute(0, 3, 1, 2), ref, 5e-5, "prop convs")
 
 
+@pytest.mark.parametrize("planes", [2, 1])
+def test_prop_convs_on_tcgen05(planes):
+    """The two 3x3 Conv2d of PropgationNet_4x (64->128 +BN+ReLU, 128->144) on the halo-slab tcgen05 kernel."""
+    d, E, O = _mods()
+    g = rnd(2, 64, 19, 37, seed=30)
+    c1 = torch.nn.Conv2d(64, 128, 3, padding=1, bias=False)
+    c2 = torch.nn.Conv2d(128, 144, 3, padding=1, bias=False)
+    bn = torch.nn.BatchNorm2d(128).eval()
+    bn.running_mean.normal_(0, 0.1, generator=torch.Generator().manual_seed(3)); bn.running_var.uniform_(0.5, 1.0)
+    gin = g
+    w1, w2 = c1.weight.data.clone(), c2.weight.data.clone()
+    if planes == 1:
+        gin = g.to(torch.bfloat16).float()
+        c1.weight.data, c2.weight.data = w1.to(torch.bfloat16).float(), w2.to(torch.bfloat16).float()
+    with torch.no_grad():
+        mid = F.relu(bn(c1(gin)))
+        if planes == 1:
+            mid = mid.to(torch.bfloat16).float()
+        ref = c2(mid)
+    c1.weight.data, c2.weight.data = w1, w2
+    gp = E.Planes.from_ncdhw(g.cuda(), planes)
+    p1 = E.PackedConv2dTc(c1.weight.cuda(), bn.cuda(), planes)
+    p2 = E.PackedConv2dTc(c2.weight.cuda(), None, planes)
+    m1 = E.conv2d_tc(gp, p1, E.ACT_RELU)
+    mask = E.conv2d_tc(m1, p2, E.ACT_NONE, out_fp32=True)
+    close(mask[:, 0].permute(0, 3, 1, 2), ref, 1e-4 if planes == 2 else 2e-2, "prop convs tc")
+
+
 def test_avgpool_and_planes_roundtrip():
     d, E, O = _mods()
     x = rnd(2, 32, 6, 9, 21, seed=11)
