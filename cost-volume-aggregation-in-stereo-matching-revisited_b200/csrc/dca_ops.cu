@@ -100,6 +100,11 @@ class_stats_kernel(const float* __restrict__ logits, int* __restrict__ cls, floa
 // Weights: 7 matrices stored transposed [ci][co] fp32, then 6 x (scale[32], shift[32]).
 // ------------------------------------------------------------------------------------------------
 constexpr int AT_C = 32;
+__device__ __forceinline__ float fast_exp2(float x) {   // ex2.approx: rel. error 2^-22, -inf -> 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 constexpr int AT_NMAT = 7;
 constexpr int AT_WFLOATS = AT_NMAT * AT_C * AT_C + 6 * 2 * AT_C;
 
@@ -113,8 +118,8 @@ __device__ __forceinline__ void warp_project(const float* __restrict__ in, float
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 #pragma unroll
     for (int c4 = 0; c4 < AT_C; c4 += 4) {
-      const float w0 = Wt[(c4 + 0) * AT_C + lane], w1 = Wt[(c4 + 1) * AT_C + lane];
-      const float w2 = Wt[(c4 + 2) * AT_C + lane], w3 = Wt[(c4 + 3) * AT_C + lane];
+      const float4 wv = *reinterpret_cast<const float4*>(Wt + (c4 * AT_C + lane * 4));   // [ci/4][co][4]
+      const float w0 = wv.x, w1 = wv.y, w2 = wv.z, w3 = wv.w;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 xv = *reinterpret_cast<const float4*>(in + (d0 + j) * AT_C + c4);
@@ -144,7 +149,12 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* buf = smem + ((AT_WFLOATS + 3) & ~3) + (size_t)warp * 4 * Dp * AT_C;
   float* bA = buf, *bB = buf + Dp * AT_C, *bC = buf + 2 * Dp * AT_C, *bD = buf + 3 * Dp * AT_C;
-  for (int i = threadIdx.x; i < AT_WFLOATS; i += blockDim.x) W[i] = __ldg(wts + i);
+  // matrices arrive transposed [ci][co]; keep them as [ci/4][co][4] so a lane fetches 4 input channels per LDS.128
+  for (int i = threadIdx.x; i < AT_NMAT * AT_C * AT_C; i += blockDim.x) {
+    const int m = i >> 10, r = i & 1023, ci = r >> 5, co = r & 31;
+    W[(m << 10) + ((ci >> 2) * AT_C + co) * 4 + (ci & 3)] = __ldg(wts + i);
+  }
+  for (int i = AT_NMAT * AT_C * AT_C + threadIdx.x; i < AT_WFLOATS; i += blockDim.x) W[i] = __ldg(wts + i);
   // rows [D, Dp) are never written by the loads below: clear them once so no NaN garbage circulates
   for (int i = lane; i < 4 * Dp * AT_C; i += 32) buf[i] = 0.f;
   __syncthreads();
@@ -152,7 +162,7 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
              *Wa = W + 6144;
   const float* ss = W + AT_NMAT * 1024;              // 6 x (scale, shift): q0 q1 k0 k1 v o
   const size_t plane = (size_t)B * D * HW * AT_C;
-  const float inv_sqrt = 0.35355339059327373f;       // 8^-0.5
+  const float qscale = 0.35355339059327373f * 1.4426950408889634f;   // 8^-0.5 * log2(e): scores in the log2 domain
 
   for (int pix = blockIdx.x * warps + warp; pix < B * HW; pix += gridDim.x * warps) {
     const int b = pix / HW, p = pix % HW;
@@ -181,8 +191,10 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
     // ---- attention: item = (dq, head), 4 heads x D queries ----
     for (int item = lane; item < 4 * D; item += 32) {
       const int dq = item >> 2, hd = item & 3;
-      const float4 q0 = *reinterpret_cast<const float4*>(bD + dq * AT_C + hd * 8);
-      const float4 q1 = *reinterpret_cast<const float4*>(bD + dq * AT_C + hd * 8 + 4);
+      float4 q0 = *reinterpret_cast<const float4*>(bD + dq * AT_C + hd * 8);
+      float4 q1 = *reinterpret_cast<const float4*>(bD + dq * AT_C + hd * 8 + 4);
+      q0.x *= qscale; q0.y *= qscale; q0.z *= qscale; q0.w *= qscale;
+      q1.x *= qscale; q1.y *= qscale; q1.z *= qscale; q1.w *= qscale;
       float m = -INFINITY, l = 0.f, c[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) c[i] = 0.f;
@@ -191,9 +203,8 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
         const float4 k1 = *reinterpret_cast<const float4*>(bC + dk * AT_C + hd * 8 + 4);
         float s = q0.x * k0.x + q0.y * k0.y + q0.z * k0.z + q0.w * k0.w + q1.x * k1.x + q1.y * k1.y + q1.z * k1.z +
                   q1.w * k1.w;
-        s *= inv_sqrt;
         const float mn = fmaxf(m, s);
-        const float corr = expf(m - mn), pe = expf(s - mn);
+        const float corr = fast_exp2(m - mn), pe = fast_exp2(s - mn);
         const float4 v0 = *reinterpret_cast<const float4*>(bA + dk * AT_C + hd * 8);
         const float4 v1 = *reinterpret_cast<const float4*>(bA + dk * AT_C + hd * 8 + 4);
         l = l * corr + pe;
@@ -560,7 +571,7 @@ extern "C" int dca_disp_attention(const void* x, const int* cls, const float* e,
   const int Dp = (D + 7) & ~7;
   int warps = 8;
   size_t wbytes = (size_t)((AT_WFLOATS + 3) & ~3) * sizeof(float);
-  while (warps > 1 && wbytes + (size_t)warps * 4 * Dp * AT_C * sizeof(float) > 200 * 1024) warps >>= 1;
+  while (warps > 1 && wbytes + (size_t)warps * 4 * Dp * AT_C * sizeof(float) > 227 * 1024) warps >>= 1;
   const size_t smem = wbytes + (size_t)warps * 4 * Dp * AT_C * sizeof(float);
   if (smem > 227 * 1024) return DCA_ERR_UNSUPPORTED;
   const int HW = H * W;
