@@ -138,6 +138,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     H, W, maxdisp, B = workloads.CONFIGS[args.config]
+    global METRIC
+    if args.config != "kitti_384x1248":
+        METRIC = f"{args.config} pairs/s"
 
     if args.impl == "reference":
         if rank != 0:

@@ -9,6 +9,7 @@ CONFIGS = {
     "parity_256x512": (256, 512, 192, 1),     # configs[0]
     "kitti_384x1248": (384, 1248, 192, 1),    # configs[1]  <- the metric's config
     "sceneflow_544x960": (544, 960, 192, 1),  # configs[2] (batch 64 = 64 steps of this)
+    "middlebury_1536x2048": (1536, 2048, 384, 1),   # configs[4], runs un-sharded on one 180 GB B200
     "tiny_64x128": (64, 128, 48, 1),
 }
 
