@@ -108,59 +108,138 @@ __device__ __forceinline__ float fast_exp2(float x) {   // ex2.approx: rel. erro
 constexpr int AT_NMAT = 7;
 constexpr int AT_WFLOATS = AT_NMAT * AT_C * AT_C + 6 * 2 * AT_C;
 
-__device__ __forceinline__ void warp_project(const float* __restrict__ in, float* __restrict__ out,
-                                             const float* __restrict__ Wt, const float* __restrict__ ss, int Dp,
-                                             int lane, bool affine_act) {
-  const float sc = affine_act ? ss[lane] : 1.f, sh = affine_act ? ss[AT_C + lane] : 0.f;
-  for (int d0 = 0; d0 < Dp; d0 += 8) {
-    float acc[8];
+// ---- warp-level tensor-core projection (mma.sync m16n8k16 bf16, fp32 accumulate, split-bf16 operands) ----
+// Activations live in shared memory as two bf16 planes (hi, lo), rows of 32 channels padded to 40 elements
+// (80 B pitch: conflict-free ldmatrix).  Weights are [co][ci] (K-major) bf16 hi/lo with the same pitch.
+// y[d][co] = act(scale[co] * sum_ci x[d][ci] W[co][ci] + shift[co]),  x.W ~ hi.Whi + hi.Wlo + lo.Whi
+constexpr int AT_PITCH = 40;                         // bf16 elements per smem row
+constexpr int AT_WPLANE = AT_C * AT_PITCH;           // one weight plane (32 rows)
+
+__device__ __forceinline__ void ldsm_x4(uint32_t saddr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(saddr));
+}
+__device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void at_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// src: bf16 pair [2][rows][AT_PITCH]; Wm: weight pair [2][32][AT_PITCH]; MT = number of 16-row tiles.
+// dst_pair != nullptr: result written as a bf16 pair (input of the next projection);
+// dst_f32  != nullptr: result written as fp32 [rows][32].
+template <int MT>
+__device__ __forceinline__ void warp_project_mma(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ Wm,
+                                                 const float* __restrict__ ss, bool affine_act,
+                                                 __nv_bfloat16* __restrict__ dst_pair, float* __restrict__ dst_f32,
+                                                 int lane) {
+  constexpr int ROWS = 16 * MT;
+  float acc[MT][4][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int c4 = 0; c4 < AT_C; c4 += 4) {
-      const float4 wv = *reinterpret_cast<const float4*>(Wt + (c4 * AT_C + lane * 4));   // [ci/4][co][4]
-      const float w0 = wv.x, w1 = wv.y, w2 = wv.z, w3 = wv.w;
+    for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 xv = *reinterpret_cast<const float4*>(in + (d0 + j) * AT_C + c4);
-        acc[j] = fmaf(xv.x, w0, acc[j]); acc[j] = fmaf(xv.y, w1, acc[j]);
-        acc[j] = fmaf(xv.z, w2, acc[j]); acc[j] = fmaf(xv.w, w3, acc[j]);
-      }
+      for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+  const uint32_t s_src = (uint32_t)__cvta_generic_to_shared(src);
+  const uint32_t s_w = (uint32_t)__cvta_generic_to_shared(Wm);
+  // ldmatrix row address of this lane: A tiles (row = l%8 + 8*((l/8)%2), col = 8*(l/16)); B tiles (two n-tiles per x4:
+  // row n = l%8 + 8*(l/16), col k = 8*((l/8)%2))
+  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_col = (lane >> 4) * 8;
+  const int b_row = (lane & 7) + (lane >> 4) * 8, b_col = ((lane >> 3) & 1) * 8;
+#pragma unroll
+  for (int kt = 0; kt < 2; ++kt) {
+    uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {           // n-tile pairs (0,1) and (2,3)
+      const uint32_t off = (uint32_t)(((np * 16 + b_row) * AT_PITCH + kt * 16 + b_col) * 2);
+      ldsm_x4(s_w + off, bh[2 * np][0], bh[2 * np][1], bh[2 * np + 1][0], bh[2 * np + 1][1]);
+      ldsm_x4(s_w + AT_WPLANE * 2 + off, bl[2 * np][0], bl[2 * np][1], bl[2 * np + 1][0], bl[2 * np + 1][1]);
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float v = acc[j] * sc + sh;
-      if (affine_act) v = v > 0.f ? v : 0.1f * v;
-      out[(d0 + j) * AT_C + lane] = v;
+    for (int mt = 0; mt < MT; ++mt) {
+      uint32_t ah[4], al[4];
+      const uint32_t off = (uint32_t)(((mt * 16 + a_row) * AT_PITCH + kt * 16 + a_col) * 2);
+      ldsm_x4(s_src + off, ah[0], ah[1], ah[2], ah[3]);
+      ldsm_x4(s_src + ROWS * AT_PITCH * 2 + off, al[0], al[1], al[2], al[3]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        mma_bf16(acc[mt][nt], ah, bh[nt][0], bh[nt][1]);
+        mma_bf16(acc[mt][nt], ah, bl[nt][0], bl[nt][1]);
+        mma_bf16(acc[mt][nt], al, bh[nt][0], bh[nt][1]);
+      }
+    }
+  }
+  // epilogue: thread (g = lane/4, t = lane%4) holds rows g, g+8 and columns nt*8 + 2t, +1 of every tile
+  const int g = lane >> 2, t2 = (lane & 3) * 2;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int col = nt * 8 + t2;
+    float sc0 = 1.f, sc1 = 1.f, sh0 = 0.f, sh1 = 0.f;
+    if (affine_act) { sc0 = ss[col]; sc1 = ss[col + 1]; sh0 = ss[AT_C + col]; sh1 = ss[AT_C + col + 1]; }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+      for (int hrow = 0; hrow < 2; ++hrow) {
+        const int row = mt * 16 + g + hrow * 8;
+        float v0 = acc[mt][nt][hrow * 2] * sc0 + sh0, v1 = acc[mt][nt][hrow * 2 + 1] * sc1 + sh1;
+        if (affine_act) { v0 = v0 > 0.f ? v0 : 0.1f * v0; v1 = v1 > 0.f ? v1 : 0.1f * v1; }
+        if (dst_f32) *reinterpret_cast<float2*>(dst_f32 + row * AT_C + col) = make_float2(v0, v1);
+        if (dst_pair) {
+          uint32_t hi, lo;
+          at_split2(v0, v1, hi, lo);
+          *reinterpret_cast<uint32_t*>(dst_pair + row * AT_PITCH + col) = hi;
+          *reinterpret_cast<uint32_t*>(dst_pair + ROWS * AT_PITCH + row * AT_PITCH + col) = lo;
+        }
+      }
     }
   }
   __syncwarp();
 }
 
-template <int PLANES>
+// DT = compile-time disparity count (24 at KITTI/SceneFlow: scores stay in registers, two-pass softmax); 0 = runtime D
+template <int PLANES, int MT, int DT>
 __global__ void __launch_bounds__(256)
 disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ cls, const float* __restrict__ e,
                       const float* __restrict__ S, const float* __restrict__ wts, int has_wa,
                       __nv_bfloat16* __restrict__ y, int B, int D, int H, int Wd, int pad) {
+  constexpr int ROWS = 16 * MT;
+  constexpr int PAIR = 2 * ROWS * AT_PITCH;                    // bf16 elements of one (hi, lo) activation pair
+  constexpr int FBUF = ROWS * AT_C;                            // floats of one fp32 buffer
   const int HW = H * Wd;
-  extern __shared__ __align__(16) float smem[];
-  float* W = smem;                                   // AT_WFLOATS
-  const int Dp = (D + 7) & ~7;
+  extern __shared__ __align__(16) uint8_t smem_at[];
+  __nv_bfloat16* Wsm = reinterpret_cast<__nv_bfloat16*>(smem_at);               // [7][2][32][AT_PITCH]
+  float* ss = reinterpret_cast<float*>(smem_at + AT_NMAT * 2 * AT_WPLANE * 2);   // 6 x (scale[32], shift[32])
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* buf = smem + ((AT_WFLOATS + 3) & ~3) + (size_t)warp * 4 * Dp * AT_C;
-  float* bA = buf, *bB = buf + Dp * AT_C, *bC = buf + 2 * Dp * AT_C, *bD = buf + 3 * Dp * AT_C;
-  // matrices arrive transposed [ci][co]; keep them as [ci/4][co][4] so a lane fetches 4 input channels per LDS.128
+  uint8_t* wbase = smem_at + AT_NMAT * 2 * AT_WPLANE * 2 + 6 * 64 * 4 + (size_t)warp * (3 * PAIR * 2 + 3 * FBUF * 4);
+  __nv_bfloat16* P0 = reinterpret_cast<__nv_bfloat16*>(wbase);
+  __nv_bfloat16* P1 = P0 + PAIR;
+  __nv_bfloat16* P2 = P1 + PAIR;
+  float* F0 = reinterpret_cast<float*>(P2 + PAIR);
+  float* F1 = F0 + FBUF;
+  float* F2 = F1 + FBUF;
+  // weights arrive fp32, transposed [m][ci][co]; keep them as bf16 hi/lo [m][plane][co][ci]
   for (int i = threadIdx.x; i < AT_NMAT * AT_C * AT_C; i += blockDim.x) {
     const int m = i >> 10, r = i & 1023, ci = r >> 5, co = r & 31;
-    W[(m << 10) + ((ci >> 2) * AT_C + co) * 4 + (ci & 3)] = __ldg(wts + i);
+    uint32_t lo;
+    const uint32_t hi = split_bf16(__ldg(wts + i), lo);
+    Wsm[(m * 2 + 0) * AT_WPLANE + co * AT_PITCH + ci] = __ushort_as_bfloat16((unsigned short)hi);
+    Wsm[(m * 2 + 1) * AT_WPLANE + co * AT_PITCH + ci] = __ushort_as_bfloat16((unsigned short)lo);
   }
-  for (int i = AT_NMAT * AT_C * AT_C + threadIdx.x; i < AT_WFLOATS; i += blockDim.x) W[i] = __ldg(wts + i);
-  // rows [D, Dp) are never written by the loads below: clear them once so no NaN garbage circulates
-  for (int i = lane; i < 4 * Dp * AT_C; i += 32) buf[i] = 0.f;
+  for (int i = threadIdx.x; i < 6 * 64; i += blockDim.x) ss[i] = __ldg(wts + AT_NMAT * AT_C * AT_C + i);
+  // zero this warp's buffers once: rows [D, ROWS) are never loaded and must stay finite
+  for (int i = lane; i < (3 * PAIR * 2 + 3 * FBUF * 4) / 4; i += 32) reinterpret_cast<uint32_t*>(wbase)[i] = 0u;
   __syncthreads();
-  const float* Wq0 = W, *Wq1 = W + 1024, *Wk0 = W + 2048, *Wk1 = W + 3072, *Wv = W + 4096, *Wo = W + 5120,
-             *Wa = W + 6144;
-  const float* ss = W + AT_NMAT * 1024;              // 6 x (scale, shift): q0 q1 k0 k1 v o
+  const __nv_bfloat16* Wq0 = Wsm, *Wq1 = Wsm + 2 * AT_WPLANE, *Wk0 = Wsm + 4 * AT_WPLANE, *Wk1 = Wsm + 6 * AT_WPLANE,
+                      *Wv = Wsm + 8 * AT_WPLANE, *Wo = Wsm + 10 * AT_WPLANE, *Wa = Wsm + 12 * AT_WPLANE;
   const size_t plane = (size_t)B * D * HW * AT_C;
   const float qscale = 0.35355339059327373f * 1.4426950408889634f;   // 8^-0.5 * log2(e): scores in the log2 domain
 
@@ -168,61 +247,164 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
     const int b = pix / HW, p = pix % HW;
     const int kp = cls[pix];
     const float wp = e[pix] / S[(size_t)b * D + kp];
-    // ---- load x[d][0..31] -> bA, key -> bB.  lane = (row r = lane/4, chunk q = lane%4) ----
+    // ---- x (already hi/lo in HBM) -> P0 verbatim; key = x * (1 + [d == kp] w_p) -> P1 (re-split on that plane) ----
     for (int d0 = 0; d0 < D; d0 += 8) {
       const int d = d0 + (lane >> 2), q = lane & 3;
       if (d < D) {
-        float f[8];
-        load8<PLANES>(x, plane, (((size_t)b * D + d) * HW + p) * AT_C + q * 8, f);
-        const float ks = (d == kp) ? 1.f + wp : 1.f;
-        float4* a = reinterpret_cast<float4*>(bA + d * AT_C + q * 8);
-        float4* k = reinterpret_cast<float4*>(bB + d * AT_C + q * 8);
-        a[0] = make_float4(f[0], f[1], f[2], f[3]); a[1] = make_float4(f[4], f[5], f[6], f[7]);
-        k[0] = make_float4(f[0] * ks, f[1] * ks, f[2] * ks, f[3] * ks);
-        k[1] = make_float4(f[4] * ks, f[5] * ks, f[6] * ks, f[7] * ks);
-      }
-    }
-    __syncwarp();
-    warp_project(bA, bC, Wq0, ss + 0 * 64, Dp, lane, true);
-    warp_project(bC, bD, Wq1, ss + 1 * 64, Dp, lane, true);    // q  in bD
-    warp_project(bB, bA, Wk0, ss + 2 * 64, Dp, lane, true);
-    warp_project(bA, bC, Wk1, ss + 3 * 64, Dp, lane, true);    // k  in bC
-    warp_project(bB, bA, Wv, ss + 4 * 64, Dp, lane, true);     // v  in bA
-    // ---- attention: item = (dq, head), 4 heads x D queries ----
-    for (int item = lane; item < 4 * D; item += 32) {
-      const int dq = item >> 2, hd = item & 3;
-      float4 q0 = *reinterpret_cast<const float4*>(bD + dq * AT_C + hd * 8);
-      float4 q1 = *reinterpret_cast<const float4*>(bD + dq * AT_C + hd * 8 + 4);
-      q0.x *= qscale; q0.y *= qscale; q0.z *= qscale; q0.w *= qscale;
-      q1.x *= qscale; q1.y *= qscale; q1.z *= qscale; q1.w *= qscale;
-      float m = -INFINITY, l = 0.f, c[8];
+        const size_t off = (((size_t)b * D + d) * HW + p) * AT_C + q * 8;
+        const uint4 h = *reinterpret_cast<const uint4*>(x + off);
+        uint4 l = make_uint4(0, 0, 0, 0);
+        if (PLANES == 2) l = *reinterpret_cast<const uint4*>(x + plane + off);
+        *reinterpret_cast<uint4*>(P0 + d * AT_PITCH + q * 8) = h;
+        *reinterpret_cast<uint4*>(P0 + ROWS * AT_PITCH + d * AT_PITCH + q * 8) = l;
+        uint4 kh = h, kl = l;
+        if (d == kp) {
+          float f[8], g2[8];
+          unpack8(h, f); unpack8(l, g2);
+          const float ks = 1.f + wp;
+          uint32_t hw[4], lw[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) c[i] = 0.f;
-      for (int dk = 0; dk < D; ++dk) {
-        const float4 k0 = *reinterpret_cast<const float4*>(bC + dk * AT_C + hd * 8);
-        const float4 k1 = *reinterpret_cast<const float4*>(bC + dk * AT_C + hd * 8 + 4);
-        float s = q0.x * k0.x + q0.y * k0.y + q0.z * k0.z + q0.w * k0.w + q1.x * k1.x + q1.y * k1.y + q1.z * k1.z +
-                  q1.w * k1.w;
-        const float mn = fmaxf(m, s);
-        const float corr = fast_exp2(m - mn), pe = fast_exp2(s - mn);
-        const float4 v0 = *reinterpret_cast<const float4*>(bA + dk * AT_C + hd * 8);
-        const float4 v1 = *reinterpret_cast<const float4*>(bA + dk * AT_C + hd * 8 + 4);
-        l = l * corr + pe;
-        c[0] = c[0] * corr + pe * v0.x; c[1] = c[1] * corr + pe * v0.y;
-        c[2] = c[2] * corr + pe * v0.z; c[3] = c[3] * corr + pe * v0.w;
-        c[4] = c[4] * corr + pe * v1.x; c[5] = c[5] * corr + pe * v1.y;
-        c[6] = c[6] * corr + pe * v1.z; c[7] = c[7] * corr + pe * v1.w;
-        m = mn;
+          for (int j = 0; j < 4; ++j) at_split2((f[2 * j] + g2[2 * j]) * ks, (f[2 * j + 1] + g2[2 * j + 1]) * ks, hw[j], lw[j]);
+          kh = make_uint4(hw[0], hw[1], hw[2], hw[3]); kl = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+        *reinterpret_cast<uint4*>(P1 + d * AT_PITCH + q * 8) = kh;
+        *reinterpret_cast<uint4*>(P1 + ROWS * AT_PITCH + d * AT_PITCH + q * 8) = kl;
       }
-      const float il = 1.f / l;
-      float4* o = reinterpret_cast<float4*>(bB + dq * AT_C + hd * 8);
-      o[0] = make_float4(c[0] * il, c[1] * il, c[2] * il, c[3] * il);
-      o[1] = make_float4(c[4] * il, c[5] * il, c[6] * il, c[7] * il);
     }
     __syncwarp();
-    warp_project(bB, bC, Wo, ss + 5 * 64, Dp, lane, true);     // aug_down in bC
-    const float* res = bC;
-    if (has_wa) { warp_project(bC, bD, Wa, nullptr, Dp, lane, false); res = bD; }
+    warp_project_mma<MT>(P0, Wq0, ss + 0 * 64, true, P2, nullptr, lane);
+    warp_project_mma<MT>(P2, Wq1, ss + 1 * 64, true, nullptr, F0, lane);     // q  -> F0 (fp32)
+    warp_project_mma<MT>(P1, Wk0, ss + 2 * 64, true, P2, nullptr, lane);
+    warp_project_mma<MT>(P2, Wk1, ss + 3 * 64, true, nullptr, F1, lane);     // k  -> F1
+    warp_project_mma<MT>(P1, Wv, ss + 4 * 64, true, nullptr, F2, lane);      // v  -> F2
+    // ---- attention: item = (dq, head), 4 heads x D queries; a lane owns up to 2*MT items and walks the keys ONCE
+    //      for all of them (independent online-softmax chains interleave -> ILP); ctx -> P0 as a bf16 pair ----
+    if (DT > 0) {
+      // scores of a lane's items stay in registers: pass 1 = all dot products + running max, pass 2 = exp2 and P.V
+      constexpr int NI = (4 * (DT > 0 ? DT : 1) + 31) / 32;
+      constexpr int DK = DT > 0 ? DT : 1;
+      const int hd = lane & 3;
+      float sc[NI][DK], mx[NI];
+      {
+        float4 qa[NI], qb[NI];
+#pragma unroll
+        for (int r = 0; r < NI; ++r) {
+          const int dq = min((lane + 32 * r) >> 2, ROWS - 1);
+          qa[r] = *reinterpret_cast<const float4*>(F0 + dq * AT_C + hd * 8);
+          qb[r] = *reinterpret_cast<const float4*>(F0 + dq * AT_C + hd * 8 + 4);
+          qa[r].x *= qscale; qa[r].y *= qscale; qa[r].z *= qscale; qa[r].w *= qscale;
+          qb[r].x *= qscale; qb[r].y *= qscale; qb[r].z *= qscale; qb[r].w *= qscale;
+          mx[r] = -INFINITY;
+        }
+#pragma unroll
+        for (int dk = 0; dk < DK; ++dk) {
+          const float4 k0 = *reinterpret_cast<const float4*>(F1 + dk * AT_C + hd * 8);
+          const float4 k1 = *reinterpret_cast<const float4*>(F1 + dk * AT_C + hd * 8 + 4);
+#pragma unroll
+          for (int r = 0; r < NI; ++r) {
+            sc[r][dk] = (qa[r].x * k0.x + qa[r].y * k0.y) + (qa[r].z * k0.z + qa[r].w * k0.w) +
+                        (qb[r].x * k1.x + qb[r].y * k1.y) + (qb[r].z * k1.z + qb[r].w * k1.w);
+            mx[r] = fmaxf(mx[r], sc[r][dk]);
+          }
+        }
+      }
+      float ls[NI], c[NI][8];
+#pragma unroll
+      for (int r = 0; r < NI; ++r) {
+        ls[r] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c[r][i] = 0.f;
+      }
+#pragma unroll
+      for (int dk = 0; dk < DK; ++dk) {
+        const float4 v0 = *reinterpret_cast<const float4*>(F2 + dk * AT_C + hd * 8);
+        const float4 v1 = *reinterpret_cast<const float4*>(F2 + dk * AT_C + hd * 8 + 4);
+#pragma unroll
+        for (int r = 0; r < NI; ++r) {
+          const float pe = fast_exp2(sc[r][dk] - mx[r]);
+          ls[r] += pe;
+          c[r][0] = fmaf(pe, v0.x, c[r][0]); c[r][1] = fmaf(pe, v0.y, c[r][1]);
+          c[r][2] = fmaf(pe, v0.z, c[r][2]); c[r][3] = fmaf(pe, v0.w, c[r][3]);
+          c[r][4] = fmaf(pe, v1.x, c[r][4]); c[r][5] = fmaf(pe, v1.y, c[r][5]);
+          c[r][6] = fmaf(pe, v1.z, c[r][6]); c[r][7] = fmaf(pe, v1.w, c[r][7]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < NI; ++r) {
+        const int item = lane + 32 * r;
+        if (item < 4 * D) {
+          const int dq = item >> 2;
+          const float il = 1.f / ls[r];
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) at_split2(c[r][2 * j] * il, c[r][2 * j + 1] * il, hw[j], lw[j]);
+          *reinterpret_cast<uint4*>(P0 + dq * AT_PITCH + hd * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(P0 + ROWS * AT_PITCH + dq * AT_PITCH + hd * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+      }
+    } else
+    {
+      constexpr int NI = 2 * MT;
+      float4 qa[NI], qb[NI];
+      float mx[NI], ls[NI], c[NI][8];
+      int hdv[NI];
+#pragma unroll
+      for (int r = 0; r < NI; ++r) {
+        const int item = lane + 32 * r;
+        const int dq = min(item >> 2, ROWS - 1);
+        hdv[r] = item & 3;
+        qa[r] = *reinterpret_cast<const float4*>(F0 + dq * AT_C + hdv[r] * 8);
+        qb[r] = *reinterpret_cast<const float4*>(F0 + dq * AT_C + hdv[r] * 8 + 4);
+        qa[r].x *= qscale; qa[r].y *= qscale; qa[r].z *= qscale; qa[r].w *= qscale;
+        qb[r].x *= qscale; qb[r].y *= qscale; qb[r].z *= qscale; qb[r].w *= qscale;
+        mx[r] = -INFINITY; ls[r] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c[r][i] = 0.f;
+      }
+      const int hd = lane & 3;                     // item & 3 == lane & 3 for every r
+      for (int dk = 0; dk < D; ++dk) {
+        const float4 k0 = *reinterpret_cast<const float4*>(F1 + dk * AT_C + hd * 8);
+        const float4 k1 = *reinterpret_cast<const float4*>(F1 + dk * AT_C + hd * 8 + 4);
+        const float4 v0 = *reinterpret_cast<const float4*>(F2 + dk * AT_C + hd * 8);
+        const float4 v1 = *reinterpret_cast<const float4*>(F2 + dk * AT_C + hd * 8 + 4);
+#pragma unroll
+        for (int r = 0; r < NI; ++r) {
+          const float s2 = (qa[r].x * k0.x + qa[r].y * k0.y) + (qa[r].z * k0.z + qa[r].w * k0.w) +
+                           (qb[r].x * k1.x + qb[r].y * k1.y) + (qb[r].z * k1.z + qb[r].w * k1.w);
+          const float mn = fmaxf(mx[r], s2);
+          const float corr = fast_exp2(mx[r] - mn), pe = fast_exp2(s2 - mn);
+          ls[r] = ls[r] * corr + pe;
+          c[r][0] = c[r][0] * corr + pe * v0.x; c[r][1] = c[r][1] * corr + pe * v0.y;
+          c[r][2] = c[r][2] * corr + pe * v0.z; c[r][3] = c[r][3] * corr + pe * v0.w;
+          c[r][4] = c[r][4] * corr + pe * v1.x; c[r][5] = c[r][5] * corr + pe * v1.y;
+          c[r][6] = c[r][6] * corr + pe * v1.z; c[r][7] = c[r][7] * corr + pe * v1.w;
+          mx[r] = mn;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < NI; ++r) {
+        const int item = lane + 32 * r;
+        if (item < 4 * D) {
+          const int dq = item >> 2;
+          const float il = 1.f / ls[r];
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) at_split2(c[r][2 * j] * il, c[r][2 * j + 1] * il, hw[j], lw[j]);
+          *reinterpret_cast<uint4*>(P0 + dq * AT_PITCH + hd * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(P0 + ROWS * AT_PITCH + dq * AT_PITCH + hd * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+      }
+    }
+    __syncwarp();
+    const float* res;
+    if (has_wa) {
+      warp_project_mma<MT>(P0, Wo, ss + 5 * 64, true, P1, nullptr, lane);    // aug_down -> P1
+      warp_project_mma<MT>(P1, Wa, nullptr, false, nullptr, F0, lane);       // t = Wa . aug_down -> F0
+      res = F0;
+    } else {
+      warp_project_mma<MT>(P0, Wo, ss + 5 * 64, true, nullptr, F0, lane);
+      res = F0;
+    }
     // ---- store [d][32] rows: lane = (row, chunk).  pad = 1 writes into a tensor with a replicated 1-voxel border
     //      ([D+2][H+2][W+2], what the trilinear-x2 "up2" GEMM consumes) ----
     const int ph = p / Wd, pw = p - ph * Wd;
@@ -568,25 +750,34 @@ extern "C" int dca_disp_attention(const void* x, const int* cls, const float* e,
   if (pad != 0 && pad != 1) return DCA_ERR_ARG;
   if (!x || !cls || !e || !S || !weights || !y || planes < 1 || planes > 2 || B <= 0 || D <= 0) return DCA_ERR_ARG;
   if (C != AT_C) return DCA_ERR_UNSUPPORTED;
-  const int Dp = (D + 7) & ~7;
+  const int MT = (D + 15) / 16;
+  if (MT > 4) return DCA_ERR_UNSUPPORTED;
+  const size_t wbytes = (size_t)AT_NMAT * 2 * AT_WPLANE * 2 + 6 * 64 * 4;
+  const size_t per_warp = (size_t)3 * (2 * 16 * MT * AT_PITCH) * 2 + (size_t)3 * (16 * MT * AT_C) * 4;
   int warps = 8;
-  size_t wbytes = (size_t)((AT_WFLOATS + 3) & ~3) * sizeof(float);
-  while (warps > 1 && wbytes + (size_t)warps * 4 * Dp * AT_C * sizeof(float) > 227 * 1024) warps >>= 1;
-  const size_t smem = wbytes + (size_t)warps * 4 * Dp * AT_C * sizeof(float);
-  if (smem > 227 * 1024) return DCA_ERR_UNSUPPORTED;
+  while (warps > 1 && wbytes + warps * per_warp > 224 * 1024) --warps;
+  const size_t smem = wbytes + warps * per_warp;
   const int HW = H * W;
   int grid = (B * HW + warps - 1) / warps;
-  if (grid > 148 * 4) grid = 148 * 4;
+  if (grid > 148) grid = 148;            // persistent: one CTA per SM pays the weight-staging prologue once
   cudaStream_t st = (cudaStream_t)stream;
-  if (planes == 2) {
-    cudaFuncSetAttribute(disp_attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    disp_attention_kernel<2><<<grid, warps * 32, smem, st>>>((const __nv_bfloat16*)x, cls, e, S, weights, has_wa,
-                                                             (__nv_bfloat16*)y, B, D, H, W, pad);
+#define DCA_AT_LAUNCH2(P_, MT_, DT_)                                                                             \
+  do {                                                                                                           \
+    auto kern = disp_attention_kernel<P_, MT_, DT_>;                                                                \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
+    kern<<<grid, warps * 32, smem, st>>>((const __nv_bfloat16*)x, cls, e, S, weights, has_wa, (__nv_bfloat16*)y, B, \
+                                         D, H, W, pad);                                                          \
+  } while (0)
+#define DCA_AT_LAUNCH(P_, MT_) DCA_AT_LAUNCH2(P_, MT_, 0)
+  if (D == 24) {
+    if (planes == 2) DCA_AT_LAUNCH2(2, 2, 24); else DCA_AT_LAUNCH2(1, 2, 24);
+  } else if (planes == 2) {
+    if (MT == 1) DCA_AT_LAUNCH(2, 1); else if (MT == 2) DCA_AT_LAUNCH(2, 2); else if (MT == 3) DCA_AT_LAUNCH(2, 3); else DCA_AT_LAUNCH(2, 4);
   } else {
-    cudaFuncSetAttribute(disp_attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    disp_attention_kernel<1><<<grid, warps * 32, smem, st>>>((const __nv_bfloat16*)x, cls, e, S, weights, has_wa,
-                                                             (__nv_bfloat16*)y, B, D, H, W, pad);
+    if (MT == 1) DCA_AT_LAUNCH(1, 1); else if (MT == 2) DCA_AT_LAUNCH(1, 2); else if (MT == 3) DCA_AT_LAUNCH(1, 3); else DCA_AT_LAUNCH(1, 4);
   }
+#undef DCA_AT_LAUNCH
+#undef DCA_AT_LAUNCH2
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }
