@@ -2,6 +2,7 @@
 from . import _lib, engine
 from .cva import Multi_Aggregation, cva
 from .gwcnet_dca_g import GwcNet, feature_extraction, hourglass
+from .pipeline import HotPathPipeline
 from .self_attention import SelfAttentionBlock
 from .semantic_level import SemanticLevelContext
 from .submodule import (PropgationNet_4x, build_concat_volume, build_cost_planes, build_gwc_volume, convbn,
@@ -9,4 +10,4 @@ from .submodule import (PropgationNet_4x, build_concat_volume, build_cost_planes
 
 __all__ = ["GwcNet", "feature_extraction", "hourglass", "cva", "Multi_Aggregation", "SemanticLevelContext",
            "SelfAttentionBlock", "PropgationNet_4x", "build_gwc_volume", "build_concat_volume", "build_cost_planes",
-           "disparity_regression", "softmax_disparity_regression", "convbn", "convbn_3d", "engine"]
+           "disparity_regression", "softmax_disparity_regression", "convbn", "convbn_3d", "engine", "HotPathPipeline"]
