@@ -26,6 +26,8 @@ SIGNATURES = {
                       _c_int] + [_c_int] * 9 + [_vp],
     "dca_pack_weights_tc": [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp],
     "dca_pack_weights_tc_bytes": [_c_int] * 4,
+    "dca_conv1_taps_tc": [_vp, _c_int, _vp, _vp] + [_c_int] * 5 + [_vp],
+    "dca_tap_gather3d": [_vp, _vp] + [_c_int] * 4 + [_vp],
     "dca_conv2d_tc": [_vp, _c_int, _vp, _vp, _vp, _vp, _c_int, _c_int] + [_c_int] * 5 + [_vp],
     "dca_pack_weights_tc2d": [_vp, _c_int, _c_int, _vp, _c_int, _vp],
     "dca_pack_weights_tc2d_bytes": [_c_int] * 3,

@@ -316,7 +316,13 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
           if (c0 != 0) load_raw16(post_raw, p.res_post, p.res_plane, p.planes_res, off);
           add_raw16(v, post_raw, p.planes_res);
         }
-        if (p.out_f32) {                      // fp32 channels-last output (mask logits of the propagation net)
+        if (p.out_f32 == 2) {                 // fp32 CHANNEL-major output [Cout][nvox] (per-tap partial sums of the 32->1 convs)
+          float* yf = reinterpret_cast<float*>(p.y);
+          const size_t nvox = (size_t)p.B * p.Do * p.Ho * p.Wo;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (p.co_base + cb + j < p.cout_valid) yf[(size_t)(p.co_base + cb + j) * nvox + vox] = v[j];
+        } else if (p.out_f32) {               // fp32 channels-last output (mask logits of the propagation net)
           float* yf = reinterpret_cast<float*>(p.y) + off;
 #pragma unroll
           for (int j = 0; j < 16; ++j)
@@ -1342,4 +1348,34 @@ extern "C" int dca_conv2d_tc(const void* x, int planes, const void* w_tc2d, cons
     if (rc != DCA_OK) return rc;
   }
   return DCA_OK;
+}
+
+// 1x1x1 conv 32 -> ntap (<= 32) "per-tap partial products" of a 3x3x3 conv to ONE channel (cva.classify.2 cva.py:53,
+// classif3.2 gwcnet_dca_g.py:168):  P[tap][v] = sum_c x[v][c] * w[tap][c], fp32, tap-major [ntap][B*D*H*W].
+// dca_tap_gather3d then sums P over the 27 shifted taps.  w_tc = dca_pack_weights_tc of a [32][32][1] weight whose
+// rows >= ntap are zero.
+extern "C" int dca_conv1_taps_tc(const void* x, int planes, const void* w_tc, float* P, int ntap, int B, int D, int H,
+                                 int W, void* stream) {
+  if (!x || !w_tc || !P || planes < 1 || planes > 2 || ntap <= 0 || ntap > 32 || B <= 0) return DCA_ERR_ARG;
+  const long long nvox = (long long)B * D * H * W;
+  if ((nvox % 8) != 0 || nvox / 8 >= (1ll << 31)) return DCA_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Pn = planes, Cin = 32, Cout = 32;
+  TcMaps maps;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  const int rows = (int)(nvox / 8);
+  if (!make_act_map(&maps.a[0], x, Cin, 8, rows, 1, Pn, (size_t)Cin, (size_t)8 * Cin, (size_t)nvox * Cin, (size_t)nvox * Cin))
+    return DCA_ERR_LAUNCH;
+  for (int i = 1; i < 9; ++i) maps.a[i] = maps.a[0];
+  if (!make_w_map(&maps.w, w_tc, Cin, Pn * Cout, Pn * Cout)) return DCA_ERR_LAUNCH;
+  p.B = 1; p.Do = 1; p.Ho = rows; p.Wo = 8;
+  p.y = (__nv_bfloat16*)P; p.planes_out = Pn; p.act = 0; p.npart = Pn; p.ngrp = 1; p.dbg = g_dbg;
+  p.ldc = Cout; p.cout_valid = ntap; p.out_f32 = 2;
+  p.nslab = 3;
+  p.Dt = 1; p.Ht = rows; p.Wt = 8; p.out_stride = 1; p.ncls = 1;
+  p.ntaps = 1; p.tap_map[0] = 0; p.tap_w[0] = 0;
+  p.cls_tap0[0] = 0; p.cls_tap0[1] = 1;
+  p.tiles_w = 1; p.tiles_h = (rows + TC_TH - 1) / TC_TH;
+  return Pn == 2 ? launch_tc<32, 32, 2>(maps, p, st) : launch_tc<32, 32, 1>(maps, p, st);
 }

@@ -707,6 +707,39 @@ __global__ void fold_bn_kernel(const float* __restrict__ gamma, const float* __r
   }
 }
 
+// out[b,d,h,w] = sum over the 27 taps (kd,kh,kw) of P[tap][b, d+kd-1, h+kh-1, w+kw-1] (zero outside): the shifted
+// sum that turns the per-tap products of dca_conv1_taps_tc into the 3x3x3 conv to one channel.  P is tap-major, so
+// every one of a thread's 27 loads is coalesced along w.
+__global__ void __launch_bounds__(256)
+tap_gather3d_kernel(const float* __restrict__ P, float* __restrict__ out, int B, int D, int H, int W) {
+  const size_t nvox = (size_t)B * D * H * W;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
+    const int w = (int)(v % W);
+    size_t r = v / W;
+    const int h = (int)(r % H); r /= H;
+    const int d = (int)(r % D);
+    float acc = 0.f;
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd) {
+      const int dz = d + kd - 1;
+      if (dz < 0 || dz >= D) continue;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int hy = h + kh - 1;
+        if (hy < 0 || hy >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int wx = w + kw - 1;
+          if (wx < 0 || wx >= W) continue;
+          const long long nb = (long long)v + ((long long)(kd - 1) * H + (kh - 1)) * W + (kw - 1);
+          acc += __ldg(P + (size_t)((kd * 3 + kh) * 3 + kw) * nvox + nb);
+        }
+      }
+    }
+    out[v] = acc;
+  }
+}
+
 static inline int grid_for(size_t total, int threads) {
   size_t g = (total + threads - 1) / threads;
   const size_t cap = 148 * 32;
@@ -813,6 +846,14 @@ extern "C" int dca_convex_upsample(const float* mask, const float* disp, float* 
   if (!mask || !disp || !out || B <= 0 || H <= 0 || W <= 0) return DCA_ERR_ARG;
   const size_t total = (size_t)B * H * W * 4;
   convex_upsample_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mask, disp, out, B, H, W);
+  DCA_RETURN_IF_LAUNCH_FAILED();
+  return DCA_OK;
+}
+
+extern "C" int dca_tap_gather3d(const float* P, float* out, int B, int D, int H, int W, void* stream) {
+  if (!P || !out || B <= 0 || D <= 0 || H <= 0 || W <= 0) return DCA_ERR_ARG;
+  const size_t total = (size_t)B * D * H * W;
+  tap_gather3d_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(P, out, B, D, H, W);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }

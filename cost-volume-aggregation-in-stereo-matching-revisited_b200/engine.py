@@ -121,6 +121,7 @@ class Options:
     tc_modes = {0, 1, 2, 3}       # conv modes the tcgen05 kernel takes (K3S1, K3S2, T3S2, K1)
     fuse_upsample_in_conv = True  # cva fuse stage: fold the trilinear upsample into the 1x1x1 conv's epilogue
     fuse_redir_in_deconv = True   # Multi_Aggregation: conv3 (transposed) + redir (1x1x1) as one GEMM
+    cout1_on_tc = True            # 32->1 convs: tensor-core per-tap GEMM + shifted sum instead of the CUDA-core kernel
     prop_on_tc = True             # the two 3x3 Conv2d of PropgationNet_4x on the halo-slab tcgen05 kernel
     use_up2 = True                # class-wise halo-slab kernel for the transposed conv and the trilinear fuse stage
 
@@ -214,6 +215,40 @@ def conv_cout1(x: Planes, w27: torch.Tensor):
     y = torch.empty((x.B, x.D, x.H, x.W), dtype=torch.float32, device=x.t.device)
     _lib.call("dca_conv3d_cout1", x.ptr, x.planes, w27.data_ptr(), y.data_ptr(), x.B, x.C, x.D, x.H, x.W, _stream())
     return y
+
+
+class PackedCout1:
+    """Conv3d(32 -> 1, k3) packed twice: host [27][32] fp32 for the CUDA-core marching kernel, and a [32][32] 1x1x1
+    bf16 operand pack (row = tap) for the tensor-core per-tap GEMM + shifted-sum path."""
+
+    def __init__(self, weight, planes):
+        self.host = pack_cout1(weight)
+        w = weight.detach().float()
+        ci = w.shape[1]
+        self.w_tc = None
+        if ci == 32:
+            wt = torch.zeros((32, ci, 1, 1, 1), dtype=torch.float32, device=w.device)
+            wt[:27, :, 0, 0, 0] = w.reshape(ci, 27).t()
+            nb = _lib.load().dca_pack_weights_tc_bytes(32, ci, 1, planes)
+            self.w_tc = torch.empty(nb, dtype=torch.uint8, device=w.device)
+            _lib.call("dca_pack_weights_tc", wt.data_ptr(), 0, 32, ci, 1, self.w_tc.data_ptr(), planes, _stream())
+            torch.cuda.current_stream().synchronize()
+        self.planes = planes
+
+
+def conv_cout1_any(x: Planes, pc):
+    """32 -> 1 channel 3x3x3 conv: tensor-core per-tap GEMM + 27-tap shifted sum when possible, else the CUDA-core
+    marching kernel."""
+    nvox = x.B * x.D * x.H * x.W
+    if (Options.use_tc and Options.cout1_on_tc and isinstance(pc, PackedCout1) and pc.w_tc is not None
+            and pc.planes == x.planes and nvox % 8 == 0):
+        P = torch.empty((27, nvox), dtype=torch.float32, device=x.t.device)
+        _lib.call("dca_conv1_taps_tc", x.ptr, x.planes, pc.w_tc.data_ptr(), P.data_ptr(), 27, x.B, x.D, x.H, x.W,
+                  _stream())
+        y = torch.empty((x.B, x.D, x.H, x.W), dtype=torch.float32, device=x.t.device)
+        _lib.call("dca_tap_gather3d", P.data_ptr(), y.data_ptr(), x.B, x.D, x.H, x.W, _stream())
+        return y
+    return conv_cout1(x, pc.host if isinstance(pc, PackedCout1) else pc)
 
 
 def pack_cout1(weight):
@@ -327,7 +362,7 @@ class PackedCva:
     def __init__(self, m, planes):
         self.down = pack_convbn(m.downsample[1])
         self.cls0 = pack_convbn(m.classify[0])
-        self.cls2 = pack_cout1(m.classify[2].weight)
+        self.cls2 = PackedCout1(m.classify[2].weight, planes)
         fuse_w = m.fuse[0][0].weight                      # [32, 64, 1,1,1]: in = cat(aug, cost)
         self.attn = PackedAttention(m.slc_net.cross_attention, fuse_w)
         pc_c = PackedConv(fuse_w.detach()[:, 32:].contiguous(), m.fuse[0][1])
@@ -387,7 +422,7 @@ def cva_forward(pk: PackedCva, cost: Planes, res_post: Planes = None, keep=None)
     pooled = avgpool(cost)
     cost_down = conv(pooled, pk.down, K3S1, ACT_RELU)
     h = conv(cost_down, pk.cls0, K3S1, ACT_RELU)
-    logits = conv_cout1(h, pk.cls2)
+    logits = conv_cout1_any(h, pk.cls2)
     cls, e, S = class_stats(logits)
     use_up2 = Options.use_tc and Options.use_up2 and pk.attn.has_wa
     t = disp_attention(cost_down, cls, e, S, pk.attn.buf, pk.attn.has_wa, pad=use_up2)
@@ -432,7 +467,7 @@ class PackedHotPath:
         self.dres1_0 = pack_convbn(net.dres1[0]); self.dres1_2 = pack_convbn(net.dres1[2])
         self.cva = [PackedCva(m, planes) for m in (net.cva1, net.cva2, net.cva3)]
         self.cls3_0 = pack_convbn(net.classif3[0])
-        self.cls3_2 = pack_cout1(net.classif3[2].weight)
+        self.cls3_2 = PackedCout1(net.classif3[2].weight, planes)
         self.prop0 = pack_convbn(net.prop.conv[0])
         self.prop2 = PackedConv(net.prop.conv[2].weight)
         self.prop0_tc = PackedConv2dTc(net.prop.conv[0][0].weight, net.prop.conv[0][1], planes)
@@ -460,7 +495,7 @@ def hot_path_forward(pk: PackedHotPath, gwc_l, gwc_r, cat_l, cat_r, g, keep=None
     logits2, out2 = cva_forward(pk.cva[1], out1, keep=k2)
     _, out3 = cva_forward(pk.cva[2], out2, keep=k3)
     h = conv(out3, pk.cls3_0, K3S1, ACT_RELU)
-    logits = conv_cout1(h, pk.cls3_2)
+    logits = conv_cout1_any(h, pk.cls3_2)
     pred_q = softmax_regress(logits)
     gp = Planes.from_ncdhw(_f32c(g), planes=P)
     if Options.use_tc and Options.prop_on_tc:

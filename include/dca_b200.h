@@ -83,6 +83,11 @@ long long dca_pack_weights_tc_bytes(int Co, int Ci, int taps, int planes);
 int dca_up2_tc(int kind, const void* x, int planes, const void* side, int side_c, const void* w_tc, const float* scale,
                const float* shift, const void* res_post, int planes_res, void* y, int act, int B, int Cin, int Dl,
                int Hl, int Wl, void* stream);
+/* Conv3d k3 s1 p1, 32 -> 1 channel on the tensor cores: per-tap products P[tap][v] = <x[v,:], w[tap,:]> as a 1x1x1
+ * GEMM (fp32, tap-major [ntap][B*D*H*W]) followed by the 27-tap shifted sum (cva.py:53, gwcnet_dca_g.py:168). */
+int dca_conv1_taps_tc(const void* x, int planes, const void* w_tc, float* P, int ntap, int B, int D, int H, int W,
+                      void* stream);
+int dca_tap_gather3d(const float* P, float* out, int B, int D, int H, int W, void* stream);
 /* 2-D 3x3 s1 p1 convs of the propagation net (gwcnet_dca_g.py:112-115) on the halo-slab tcgen05 kernel.
  * x [planes][B][1][H][W][Cin] (Cin 64/128); y cost planes (Cout % 64 == 0) or fp32 channels-last [B][H][W][Cout]. */
 int dca_conv2d_tc(const void* x, int planes, const void* w_tc2d, const float* scale, const float* shift, void* y,
