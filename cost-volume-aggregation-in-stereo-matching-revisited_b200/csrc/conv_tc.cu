@@ -42,6 +42,7 @@ struct TcParams {
   int Dt, Ht, Wt;                 // tile-space extent
   int tiles_w, tiles_h;
   int out_stride, out_off[3];
+  int out_stride_d;                // depth stride of the output mapping (0 = same as out_stride)
   int ncls;                        // output classes sharing one launch (8 parity classes of a transposed conv, else 1)
   unsigned char cls_tap0[9];       // taps [cls_tap0[c], cls_tap0[c+1]) belong to class c
   signed char cls_off[8][3];       // output offset of class c
@@ -227,7 +228,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
     const int b = r / p.Dt;
     const uint32_t acc = it & 1;
     const int ty = th * TC_TH + hh, tx = tw * TC_TW + ww;
-    int oz = td * p.out_stride + p.cls_off[cls][0], oy = ty * p.out_stride + p.cls_off[cls][1],
+    int oz = td * (p.out_stride_d ? p.out_stride_d : p.out_stride) + p.cls_off[cls][0], oy = ty * p.out_stride + p.cls_off[cls][1],
         ox = tx * p.out_stride + p.cls_off[cls][2];
     const bool valid = (ty < p.Ht) && (tx < p.Wt) && (oz < p.Do) && (oy < p.Ho) && (ox < p.Wo);
     const size_t vox = (((size_t)b * p.Do + oz) * p.Ho + oy) * p.Wo + ox;
@@ -778,7 +779,7 @@ conv_tc_up2_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const 
             tma_load_5d(slab_base + sb * Cfg::SLAB_SET + (sl * PLANES + pl) * Cfg::SLAB_PITCH, &maps.a[0], &sfull[sb], 0,
                         tw * TC_TW, th * TC_TH, td + u.slab_dz[sl], pl * p.B + b);
         if (++sb == Cfg::NBUF) { sb = 0; pb ^= 1; }
-        for (int cls = 0; cls < 8; ++cls) {
+        for (int cls = 0; cls < p.ncls; ++cls) {
           if (u.has_side) {
             mbar_wait(&dempty[sd], pd ^ 1);
             mbar_expect_tx(&dfull[sd], PLANES * Cfg::A_BYTES);
@@ -815,7 +816,7 @@ conv_tc_up2_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const 
         mbar_wait(&sfull[sb], pb);
         tc_fence_after();
         const uint32_t set_u32 = slab_u32 + sb * Cfg::SLAB_SET;
-        for (int cls = 0; cls < 8; ++cls, ++it) {
+        for (int cls = 0; cls < p.ncls; ++cls, ++it) {
           const uint32_t acc = it & 1;
           mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
           tc_fence_after();
@@ -1034,11 +1035,12 @@ extern "C" int dca_up2_tc(int kind, const void* x, int planes, const void* side,
                           const float* scale, const float* shift, const void* res_post, int planes_res, void* y, int act,
                           int B, int Cin, int Dl, int Hl, int Wl, void* stream) {
   if (!x || !w_tc || !y || B <= 0 || planes < 1 || planes > 2 || Dl <= 0 || Hl <= 0 || Wl <= 0) return DCA_ERR_ARG;
-  if (kind < 0 || kind > 1 || (kind == 1 && (!side || Cin != 32)) || (Cin != 32 && Cin != 64)) return DCA_ERR_UNSUPPORTED;
+  if (kind < 0 || kind > 2 || (kind >= 1 && (!side || Cin != 32)) || (Cin != 32 && Cin != 64)) return DCA_ERR_UNSUPPORTED;
   if (side && (side_c <= 0 || side_c > Cin || (side_c % 8) != 0)) return DCA_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int P = planes, Cout = 32;
-  const int Do = 2 * Dl, Ho = 2 * Hl, Wo = 2 * Wl;
+  // kind 2: x is already at the OUTPUT depth (Dl = output depth); only H and W double
+  const int Do = (kind == 2) ? Dl : 2 * Dl, Ho = 2 * Hl, Wo = 2 * Wl;
   TcMaps maps;
   TcParams p;
   Up2Params u;
@@ -1051,21 +1053,23 @@ extern "C" int dca_up2_tc(int kind, const void* x, int planes, const void* side,
   p.y = (__nv_bfloat16*)y; p.y_plane = p.res_plane; p.planes_out = P; p.act = act;
   p.npart = P; p.ngrp = 1; p.dbg = g_dbg;
   p.ldc = Cout; p.cout_valid = Cout;
-  p.Dt = Dl; p.Ht = Hl; p.Wt = Wl; p.out_stride = 2; p.ncls = 8; p.cls_inner = 1;
+  p.Dt = Dl; p.Ht = Hl; p.Wt = Wl; p.out_stride = 2; p.ncls = (kind == 2) ? 4 : 8; p.cls_inner = 1;
+  if (kind == 2) p.out_stride_d = 1;
   p.tiles_w = (Wl + TC_TW - 1) / TC_TW; p.tiles_h = (Hl + TC_TH - 1) / TC_TH;
-  // main input: halo box 10 x 18 whose origin is the tile origin (kind 1: the +1 of the padding cancels the -1 halo)
-  const int pad = (kind == 1) ? 2 : 0;
-  const int Dx = Dl + pad, Hx = Hl + pad, Wx = Wl + pad;
+  // main input: halo box 10 x 18 whose origin is the tile origin (kinds 1/2: the +1 of the padding cancels the -1 halo)
+  const int pad = (kind >= 1) ? 2 : 0;
+  const int Dx = Dl + (kind == 1 ? 2 : 0), Hx = Hl + pad, Wx = Wl + pad;
   if (!make_act_map(&maps.a[0], x, Cin, Wx, Hx, Dx, P * B, (size_t)Cin, (size_t)Wx * Cin, (size_t)Hx * Wx * Cin,
                     (size_t)Dx * Hx * Wx * Cin, HB_W, HB_H))
     return DCA_ERR_LAUNCH;
   for (int i = 1; i < 9; ++i) maps.a[i] = maps.a[0];
   if (side) {
     const size_t qW = side_c, qH = (size_t)Wo * side_c, qD = (size_t)Ho * Wo * side_c, qB = (size_t)Do * Ho * Wo * side_c;
-    for (int pc = 0; pc < 8; ++pc) {
-      const int pz = (pc >> 2) & 1, py = (pc >> 1) & 1, px = pc & 1;
+    for (int pc = 0; pc < p.ncls; ++pc) {
+      const int pz = (kind == 2) ? 0 : (pc >> 2) & 1, py = (pc >> 1) & 1, px = pc & 1;
       const __nv_bfloat16* base = (const __nv_bfloat16*)side + pz * qD + py * qH + px * qW;
-      if (!make_act_map(&maps.a[1 + pc], base, side_c, Wl, Hl, Dl, P * B, 2 * qW, 2 * qH, 2 * qD, qB, TC_TW, TC_TH, Cin))
+      if (!make_act_map(&maps.a[1 + pc], base, side_c, Wl, Hl, Dl, P * B, 2 * qW, 2 * qH, (kind == 2 ? 1 : 2) * qD, qB, TC_TW,
+                        TC_TH, Cin))
         return DCA_ERR_LAUNCH;
     }
     u.has_side = 1;
@@ -1111,10 +1115,37 @@ extern "C" int dca_up2_tc(int kind, const void* x, int planes, const void* side,
       }
     }
   }
-  u.cls_tap0[8] = (unsigned char)ntaps;
-  const int wt = (kind == 0) ? (side ? 28 : 27) : 5;
+  if (kind == 2) {
+    // bilinear x2 in (h, w) of a tensor already interpolated along depth: 4 classes x 4 taps, weights {9,3,1}/16 * I
+    ntaps = 0;
+    memset(u.taps, 0, sizeof(u.taps));
+    u.nslab = 1; u.slab_dz[0] = 0;
+    u.side_widx = 3; u.wres = 1; u.nw = 4;
+    for (int pc = 0; pc < 4; ++pc) {
+      const int par[2] = {(pc >> 1) & 1, pc & 1};
+      u.cls_tap0[pc] = (unsigned char)ntaps;
+      p.cls_off[pc][0] = 0; p.cls_off[pc][1] = (signed char)par[0]; p.cls_off[pc][2] = (signed char)par[1];
+      for (int m = 0; m < 4; ++m) {
+        int n75 = 0, off[2];
+        for (int a = 0; a < 2; ++a) {
+          const int second = (m >> (1 - a)) & 1;
+          off[a] = par[a] + second;
+          const bool is75 = par[a] ? (second == 0) : (second == 1);
+          n75 += is75 ? 1 : 0;
+        }
+        Up2Tap& t = u.taps[ntaps++];
+        t.slab = 0; t.dy = (unsigned char)off[0]; t.dx = (unsigned char)off[1];
+        t.widx = (unsigned char)(2 - n75);                       // 0: 9/16, 1: 3/16, 2: 1/16
+      }
+    }
+    for (int pc = 4; pc <= 8; ++pc) u.cls_tap0[pc] = (unsigned char)ntaps;
+  } else {
+    u.cls_tap0[8] = (unsigned char)ntaps;
+  }
+  const int wt = (kind == 0) ? (side ? 28 : 27) : (kind == 1 ? 5 : 4);
   if (!make_w_map(&maps.w, w_tc, Cin, wt * P * Cout, P * Cout)) return DCA_ERR_LAUNCH;
   if (kind == 1) return P == 2 ? launch_up2<32, 2, 3>(maps, p, u, st) : launch_up2<32, 1, 3>(maps, p, u, st);
+  if (kind == 2) return P == 2 ? launch_up2<32, 2, 2>(maps, p, u, st) : launch_up2<32, 1, 2>(maps, p, u, st);
   if (Cin == 64) return P == 2 ? launch_up2<64, 2, 2>(maps, p, u, st) : launch_up2<64, 1, 2>(maps, p, u, st);
   return P == 2 ? launch_up2<32, 2, 2>(maps, p, u, st) : launch_up2<32, 1, 2>(maps, p, u, st);
 }

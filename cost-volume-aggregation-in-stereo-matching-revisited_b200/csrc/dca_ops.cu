@@ -408,6 +408,38 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
     // ---- store [d][32] rows: lane = (row, chunk).  pad = 1 writes into a tensor with a replicated 1-voxel border
     //      ([D+2][H+2][W+2], what the trilinear-x2 "up2" GEMM consumes) ----
     const int ph = p / Wd, pw = p - ph * Wd;
+    if (pad == 2) {
+      // output [B][2D][H+2][W+2][32]: trilinear's depth axis is resolved here (x2, align_corners=False, clamped), the
+      // h/w borders are replicated; the up2 GEMM (kind 2) then only interpolates bilinearly in (h, w)
+      const int Dz = 2 * D, Hp2 = H + 2, Wp2 = Wd + 2;
+      const size_t oplane = (size_t)B * Dz * Hp2 * Wp2 * AT_C;
+      for (int z0 = 0; z0 < Dz; z0 += 8) {
+        const int z = z0 + (lane >> 2), q = lane & 3;
+        if (z < Dz) {
+          const int i = z >> 1;
+          const int ia = (z & 1) ? i : max(i - 1, 0), ib = (z & 1) ? min(i + 1, D - 1) : i;
+          const float wa = (z & 1) ? 0.75f : 0.25f, wb = 1.f - wa;
+          float f[8];
+          const float4 a0 = *reinterpret_cast<const float4*>(res + ia * AT_C + q * 8);
+          const float4 a1 = *reinterpret_cast<const float4*>(res + ia * AT_C + q * 8 + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(res + ib * AT_C + q * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(res + ib * AT_C + q * 8 + 4);
+          f[0] = wa * a0.x + wb * b0.x; f[1] = wa * a0.y + wb * b0.y; f[2] = wa * a0.z + wb * b0.z; f[3] = wa * a0.w + wb * b0.w;
+          f[4] = wa * a1.x + wb * b1.x; f[5] = wa * a1.y + wb * b1.y; f[6] = wa * a1.z + wb * b1.z; f[7] = wa * a1.w + wb * b1.w;
+          for (int iy = 0; iy < 3; ++iy) {
+            const int yy = iy == 0 ? ph + 1 : (iy == 1 ? (ph == 0 ? 0 : -1) : (ph == H - 1 ? H + 1 : -1));
+            if (yy < 0) continue;
+            for (int ix = 0; ix < 3; ++ix) {
+              const int xx = ix == 0 ? pw + 1 : (ix == 1 ? (pw == 0 ? 0 : -1) : (pw == Wd - 1 ? Wd + 1 : -1));
+              if (xx < 0) continue;
+              store8<PLANES>(y, oplane, ((((size_t)b * Dz + z) * Hp2 + yy) * Wp2 + xx) * AT_C + q * 8, f);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      continue;
+    }
     const int Dp2 = D + 2 * pad, Hp2 = H + 2 * pad, Wp2 = Wd + 2 * pad;
     const size_t oplane = (size_t)B * Dp2 * Hp2 * Wp2 * AT_C;
     for (int d0 = 0; d0 < D; d0 += 8) {
@@ -780,7 +812,7 @@ extern "C" int dca_class_stats(const float* logits, int* cls, float* e, float* S
 extern "C" int dca_disp_attention(const void* x, const int* cls, const float* e, const float* S, const float* weights,
                                   int has_wa, void* y, int pad, int planes, int B, int C, int D, int H, int W,
                                   void* stream) {
-  if (pad != 0 && pad != 1) return DCA_ERR_ARG;
+  if (pad < 0 || pad > 2) return DCA_ERR_ARG;
   if (!x || !cls || !e || !S || !weights || !y || planes < 1 || planes > 2 || B <= 0 || D <= 0) return DCA_ERR_ARG;
   if (C != AT_C) return DCA_ERR_UNSUPPORTED;
   const int MT = (D + 15) / 16;

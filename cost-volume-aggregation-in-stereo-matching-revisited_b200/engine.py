@@ -123,6 +123,7 @@ class Options:
     fuse_redir_in_deconv = True   # Multi_Aggregation: conv3 (transposed) + redir (1x1x1) as one GEMM
     cout1_on_tc = True            # 32->1 convs: tensor-core per-tap GEMM + shifted sum instead of the CUDA-core kernel
     prop_on_tc = True             # the two 3x3 Conv2d of PropgationNet_4x on the halo-slab tcgen05 kernel
+    up2_bilinear = True           # fuse stage: depth interpolation in the attention store, bilinear 4-class GEMM
     use_up2 = True                # class-wise halo-slab kernel for the transposed conv and the trilinear fuse stage
 
 
@@ -277,18 +278,24 @@ def class_stats(logits):
     return cls, e, S
 
 
-def disp_attention(x: Planes, cls, e, S, weights, has_wa, pad=False):
-    """pad=True: the result gets a replicated 1-voxel border ([D+2][H+2][W+2]) for the up2 (trilinear) GEMM."""
-    k = 2 if pad else 0
-    y = Planes(x.B, x.D + k, x.H + k, x.W + k, x.C, x.planes, x.t.device)
+def disp_attention(x: Planes, cls, e, S, weights, has_wa, pad=0):
+    """pad=1: the result gets a replicated 1-voxel border ([D+2][H+2][W+2]) for the up2 (trilinear) GEMM;
+    pad=2: the result is already interpolated x2 along depth and border-replicated in h/w ([2D][H+2][W+2])."""
+    pad = int(pad)
+    if pad == 2:
+        y = Planes(x.B, 2 * x.D, x.H + 2, x.W + 2, x.C, x.planes, x.t.device)
+    else:
+        k = 2 if pad else 0
+        y = Planes(x.B, x.D + k, x.H + k, x.W + k, x.C, x.planes, x.t.device)
     _lib.call("dca_disp_attention", x.ptr, cls.data_ptr(), e.data_ptr(), S.data_ptr(), weights.data_ptr(),
               int(has_wa), y.ptr, int(pad), x.planes, x.B, x.C, x.D, x.H, x.W, _stream())
     return y
 
 
 def up2(kind, x: Planes, side: Planes, w_tc, scale, shift, act, cin, dl, hl, wl, res_post: Planes = None):
-    """dca_up2_tc: kind 0 transposed conv (+side 1x1x1), kind 1 trilinear x2 of a padded tensor + side 1x1x1."""
-    y = Planes(x.B, 2 * dl, 2 * hl, 2 * wl, 32, x.planes, x.t.device)
+    """dca_up2_tc: kind 0 transposed conv (+side 1x1x1), kind 1 trilinear x2 of a padded tensor + side 1x1x1,
+    kind 2 bilinear x2 in (h, w) of a depth-interpolated padded tensor + side 1x1x1 (dl = OUTPUT depth)."""
+    y = Planes(x.B, dl if kind == 2 else 2 * dl, 2 * hl, 2 * wl, 32, x.planes, x.t.device)
     _lib.call("dca_up2_tc", kind, x.ptr, x.planes, side.ptr if side is not None else 0,
               side.C if side is not None else 0, w_tc.data_ptr(), _ptr(scale), _ptr(shift),
               res_post.ptr if res_post is not None else 0, res_post.planes if res_post is not None else 1, y.ptr, act,
@@ -389,6 +396,15 @@ class PackedCva:
         self.fuse_up2_w = torch.empty(nb, dtype=torch.uint8, device=fuse_w.device)
         _lib.call("dca_pack_weights_tc", w5.data_ptr(), 0, 32, 32, 5, self.fuse_up2_w.data_ptr(), planes, _stream())
         torch.cuda.current_stream().synchronize()
+        # same with the depth axis resolved upstream: bilinear taps {9,3,1}/16 * I and Wc
+        w4 = torch.zeros((32, 32, 4), dtype=torch.float32, device=fuse_w.device)
+        for i, wv in enumerate((9.0, 3.0, 1.0)):
+            w4[:, :, i] = eye * (wv / 16.0)
+        w4[:, :, 3] = fuse_w.detach().float()[:, 32:, 0, 0, 0]
+        nb4 = _lib.load().dca_pack_weights_tc_bytes(32, 32, 4, planes)
+        self.fuse_up2b_w = torch.empty(nb4, dtype=torch.uint8, device=fuse_w.device)
+        _lib.call("dca_pack_weights_tc", w4.data_ptr(), 0, 32, 32, 4, self.fuse_up2b_w.data_ptr(), planes, _stream())
+        torch.cuda.current_stream().synchronize()
 
 
 class _FusedDeconv:
@@ -425,8 +441,13 @@ def cva_forward(pk: PackedCva, cost: Planes, res_post: Planes = None, keep=None)
     logits = conv_cout1_any(h, pk.cls2)
     cls, e, S = class_stats(logits)
     use_up2 = Options.use_tc and Options.use_up2 and pk.attn.has_wa
-    t = disp_attention(cost_down, cls, e, S, pk.attn.buf, pk.attn.has_wa, pad=use_up2)
-    if use_up2:
+    bil = use_up2 and Options.up2_bilinear
+    t = disp_attention(cost_down, cls, e, S, pk.attn.buf, pk.attn.has_wa, pad=(2 if bil else (1 if use_up2 else 0)))
+    if bil:
+        # depth axis of the trilinear already resolved by the attention kernel's store; 4-class bilinear GEMM here
+        fused = up2(2, t, cost, pk.fuse_up2b_w, pk.fuse_scale, pk.fuse_shift, ACT_NONE, 32, cost.D, cost_down.H,
+                    cost_down.W)
+    elif use_up2:
         # trilinear x2 + cat + 1x1x1 fuse + BN as ONE class-wise GEMM over halo slabs of the padded low-res tensor
         fused = up2(1, t, cost, pk.fuse_up2_w, pk.fuse_scale, pk.fuse_shift, ACT_NONE, 32, cost_down.D, cost_down.H,
                     cost_down.W)

@@ -79,6 +79,9 @@ long long dca_pack_weights_tc_bytes(int Co, int Ci, int taps, int planes);
  *           x [planes][B][Dl][Hl][Wl][Cin]; w_tc = 27 taps (+ tap 27: side weights zero-padded to Cin)
  *   kind 1: y = act(scale * (trilinear_x2(x) + side 1x1x1) + shift) + res_post                  (cva.py:64,55,69)
  *           x = border-replicated [planes][B][Dl+2][Hl+2][Wl+2][32]; w_tc = 5 taps: {27,9,3,1}/64*I, side weights
+ *   kind 2: like kind 1 but x = [planes][B][Dl][Hl+2][Wl+2][32] is already at the output depth Dl (depth axis
+ *           interpolated by the producer): bilinear x2 in (h, w) only; w_tc = 4 taps {9,3,1}/16*I, side weights;
+ *           side / y are [planes][B][Dl][2Hl][2Wl][..]
  * side [planes][B][2Dl][2Hl][2Wl][side_c]; Cout = 32. */
 int dca_up2_tc(int kind, const void* x, int planes, const void* side, int side_c, const void* w_tc, const float* scale,
                const float* shift, const void* res_post, int planes_res, void* y, int act, int B, int Cin, int Dl,
@@ -104,7 +107,9 @@ int dca_avgpool3d(const void* x, void* y, int planes, int B, int C, int Di, int 
 /* logits fp32 [B,D,H,W] -> class map int32 [B,H,W], e = exp(P[k_p]) [B,H,W], S [B,D] (zeroed here). */
 int dca_class_stats(const float* logits, int* cls, float* e, float* S, int B, int D, int H, int W, void* stream);
 /* weights: 7 x [32][32] transposed (q0,q1,k0,k1,v,o,Wa) then 6 x (scale[32],shift[32]). */
-/* pad = 1: y is [planes][B][D+2][H+2][W+2][C] with a replicated 1-voxel border (input of dca_up2_tc kind 1). */
+/* pad = 1: y is [planes][B][D+2][H+2][W+2][C] with a replicated 1-voxel border (input of dca_up2_tc kind 1).
+ * pad = 2: y is [planes][B][2D][H+2][W+2][C]: already interpolated x2 along depth (align_corners=False), h/w borders
+ *          replicated (input of dca_up2_tc kind 2). */
 int dca_disp_attention(const void* x, const int* cls, const float* e, const float* S, const float* weights,
                        int has_wa, void* y, int pad, int planes, int B, int C, int D, int H, int W, void* stream);
 /* y = scale * (trilinear_x2(t) + WcT^T cost) + shift ; t at (Dl,Hl,Wl), cost / y at twice that. */
