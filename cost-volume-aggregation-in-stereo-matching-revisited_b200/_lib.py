@@ -26,6 +26,9 @@ SIGNATURES = {
                       _c_int] + [_c_int] * 9 + [_vp],
     "dca_pack_weights_tc": [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp],
     "dca_pack_weights_tc_bytes": [_c_int] * 4,
+    "dca_conv3d_tc_march": [_vp, _c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _c_int] + [_c_int] * 5 + [_vp],
+    "dca_pack_weights_tc_march": [_vp, _c_int, _vp, _c_int, _vp],
+    "dca_pack_weights_tc_march_bytes": [_c_int] * 2,
     "dca_conv1_taps_tc": [_vp, _c_int, _vp, _vp] + [_c_int] * 5 + [_vp],
     "dca_tap_gather3d": [_vp, _vp] + [_c_int] * 4 + [_vp],
     "dca_conv2d_tc": [_vp, _c_int, _vp, _vp, _vp, _vp, _c_int, _c_int] + [_c_int] * 5 + [_vp],
@@ -45,7 +48,8 @@ SIGNATURES = {
     "dca_pack_weights": [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp],
     "dca_fold_bn": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _c_int, _c_int, _vp],
 }
-_RESTYPES = {"dca_pack_weights_tc_bytes": ctypes.c_longlong, "dca_pack_weights_tc2d_bytes": ctypes.c_longlong}
+_RESTYPES = {"dca_pack_weights_tc_bytes": ctypes.c_longlong, "dca_pack_weights_tc2d_bytes": ctypes.c_longlong,
+             "dca_pack_weights_tc_march_bytes": ctypes.c_longlong}
 
 ERRORS = {-1: "DCA_ERR_ARG (bad pointer/shape)", -2: "DCA_ERR_LAUNCH (CUDA launch failed)",
           -3: "DCA_ERR_UNSUPPORTED (shape outside what the kernels support)"}

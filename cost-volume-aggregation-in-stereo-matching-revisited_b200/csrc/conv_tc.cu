@@ -56,6 +56,7 @@ struct TcParams {
   const __nv_bfloat16* up; int planes_up;   // optional half-resolution tensor added (trilinear x2) before BN
   int nslab; int slab_c0[3]; int slab_dz[3];   // halo kernel: slabs per tile (3 depth slabs, or channel halves in 2-D)
   int ldc, co_base, cout_valid, out_f32;        // output row pitch / first channel / valid channels / fp32 output
+  int march_n;                     // > 0: depth-marching kernel, a work item = march_n consecutive output planes
   int cls_inner;                   // epilogue/work order: CTA owns whole tiles, classes inside (up2 kernel)
   int linear;                      // 1x1x1 convs: tiles are 128 CONSECUTIVE voxels (8 KB bursts); rB/rD/rH/rW = real dims
   int rB, rD, rH, rW;
@@ -172,6 +173,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(z) : "memory");
+}
 // (a, b) -> packed bf16x2 hi and bf16x2 lo (= bf16 of the remainders)
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -217,10 +224,15 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
   const int step = p.cls_inner ? 1 : (int)gridDim.x;
   const int first = p.cls_inner ? 0 : (int)blockIdx.x;
   const int my_tiles = p.cls_inner ? ((total_tiles > (int)blockIdx.x) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0) : 0;
-  const int n_items = p.cls_inner ? my_tiles * p.ncls : total_tiles;
-  for (int item = first; item < n_items; item += step, ++it) {
-    int r, cls;
-    if (p.cls_inner) { cls = item % p.ncls; r = (int)blockIdx.x + (item / p.ncls) * (int)gridDim.x; }
+  // march mode: a CTA owns whole work items (tile column x chunk of march_n output planes) and walks the planes inside;
+  // the accumulator of plane j sits in TMEM columns 32*(n-1-j) and is announced by its own mbarrier tfull[j]
+  const int mn = p.march_n;
+  const int my_march = mn ? ((total_tiles > (int)blockIdx.x) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0) : 0;
+  const int n_items = mn ? my_march * mn : (p.cls_inner ? my_tiles * p.ncls : total_tiles);
+  for (int item = (mn ? 0 : first); item < n_items; item += (mn ? 1 : step), ++it) {
+    int r, cls, mj = 0, mwi = 0;
+    if (mn) { cls = 0; mwi = item / mn; mj = item - mwi * mn; r = (int)blockIdx.x + mwi * (int)gridDim.x; }
+    else if (p.cls_inner) { cls = item % p.ncls; r = (int)blockIdx.x + (item / p.ncls) * (int)gridDim.x; }
     else { cls = item % p.ncls; r = item / p.ncls; }
     const int tw = r % p.tiles_w; r /= p.tiles_w;
     const int th = r % p.tiles_h; r /= p.tiles_h;
@@ -228,7 +240,17 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
     const int b = r / p.Dt;
     const uint32_t acc = it & 1;
     const int ty = th * TC_TH + hh, tx = tw * TC_TW + ww;
-    int oz = td * (p.out_stride_d ? p.out_stride_d : p.out_stride) + p.cls_off[cls][0], oy = ty * p.out_stride + p.cls_off[cls][1],
+    if (mn && mj == 0) {
+      // new work item: clear this thread's slice of the accumulator window, then tell the MMA warp (tempty[0])
+      const uint32_t zaddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * 16;
+      for (int jj = 0; jj < mn; ++jj) tmem_st16_zero(zaddr + 32 * jj);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[0]);
+    }
+    int oz = mn ? td * mn + mj : td * (p.out_stride_d ? p.out_stride_d : p.out_stride) + p.cls_off[cls][0],
+        oy = ty * p.out_stride + p.cls_off[cls][1],
         ox = tx * p.out_stride + p.cls_off[cls][2];
     const bool valid = (ty < p.Ht) && (tx < p.Wt) && (oz < p.Do) && (oy < p.Ho) && (ox < p.Wo);
     const size_t vox = (((size_t)b * p.Do + oz) * p.Ho + oy) * p.Wo + ox;
@@ -272,15 +294,17 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
         for (int j = 0; j < 16; ++j) upv[j] = fmaf(wgt, f[j], upv[j]);
       }
     }
-    mbar_wait(&tfull[acc], (it >> 1) & 1);
+    if (mn) mbar_wait(&tfull[mj], (uint32_t)(mwi & 1));
+    else mbar_wait(&tfull[acc], (it >> 1) & 1);
     tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)(PLANES * COUT) + half * 16;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * 16 +
+                           (mn ? (uint32_t)(32 * (mn - 1 - mj)) : acc * (uint32_t)(PLANES * COUT));
 #pragma unroll 1
     for (int c0 = 0; c0 < COUT; c0 += 32) {
       uint32_t rh[16];
       float v[16];
       tmem_ld16(taddr + c0, rh);
-      if (PLANES == 2) {
+      if (PLANES == 2 && !mn) {          // (march mode sums hi.Whi + hi.Wlo + lo.Whi into ONE column block)
         uint32_t rl[16];
         tmem_ld16(taddr + COUT + c0, rl);
         tmem_ld_wait();
@@ -291,7 +315,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rh[j]);
       }
-      if (c0 + 32 >= COUT) {           // all TMEM reads of this tile are done: hand the buffer back
+      if (c0 + 32 >= COUT && !mn) {    // all TMEM reads of this tile are done: hand the buffer back
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -485,6 +509,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 // chunks of 3 taps (one (kd,kh) row) through their own mbarrier ring.
 // =====================================================================================================
 constexpr int HB_W = TC_TW + 2, HB_H = TC_TH + 2;     // halo box 10 x 18
+static int g_num_sms = 0;
 
 template <int CIN, int COUT, int PLANES>
 struct HaloCfg {
@@ -881,6 +906,240 @@ conv_tc_up2_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const 
   }
 }
 
+
+// =====================================================================================================
+// Depth-marching 3x3x3 stride-1 conv, Cout = 32: the three depth taps are folded into the GEMM's N.
+// A work item = one (h, w) tile column x a chunk of n <= 16 output planes.  The CTA walks the n+2 input planes of
+// the chunk; the halo slab of input plane d' is read ONCE per (kh, kw) and multiplied against the weights of all
+// three kd at once (B rows [W_kd0; W_kd1; W_kd2], N = 96), landing in the accumulators of output planes
+// d'+1, d', d'-1, which sit side by side in TMEM: output plane j of the chunk owns columns 32*(n-1-j), so every
+// slab's three targets are one contiguous 96-column window that slides down by 32 columns per plane.
+// Per tap the activation tile is read from shared memory once instead of three times (the per-tile kernels are
+// SMEM-operand bound at N = 32/64).  Parity precision issues hi.Whi, hi.Wlo and lo.Whi into the SAME columns.
+// The window is zeroed by the epilogue warps before an item starts (every MMA accumulates), each finished plane
+// is announced through its own mbarrier, and the epilogue drains it while the MMA warp keeps marching.
+// =====================================================================================================
+template <int CIN, int PLANES>
+struct MarchCfg {
+  static constexpr int COUT = 32;
+  static constexpr int ROWB = CIN * 2;
+  static constexpr int SLAB_BYTES = HB_W * HB_H * ROWB;
+  static constexpr int SLAB_PITCH = (SLAB_BYTES + 1023) / 1024 * 1024;
+  static constexpr int A_SLOT = PLANES * SLAB_PITCH;
+  static constexpr int WP_BYTES = 3 * COUT * ROWB;              // one plane of one (kh,kw): rows [kd][co]
+  static constexpr int TAP_BYTES = PLANES * WP_BYTES;
+  static constexpr int BUDGET = 200 * 1024;
+  static constexpr bool WRES = (9 * TAP_BYTES + 2 * A_SLOT) <= BUDGET;
+  static constexpr int A_SLOTS_RES = ((BUDGET - 9 * TAP_BYTES) / A_SLOT) > 4 ? 4 : ((BUDGET - 9 * TAP_BYTES) / A_SLOT);
+  static constexpr int A_SLOTS = WRES ? A_SLOTS_RES : 2;
+  static constexpr int W_SLOTS_STR = ((BUDGET - 2 * A_SLOT) / TAP_BYTES) > 6 ? 6 : ((BUDGET - 2 * A_SLOT) / TAP_BYTES);
+  static constexpr int W_SLOTS = WRES ? 1 : W_SLOTS_STR;
+  static constexpr int W_BYTES_TOTAL = WRES ? 9 * TAP_BYTES : W_SLOTS * TAP_BYTES;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int MAXN = 16;
+  static constexpr int SMEM_BYTES = A_SLOTS * A_SLOT + W_BYTES_TOTAL + 1024 + 512 + 2 * COUT * 4;
+};
+
+template <int CIN, int PLANES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_march_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+  using Cfg = MarchCfg<CIN, PLANES>;
+  constexpr int COUT = Cfg::COUT;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_base = smem;
+  uint8_t* w_base = smem + Cfg::A_SLOTS * Cfg::A_SLOT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_base + Cfg::W_BYTES_TOTAL);
+  uint64_t* afull = bars;                        // [A_SLOTS]
+  uint64_t* aempty = afull + Cfg::A_SLOTS;       // [A_SLOTS]
+  uint64_t* wfull = aempty + Cfg::A_SLOTS;       // [W_SLOTS]
+  uint64_t* wempty = wfull + Cfg::W_SLOTS;       // [W_SLOTS]
+  uint64_t* oready = wempty + Cfg::W_SLOTS;      // [MAXN] output plane j of the current item is complete
+  uint64_t* tzero = oready + Cfg::MAXN;          // [1]    accumulator window cleared for the next item
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tzero + 1);
+  float* s_scale = reinterpret_cast<float*>(w_base + Cfg::W_BYTES_TOTAL + 512);
+  float* s_shift = s_scale + COUT;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = p.march_n;
+  const int total_items = p.B * p.Dt * p.tiles_h * p.tiles_w;      // p.Dt = number of depth chunks
+
+  if (threadIdx.x < COUT) {
+    s_scale[threadIdx.x] = p.scale ? p.scale[threadIdx.x] : 1.f;
+    s_shift[threadIdx.x] = p.shift ? p.shift[threadIdx.x] : 0.f;
+  }
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
+    for (int i = 0; i < Cfg::W_SLOTS; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
+    for (int i = 0; i < Cfg::MAXN; ++i) mbar_init(&oready[i], 1);
+    mbar_init(tzero, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&maps.a[0]);
+    prefetch_tmap(&maps.w);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      if (Cfg::WRES) {
+        mbar_expect_tx(&wfull[0], 9 * Cfg::TAP_BYTES);
+        for (int t = 0; t < 9; ++t)
+          tma_load_2d(w_base + t * Cfg::TAP_BYTES, &maps.w, &wfull[0], 0, t * PLANES * 3 * COUT);
+      }
+      uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        int r = item;
+        const int tw = r % p.tiles_w; r /= p.tiles_w;
+        const int th = r % p.tiles_h; r /= p.tiles_h;
+        const int ch = r % p.Dt;
+        const int b = r / p.Dt;
+        for (int sidx = 0; sidx < n + 2; ++sidx) {
+          const int dprime = ch * n - 1 + sidx;
+          mbar_wait(&aempty[sa], pa ^ 1);
+          mbar_expect_tx(&afull[sa], PLANES * Cfg::SLAB_BYTES);
+#pragma unroll
+          for (int pl = 0; pl < PLANES; ++pl)
+            tma_load_5d(a_base + sa * Cfg::A_SLOT + pl * Cfg::SLAB_PITCH, &maps.a[0], &afull[sa], 0, tw * TC_TW - 1,
+                        th * TC_TH - 1, dprime, pl * p.B + b);
+          if (++sa == Cfg::A_SLOTS) { sa = 0; pa ^= 1; }
+          if (!Cfg::WRES) {
+            for (int t = 0; t < 9; ++t) {
+              mbar_wait(&wempty[sw], pw ^ 1);
+              mbar_expect_tx(&wfull[sw], Cfg::TAP_BYTES);
+              tma_load_2d(w_base + sw * Cfg::TAP_BYTES, &maps.w, &wfull[sw], 0, t * PLANES * 3 * COUT);
+              if (++sw == Cfg::W_SLOTS) { sw = 0; pw ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    {
+      const bool leader = elect_one();
+      constexpr uint64_t DA = desc_const<Cfg::ROWB>(HB_W * Cfg::ROWB);
+      constexpr uint64_t DB = desc_const<Cfg::ROWB>(8 * Cfg::ROWB);
+      if (Cfg::WRES) { mbar_wait(&wfull[0], 0); tc_fence_after(); }
+      const uint32_t a_u32 = smem_u32(a_base), w_u32 = smem_u32(w_base);
+      uint32_t sa = 0, pa = 0, sw = 0, pw = 0, wi = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++wi) {
+        const int ch = (item / (p.tiles_w * p.tiles_h)) % p.Dt;
+        mbar_wait(tzero, wi & 1);                  // accumulator window cleared by the epilogue warps
+        tc_fence_after();
+#pragma unroll 1
+        for (int sidx = 0; sidx < n + 2; ++sidx) {
+          const int dprime = ch * n - 1 + sidx;
+          // output index inside the chunk fed through kd: j = sidx - kd, must lie in [0, n)
+          const int kd_lo = max(0, sidx - n + 1), kd_hi = min(2, sidx);
+          const int nkd = kd_hi - kd_lo + 1;
+          const uint32_t idesc = make_idesc(TC_M, 32 * nkd);
+          const uint32_t d_addr = tmem_base + (uint32_t)(32 * (n - 1 - (sidx - kd_lo)));
+          const uint32_t w_off = (uint32_t)(kd_lo * COUT) * Cfg::ROWB;          // skip the kd blocks that fall outside
+          const bool live = dprime >= 0 && dprime < p.Do;                       // (OOB planes are all zeros: skip the MMAs)
+          mbar_wait(&afull[sa], pa);
+          tc_fence_after();
+          const uint64_t da_slab = DA + ((a_u32 + sa * Cfg::A_SLOT) >> 4);
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              uint32_t wtap;
+              if (Cfg::WRES) {
+                wtap = w_u32 + (uint32_t)(kh * 3 + kw) * Cfg::TAP_BYTES;
+              } else {
+                mbar_wait(&wfull[sw], pw);
+                tc_fence_after();
+                wtap = w_u32 + sw * Cfg::TAP_BYTES;
+              }
+              const uint64_t db_hi = DB + ((wtap + w_off) >> 4);
+              const uint64_t db_lo = DB + ((wtap + Cfg::WP_BYTES + w_off) >> 4);
+#pragma unroll
+              for (int k = 0; k < CIN / 16; ++k) {
+                const uint64_t da = da_slab + (uint64_t)(((kh * HB_W + kw) * Cfg::ROWB + k * 32) >> 4);
+                if (leader && live) {
+                  umma_bf16(d_addr, da, db_hi + (uint64_t)(k * 2), idesc, 1u);
+                  if (PLANES == 2) {
+                    umma_bf16(d_addr, da, db_lo + (uint64_t)(k * 2), idesc, 1u);
+                    umma_bf16(d_addr, da + (uint64_t)(Cfg::SLAB_PITCH >> 4), db_hi + (uint64_t)(k * 2), idesc, 1u);
+                  }
+                }
+              }
+              if (!Cfg::WRES) {
+                __syncwarp();
+                if (leader) umma_commit(&wempty[sw]);
+                if (++sw == Cfg::W_SLOTS) { sw = 0; pw ^= 1; }
+              }
+            }
+          }
+          __syncwarp();
+          if (leader) {
+            umma_commit(&aempty[sa]);
+            if (sidx >= 2) umma_commit(&oready[sidx - 2]);      // output plane sidx-2 has received all three kd
+          }
+          __syncwarp();
+          if (++sa == Cfg::A_SLOTS) { sa = 0; pa ^= 1; }
+        }
+      }
+    }
+  } else {
+    tc_epilogue<COUT, PLANES>(p, total_items, tmem_base, oready, tzero, s_scale, s_shift, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// march weight pack: [tap (kh,kw) 9][plane][kd 3][co 32][ci] bf16
+__global__ void pack_weight_tc_march_kernel(const float* __restrict__ w, int Ci, __nv_bfloat16* __restrict__ out, int planes) {
+  const int total = 27 * 32 * Ci;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ci = i % Ci, co = (i / Ci) % 32, t27 = i / (Ci * 32);
+    const int kd = t27 / 9, khw = t27 % 9;
+    const float v = w[((size_t)co * Ci + ci) * 27 + t27];
+    uint32_t lo;
+    const uint32_t hi = split_bf16(v, lo);
+    const size_t row_hi = ((size_t)(khw * planes + 0) * 3 + kd) * 32 + co;
+    out[row_hi * Ci + ci] = __ushort_as_bfloat16((unsigned short)hi);
+    if (planes == 2) {
+      const size_t row_lo = ((size_t)(khw * planes + 1) * 3 + kd) * 32 + co;
+      out[row_lo * Ci + ci] = __ushort_as_bfloat16((unsigned short)lo);
+    }
+  }
+}
+
+template <int CIN, int PLANES>
+static int launch_tc_march(const TcMaps& maps, const TcParams& p, cudaStream_t st) {
+  using Cfg = MarchCfg<CIN, PLANES>;
+  static_assert(Cfg::A_SLOTS >= 2 && Cfg::W_SLOTS >= 1, "smem plan");
+  static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "smem plan");
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  cudaFuncSetAttribute(conv_tc_march_kernel<CIN, PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  const int total = p.B * p.Dt * p.tiles_h * p.tiles_w;
+  const int grid = total < g_num_sms ? total : g_num_sms;
+  conv_tc_march_kernel<CIN, PLANES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);
+  DCA_RETURN_IF_LAUNCH_FAILED();
+  return DCA_OK;
+}
+
 // ------------------------------------------------------------------ weight pack: [tap][plane][Cout][Cin] bf16
 __global__ void pack_weight_tc_kernel(const float* __restrict__ w, int transposed, int Co, int Ci, int taps,
                                       __nv_bfloat16* __restrict__ out, int planes) {
@@ -941,7 +1200,6 @@ static bool make_w_map(CUtensorMap* m, const void* base, int Cin, int rows, int 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static int g_num_sms = 0;
 static int g_use_halo = 1;
 static int g_ngrp = 1, g_lo_sep = 0;
 static int g_dbg = 0;
@@ -1409,4 +1667,50 @@ extern "C" int dca_conv1_taps_tc(const void* x, int planes, const void* w_tc, fl
   p.cls_tap0[0] = 0; p.cls_tap0[1] = 1;
   p.tiles_w = 1; p.tiles_h = (rows + TC_TH - 1) / TC_TH;
   return Pn == 2 ? launch_tc<32, 32, 2>(maps, p, st) : launch_tc<32, 32, 1>(maps, p, st);
+}
+
+extern "C" long long dca_pack_weights_tc_march_bytes(int Ci, int planes) {
+  if ((Ci != 32 && Ci != 64) || planes < 1 || planes > 2) return 0;
+  return (long long)27 * planes * 32 * Ci * 2;
+}
+
+extern "C" int dca_pack_weights_tc_march(const float* w, int Ci, void* out, int planes, void* stream) {
+  if (!w || !out || dca_pack_weights_tc_march_bytes(Ci, planes) == 0) return DCA_ERR_ARG;
+  const int total = 27 * 32 * Ci;
+  pack_weight_tc_march_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, Ci, (__nv_bfloat16*)out, planes);
+  DCA_RETURN_IF_LAUNCH_FAILED();
+  return DCA_OK;
+}
+
+// Conv3d k3 s1 p1, Cout = 32, depth-marching kernel (kd folded into N).  Same epilogue contract as dca_conv3d_tc:
+//   y = act(scale * conv(x, w) + shift + res_pre) + res_post ;  w_march from dca_pack_weights_tc_march.
+extern "C" int dca_conv3d_tc_march(const void* x, int planes, const void* w_march, const float* scale, const float* shift,
+                                   const void* res_pre, const void* res_post, int planes_res, void* y, int act, int B,
+                                   int Cin, int D, int H, int W, void* stream) {
+  if (!x || !w_march || !y || B <= 0 || planes < 1 || planes > 2 || D <= 0 || H <= 0 || W <= 0) return DCA_ERR_ARG;
+  if (Cin != 32 && Cin != 64) return DCA_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = planes, Cout = 32;
+  TcMaps maps;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.Do = D; p.Ho = H; p.Wo = W;
+  p.scale = scale; p.shift = shift;
+  p.res_pre = (const __nv_bfloat16*)res_pre; p.res_post = (const __nv_bfloat16*)res_post;
+  p.res_plane = (size_t)B * D * H * W * Cout; p.planes_res = planes_res;
+  p.y = (__nv_bfloat16*)y; p.y_plane = p.res_plane; p.planes_out = P; p.act = act;
+  p.npart = 1; p.ngrp = 1; p.dbg = g_dbg;
+  p.ldc = Cout; p.cout_valid = Cout;
+  const int n = D < 16 ? D : 16;
+  p.march_n = n;
+  p.Dt = (D + n - 1) / n;                      // depth chunks
+  p.Ht = H; p.Wt = W; p.out_stride = 1; p.ncls = 1;
+  p.tiles_w = (W + TC_TW - 1) / TC_TW; p.tiles_h = (H + TC_TH - 1) / TC_TH;
+  if (!make_act_map(&maps.a[0], x, Cin, W, H, D, P * B, (size_t)Cin, (size_t)W * Cin, (size_t)H * W * Cin,
+                    (size_t)D * H * W * Cin, HB_W, HB_H))
+    return DCA_ERR_LAUNCH;
+  for (int i = 1; i < 9; ++i) maps.a[i] = maps.a[0];
+  if (!make_w_map(&maps.w, w_march, Cin, 9 * P * 3 * Cout, P * 3 * Cout)) return DCA_ERR_LAUNCH;
+  if (Cin == 32) return P == 2 ? launch_tc_march<32, 2>(maps, p, st) : launch_tc_march<32, 1>(maps, p, st);
+  return P == 2 ? launch_tc_march<64, 2>(maps, p, st) : launch_tc_march<64, 1>(maps, p, st);
 }

@@ -94,6 +94,7 @@ class PackedConv:
             _lib.call("dca_fold_bn", g.data_ptr(), b.data_ptr(), m.data_ptr(), v.data_ptr(), float(bn.eps),
                       self.scale.data_ptr(), self.shift.data_ptr(), co, self.cout_pad, _stream())
         self.w_tc = None     # bf16 operand pack for the tcgen05 kernels (filled by pack_tc)
+        self.w_march = None  # [kh*3+kw][plane][kd][32][Cin] pack of the depth-marching kernel (k3, Cout == 32)
         self.tc_planes = 0
         self._keep = (w,)
 
@@ -105,6 +106,11 @@ class PackedConv:
         _lib.call("dca_pack_weights_tc", self._keep[0].data_ptr(), int(transposed), self.cout, self.cin, self.taps,
                   self.w_tc.data_ptr(), planes, _stream())
         self.tc_planes = planes
+        if not transposed and self.taps == 27 and self.cout == 32 and self.cin in (32, 64):
+            nb = _lib.load().dca_pack_weights_tc_march_bytes(self.cin, planes)
+            self.w_march = torch.empty(nb, dtype=torch.uint8, device=self.w.device)
+            _lib.call("dca_pack_weights_tc_march", self._keep[0].data_ptr(), self.cin, self.w_march.data_ptr(), planes,
+                      _stream())
         return True
 
 
@@ -121,6 +127,8 @@ class Options:
     tc_modes = {0, 1, 2, 3}       # conv modes the tcgen05 kernel takes (K3S1, K3S2, T3S2, K1)
     fuse_upsample_in_conv = True  # cva fuse stage: fold the trilinear upsample into the 1x1x1 conv's epilogue
     fuse_redir_in_deconv = True   # Multi_Aggregation: conv3 (transposed) + redir (1x1x1) as one GEMM
+    use_march = True              # k3 s1 Cout=32 convs: depth-marching kernel (kd folded into the GEMM N)
+    march_min_items = 296         # ... when there are at least 2 work items per SM
     cout1_on_tc = True            # 32->1 convs: tensor-core per-tap GEMM + shifted sum instead of the CUDA-core kernel
     prop_on_tc = True             # the two 3x3 Conv2d of PropgationNet_4x on the halo-slab tcgen05 kernel
     up2_bilinear = True           # fuse stage: depth interpolation in the attention store, bilinear 4-class GEMM
@@ -150,6 +158,14 @@ def conv(x: Planes, pc: PackedConv, mode=K3S1, act=ACT_NONE, res_pre: Planes = N
     else:
         y = Planes(x.B, Do, Ho, Wo, pc.cout, planes_out, dev)
         yptr = y.ptr
+    if (Options.use_tc and Options.use_march and mode == K3S1 and not out_fp32 and up is None and side is None
+            and pc.w_march is not None and pc.tc_planes == x.planes and planes_out == x.planes
+            and x.B * ((x.D + 15) // 16) * ((x.H + 15) // 16) * ((x.W + 7) // 8) >= Options.march_min_items):
+        # depth-marching kernel: enough (tile column x depth chunk) work items to fill the SMs
+        _lib.call("dca_conv3d_tc_march", x.ptr, x.planes, pc.w_march.data_ptr(), _ptr(pc.scale), _ptr(pc.shift),
+                  res_pre.ptr if res_pre is not None else 0, res_post.ptr if res_post is not None else 0, planes_res,
+                  yptr, act, x.B, pc.cin, x.D, x.H, x.W, _stream())
+        return y
     if (Options.use_tc and not out_fp32 and pc.w_tc is not None and pc.tc_planes == x.planes
             and tc_supported(mode, pc.cin, pc.cout)):
         _lib.call("dca_conv3d_tc", mode, x.ptr, x.planes, pc.w_tc.data_ptr(), _ptr(pc.scale), _ptr(pc.shift),

@@ -91,6 +91,14 @@ int dca_up2_tc(int kind, const void* x, int planes, const void* side, int side_c
 int dca_conv1_taps_tc(const void* x, int planes, const void* w_tc, float* P, int ntap, int B, int D, int H, int W,
                       void* stream);
 int dca_tap_gather3d(const float* P, float* out, int B, int D, int H, int W, void* stream);
+/* Depth-marching member of the family: Conv3d k3 s1 p1, Cout = 32, Cin in {32,64}.  A CTA walks the input planes of a
+ * chunk of <= 16 output planes; each halo slab is read once per (kh,kw) for all three kd (N = 96).  Same epilogue
+ * contract as dca_conv3d_tc.  w_march from dca_pack_weights_tc_march ([kh*3+kw][plane][kd][32][Cin] bf16). */
+int dca_conv3d_tc_march(const void* x, int planes, const void* w_march, const float* scale, const float* shift,
+                        const void* res_pre, const void* res_post, int planes_res, void* y, int act, int B, int Cin,
+                        int D, int H, int W, void* stream);
+int dca_pack_weights_tc_march(const float* w, int Ci, void* out, int planes, void* stream);
+long long dca_pack_weights_tc_march_bytes(int Ci, int planes);
 /* 2-D 3x3 s1 p1 convs of the propagation net (gwcnet_dca_g.py:112-115) on the halo-slab tcgen05 kernel.
  * x [planes][B][1][H][W][Cin] (Cin 64/128); y cost planes (Cout % 64 == 0) or fp32 channels-last [B][H][W][Cout]. */
 int dca_conv2d_tc(const void* x, int planes, const void* w_tc2d, const float* scale, const float* shift, void* y,

@@ -171,6 +171,41 @@ def test_conv_cout1_and_2d():
     close(mask[:, 0].permute(0, 3, 1, 2), ref, 5e-5, "prop convs")
 
 
+@pytest.mark.parametrize("ci,shape", [(32, (1, 20, 19, 37)), (64, (1, 7, 18, 34)), (32, (2, 33, 16, 8))])
+@pytest.mark.parametrize("planes", [2, 1])
+def test_conv_marching_kernel(ci, shape, planes):
+    """Depth-marching k3 s1 kernel (kd folded into N, sliding TMEM window) vs the fp32 oracle conv."""
+    d, E, O = _mods()
+    B, D, H, W = shape
+    x = rnd(B, ci, D, H, W, seed=35)
+    bn = _bn(32, 36)
+    conv = torch.nn.Conv3d(ci, 32, 3, padding=1, bias=False)
+    w = conv.weight.data
+    xin = x
+    if planes == 1:
+        xin = x.to(torch.bfloat16).float()
+        conv.weight.data = w.to(torch.bfloat16).float()
+    with torch.no_grad():
+        ref0 = bn(conv(xin))
+    conv.weight.data = w
+    res1, res2 = rnd(*ref0.shape, seed=37), rnd(*ref0.shape, seed=38)
+    if planes == 1:
+        res1, res2 = res1.to(torch.bfloat16).float(), res2.to(torch.bfloat16).float()
+    ref = F.relu(ref0 + res1) + res2
+    pc = E.PackedConv(conv.weight.cuda(), bn.cuda())
+    assert pc.pack_tc(planes) and pc.w_march is not None
+    saved = E.Options.march_min_items
+    E.Options.march_min_items = 1
+    try:
+        n0 = d._lib.LAUNCHES
+        y = E.conv(E.Planes.from_ncdhw(x.cuda(), planes), pc, E.K3S1, E.ACT_RELU,
+                   res_pre=E.Planes.from_ncdhw(res1.cuda(), planes), res_post=E.Planes.from_ncdhw(res2.cuda(), planes))
+        torch.cuda.synchronize()
+    finally:
+        E.Options.march_min_items = saved
+    close(y.to_ncdhw(), ref, 1e-4 if planes == 2 else 1e-2, "march conv")
+
+
 @pytest.mark.parametrize("planes", [2, 1])
 def test_prop_convs_on_tcgen05(planes):
     """The two 3x3 Conv2d of PropgationNet_4x (64->128 +BN+ReLU, 128->144) on the halo-slab tcgen05 kernel."""
