@@ -56,6 +56,7 @@ struct TcParams {
   const __nv_bfloat16* up; int planes_up;   // optional half-resolution tensor added (trilinear x2) before BN
   int nslab; int slab_c0[3]; int slab_dz[3];   // halo kernel: slabs per tile (3 depth slabs, or channel halves in 2-D)
   int ldc, co_base, cout_valid, out_f32;        // output row pitch / first channel / valid channels / fp32 output
+  float inv_tiles_w, inv_tiles_h, inv_Dt, inv_ncls;   // reciprocals for the epilogue's tile decode (fast_divmod)
   int march_n;                     // > 0: depth-marching kernel, a work item = march_n consecutive output planes
   int cls_inner;                   // epilogue/work order: CTA owns whole tiles, classes inside (up2 kernel)
   int linear;                      // 1x1x1 convs: tiles are 128 CONSECUTIVE voxels (8 KB bursts); rB/rD/rH/rW = real dims
@@ -65,6 +66,14 @@ struct TcParams {
   int ngrp;      // halo kernel: taps are interleaved over ngrp independent accumulator groups
   int lo_sep;    // halo kernel, parity: lo*Whi goes to its own column block
 };
+
+static inline void fill_recips(TcParams& p) {
+  p.inv_tiles_w = 1.0f / (float)(p.tiles_w > 0 ? p.tiles_w : 1);
+  p.inv_tiles_h = 1.0f / (float)(p.tiles_h > 0 ? p.tiles_h : 1);
+  p.inv_Dt = 1.0f / (float)(p.Dt > 0 ? p.Dt : 1);
+  const int nc = p.march_n > 0 ? p.march_n : (p.ncls > 0 ? p.ncls : 1);
+  p.inv_ncls = 1.0f / (float)nc;
+}
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -160,6 +169,17 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// n / d and n % d for 0 <= n < 2^24 with a precomputed float reciprocal (exact after one correction step);
+// replaces the ~25-instruction integer division sequences of the per-tile index decode
+__device__ __forceinline__ int fast_divmod(int n, int d, float inv, int& rem) {
+  int q = __float2int_rz(__int2float_rn(n) * inv);
+  int r = n - q * d;
+  if (r >= d) { ++q; r -= d; }
+  if (r < 0) { --q; r += d; }
+  rem = r;
+  return q;
+}
+
 // ------------------------------------------------------------------ shared epilogue (warps 2..9)
 // TMEM accumulator -> registers -> (+lo half) -> [+ trilinear x2 of `up`] -> BN scale/shift -> +res_pre -> act
 // -> +res_post -> bf16 planes.  Eight warps: warp w reads TMEM lanes [32*(w%4), +32) (hardware restriction) and
@@ -231,13 +251,14 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
   const int n_items = mn ? my_march * mn : (p.cls_inner ? my_tiles * p.ncls : total_tiles);
   for (int item = (mn ? 0 : first); item < n_items; item += (mn ? 1 : step), ++it) {
     int r, cls, mj = 0, mwi = 0;
-    if (mn) { cls = 0; mwi = item / mn; mj = item - mwi * mn; r = (int)blockIdx.x + mwi * (int)gridDim.x; }
-    else if (p.cls_inner) { cls = item % p.ncls; r = (int)blockIdx.x + (item / p.ncls) * (int)gridDim.x; }
-    else { cls = item % p.ncls; r = item / p.ncls; }
-    const int tw = r % p.tiles_w; r /= p.tiles_w;
-    const int th = r % p.tiles_h; r /= p.tiles_h;
-    const int td = r % p.Dt;
-    const int b = r / p.Dt;
+    if (mn) { cls = 0; mwi = fast_divmod(item, mn, p.inv_ncls, mj); r = (int)blockIdx.x + mwi * (int)gridDim.x; }
+    else if (p.cls_inner) { const int q = fast_divmod(item, p.ncls, p.inv_ncls, cls); r = (int)blockIdx.x + q * (int)gridDim.x; }
+    else if (p.ncls > 1) { r = fast_divmod(item, p.ncls, p.inv_ncls, cls); }
+    else { cls = 0; r = item; }
+    int tw, th, td;
+    r = fast_divmod(r, p.tiles_w, p.inv_tiles_w, tw);
+    r = fast_divmod(r, p.tiles_h, p.inv_tiles_h, th);
+    const int b = fast_divmod(r, p.Dt, p.inv_Dt, td);
     const uint32_t acc = it & 1;
     const int ty = th * TC_TH + hh, tx = tw * TC_TW + ww;
     if (mn && mj == 0) {
@@ -354,11 +375,19 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
             if (p.co_base + cb + j < p.cout_valid) yf[j] = v[j];
         } else {
           uint32_t hw[8], lw[8];
+          if (PLANES == 2) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) split2(v[2 * j], v[2 * j + 1], hw[j], lw[j]);
+            for (int j = 0; j < 8; ++j) split2(v[2 * j], v[2 * j + 1], hw[j], lw[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const __nv_bfloat162 hq = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+              hw[j] = *reinterpret_cast<const uint32_t*>(&hq);
+            }
+          }
           *reinterpret_cast<uint4*>(p.y + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
           *reinterpret_cast<uint4*>(p.y + off + 8) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-          if (p.planes_out == 2) {
+          if (PLANES == 2 && p.planes_out == 2) {
             *reinterpret_cast<uint4*>(p.y + p.y_plane + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
             *reinterpret_cast<uint4*>(p.y + p.y_plane + off + 8) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
           }
@@ -1135,7 +1164,8 @@ static int launch_tc_march(const TcMaps& maps, const TcParams& p, cudaStream_t s
   cudaFuncSetAttribute(conv_tc_march_kernel<CIN, PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   const int total = p.B * p.Dt * p.tiles_h * p.tiles_w;
   const int grid = total < g_num_sms ? total : g_num_sms;
-  conv_tc_march_kernel<CIN, PLANES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);
+  TcParams q = p; fill_recips(q);
+  conv_tc_march_kernel<CIN, PLANES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, q);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }
@@ -1218,7 +1248,8 @@ static int launch_tc(const TcMaps& maps, const TcParams& p, cudaStream_t st) {
                        Cfg::SMEM_BYTES);
   const int total = p.B * p.Dt * p.tiles_h * p.tiles_w * p.ncls;
   const int grid = total < g_num_sms ? total : g_num_sms;
-  conv_tc_kernel<CIN, COUT, PLANES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);
+  TcParams q = p; fill_recips(q);
+  conv_tc_kernel<CIN, COUT, PLANES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, q);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }
@@ -1238,7 +1269,8 @@ static int launch_tc_halo(const TcMaps& maps, const TcParams& p, cudaStream_t st
                        Cfg::SMEM_BYTES);
   const int total = p.B * p.Dt * p.tiles_h * p.tiles_w;
   const int grid = total < g_num_sms ? total : g_num_sms;
-  conv_tc_halo_kernel<CIN, COUT, PLANES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);
+  TcParams q = p; fill_recips(q);
+  conv_tc_halo_kernel<CIN, COUT, PLANES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, q);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }
@@ -1274,7 +1306,8 @@ static int launch_up2(const TcMaps& maps, const TcParams& p, const Up2Params& u,
   cudaFuncSetAttribute(conv_tc_up2_kernel<CIN, PLANES, NSLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   const int total = p.B * p.Dt * p.tiles_h * p.tiles_w;
   const int grid = total < g_num_sms ? total : g_num_sms;
-  conv_tc_up2_kernel<CIN, PLANES, NSLAB><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p, u);
+  TcParams q = p; fill_recips(q);
+  conv_tc_up2_kernel<CIN, PLANES, NSLAB><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, q, u);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }
