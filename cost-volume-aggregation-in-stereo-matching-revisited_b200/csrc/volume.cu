@@ -17,6 +17,8 @@
 //          G <= slot < G+Cc -> left concat copy, < G+2Cc -> right concat copy, rest zero pad.
 //   The 32 fp32 results of a lane are bf16-split, pair-exchanged by shuffle and stored as 32-bit
 //   words so that a warp store covers whole 32-byte sectors of two voxels.
+#include <cuda.h>
+
 #include "dca_common.cuh"
 
 namespace dca {
@@ -183,6 +185,330 @@ volume_fused_kernel(const float* __restrict__ gl, const float* __restrict__ gr,
   }
 }
 
+// =====================================================================================================
+// TMA-staged fused kernel for DCANet's shape (C = 320 = 40 groups x 8, 12 concat channels, W % 8 == 0).
+//   lane < G/2 owns the group PAIR (2l, 2l+1) = output channels (2l, 2l+1); a 4w x 8d register tile per group costs
+//   4 LDS.128 per 32 FMA, and the two results of a voxel are exactly one packed bf16x2 word per plane: no shuffles, a
+//   warp store = one voxel's 128-byte channel row.  Lanes G/2 .. G/2+Cc-1 copy the left / right concat features in the
+//   same product form (cl[w] * [w >= d], 1 * cr[w-d]), the rest write the zero pad.
+//   The window of a (row, 16 columns, 48 disparities) item starts at u0 = w0 - d0 - 48 (a multiple of 16 columns), is
+//   64 columns wide and out-of-image columns are zero filled by TMA (= the reference's zero-initialised volume).
+// =====================================================================================================
+constexpr int V2_TW = 16, V2_DC = 48, V2_UW = 64;    // columns / disparities per item, right window (incl. 1 spare column)
+
+// packed bf16x2 split with plain bit operations for the hi -> fp32 expansion (shift / mask instead of PRMT pairs)
+__device__ __forceinline__ void vol_split2b(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);          // a -> low half, b -> high half
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// Persistent CTAs (one per SM, 12 warps), TMA-staged and double buffered:
+//   * the transposition to [c][u/8][slot][8] is done by the TMA unit: the fp32 NCHW feature map is described as a 5-D
+//     tensor (8 columns | group/2 (+ batch) | group parity | column octet | (channel-in-group, row)), so ONE box per
+//     channel-in-group lands as 32-byte units [u/8][slot] with slot = (g & 1) * G/2 + g/2; out-of-image octets are zero
+//     filled.  No LSU work, no registers, no address arithmetic for staging.  SWIZZLE_32B swaps the two float4 of a
+//     unit in every other 128-byte row, which is exactly what makes a warp's float4 loads (lane stride 32 B) conflict
+//     free; with G % 8 == 0 the swap bit of a lane is (slot >> 2) & 1, a per-lane constant.
+//   * warps walk ONE continuous stream of 4w x 8d tiles (24 slots per item, slot s -> warp s % 12: two tiles per warp
+//     and item, measured 3 % faster than 16 warps); an item's buffer is refilled (next-but-one item) by whichever warp finishes its
+//     last tile (shared-memory counter), and announced through an mbarrier with expect_tx.
+constexpr int V3_WARPS = 12, V3_THREADS = 32 * V3_WARPS;
+constexpr int V3_SLOTS = (V2_TW / 4) * (V2_DC / 8);      // tile slots per item (24)
+
+struct VolMaps { CUtensorMap r, l, cr, cl; };
+
+__device__ __forceinline__ uint32_t v_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void v_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(v_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void v_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(v_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void v_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  const uint32_t addr = v_smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void v_tma_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                         int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(v_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(v_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void v_tma_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(v_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(v_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+template <int G, int CPG, int CC>
+struct Vol3Cfg {
+  static constexpr int HG = G / 2, LW4 = V2_TW / 4, UW4 = V2_UW / 4, LW8 = V2_TW / 8, UW8 = V2_UW / 8;
+  static constexpr int RQ = CPG * UW4 * G, LQ = CPG * LW4 * G;       // float4 counts (dense slot pitch G)
+  static constexpr int R_BYTES = RQ * 16, L_BYTES = LQ * 16, CR_BYTES = CC * V2_UW * 4, CL_BYTES = CC * V2_TW * 4;
+  static constexpr int BUF_BYTES = R_BYTES + L_BYTES + CR_BYTES + CL_BYTES;
+  static constexpr int SMEM_BYTES = 2 * BUF_BYTES + 128 + 1024;      // + barriers/counters + alignment slack
+};
+
+template <int PLANES, int G, int CPG, int CC, int CV>
+__global__ void __launch_bounds__(V3_THREADS, 1)
+volume_fused3_kernel(const __grid_constant__ VolMaps maps, __nv_bfloat16* __restrict__ vol, int B, int D, int H, int W,
+                     int dbg) {
+  using Cfg = Vol3Cfg<G, CPG, CC>;
+  constexpr int HG = Cfg::HG, LW4 = Cfg::LW4, UW4 = Cfg::UW4, LW8 = Cfg::LW8, UW8 = Cfg::UW8;
+  static_assert(G % 8 == 0, "swap bit must be a per-lane constant");
+  extern __shared__ __align__(1024) uint8_t smem_v3[];
+  uint8_t* base = smem_v3;                 // (kept a shared-space pointer: no generic loads in the inner loop)
+  if (threadIdx.x == 0 && (v_smem_u32(base) & 255u) != 0) __trap();            // SWIZZLE_32B pattern repeats every 256 bytes
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + 2 * Cfg::BUF_BYTES);     // [2]
+  unsigned* cnt = reinterpret_cast<unsigned*>(full + 2);                       // [2]
+
+  const int wtiles = (W + V2_TW - 1) / V2_TW, dchunks = (D + V2_DC - 1) / V2_DC;
+  const int per_row = wtiles * dchunks;
+  const int n_items = per_row * H * B;
+  const int my_items = (n_items > (int)blockIdx.x) ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const size_t HW = (size_t)H * W;
+
+  auto issue = [&](int k) {
+    const int item = (int)blockIdx.x + k * (int)gridDim.x, buf = k & 1;
+    const int rowi = item / per_row, inrow = item - rowi * per_row;
+    const int b = rowi / H, h = rowi - b * H;
+    const int w0 = (inrow % wtiles) * V2_TW, d0 = (inrow / wtiles) * V2_DC;
+    const int u0 = w0 - d0 - V2_DC;
+    uint8_t* bb = base + buf * Cfg::BUF_BYTES;
+    v_mbar_expect_tx(&full[buf], Cfg::BUF_BYTES);
+    for (int c = 0; c < CPG; ++c) {
+      v_tma_5d(bb + c * (UW8 * G * 32), &maps.r, &full[buf], 0, HG * b, 0, u0 >> 3, c * H + h);
+      v_tma_5d(bb + Cfg::R_BYTES + c * (LW8 * G * 32), &maps.l, &full[buf], 0, HG * b, 0, w0 >> 3, c * H + h);
+    }
+    if (CC > 0) {
+      v_tma_3d(bb + Cfg::R_BYTES + Cfg::L_BYTES, &maps.cr, &full[buf], u0, CC * b, h);
+      v_tma_3d(bb + Cfg::R_BYTES + Cfg::L_BYTES + Cfg::CR_BYTES, &maps.cl, &full[buf], w0, CC * b, h);
+    }
+  };
+
+  if (tid == 0) {
+    v_mbar_init(&full[0], 1); v_mbar_init(&full[1], 1);
+    cnt[0] = 0; cnt[1] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (my_items > 0) issue(0);
+    if (my_items > 1) issue(1);
+  }
+  __syncthreads();
+
+  const float lane_scale = lane < HG ? 1.0f / (float)CPG : 1.0f;
+  const size_t plane_stride = (size_t)B * D * H * W * CV;
+  for (int s = warp; s < my_items * V3_SLOTS; s += V3_WARPS) {
+    const int k = s / V3_SLOTS, t = s - k * V3_SLOTS;
+    const int item = (int)blockIdx.x + k * (int)gridDim.x, buf = k & 1;
+    const int rowi = item / per_row, inrow = item - rowi * per_row;
+    const int b = rowi / H, h = rowi - b * H;
+    const int w0 = (inrow % wtiles) * V2_TW, d0 = (inrow / wtiles) * V2_DC;
+    const int dcount = min(V2_DC, D - d0);
+    const int u0 = w0 - d0 - V2_DC;                     // image column of window index 0 (multiple of 4)
+    const int wq = t % LW4, wt = wq * 4;                // local column of the 4-wide tile
+    const int dt = (t / LW4) * 8;                       // local disparity of the 8-deep tile
+    const float4* Rq = reinterpret_cast<const float4*>(base + buf * Cfg::BUF_BYTES);     // [CPG][UW4][G]
+    const float4* Lq = Rq + Cfg::RQ;                                                     // [CPG][LW4][G]
+    const float4* cRq = Lq + Cfg::LQ;                                                    // [CC][UW4]
+    const float4* cLq = cRq + CC * UW4;                                                  // [CC][LW4]
+    v_mbar_wait(&full[buf], (uint32_t)((k >> 1) & 1));
+    if (w0 + wt < W && dt < dcount && !(dbg & 1)) {
+      // window index of (w0+wt+i, d0+dt+j) = wt + i - dt - j + 48 = ub + (i - j + 8),  ub = wt - dt + 40 (multiple of 4)
+      const int ub = wt - dt + V2_DC - 8;
+      float acc[2][8][4];
+      if (lane < HG) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[q][j][i] = 0.f;
+        // unit (o, slot) = 32 bytes at ((c*W8 + o)*G + slot)*32; float4 `half` of it sits at 16*(half ^ swap(slot))
+        const uint8_t* Rb = reinterpret_cast<const uint8_t*>(Rq);
+        const uint8_t* Lb = reinterpret_cast<const uint8_t*>(Lq);
+        const int ub4 = ub >> 2;
+        uint32_t lo_[2], ro_[2][3];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int slot = lane + q * HG, sw = (slot >> 2) & 1;
+          lo_[q] = (uint32_t)((((wq >> 1) * G + slot) << 5) + (((wq & 1) ^ sw) << 4));
+#pragma unroll
+          for (int kk = 0; kk < 3; ++kk)
+            ro_[q][kk] = (uint32_t)(((((ub4 + kk) >> 1) * G + slot) << 5) + ((((ub4 + kk) & 1) ^ sw) << 4));
+        }
+#pragma unroll
+        for (int c = 0; c < CPG; ++c) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const float4 l4 = *reinterpret_cast<const float4*>(Lb + c * (LW8 * G * 32) + lo_[q]);
+            const float4 r0 = *reinterpret_cast<const float4*>(Rb + c * (UW8 * G * 32) + ro_[q][0]),
+                         r1 = *reinterpret_cast<const float4*>(Rb + c * (UW8 * G * 32) + ro_[q][1]),
+                         r2 = *reinterpret_cast<const float4*>(Rb + c * (UW8 * G * 32) + ro_[q][2]);
+            const float l[4] = {l4.x, l4.y, l4.z, l4.w};
+            const float r[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) acc[q][j][i] = fmaf(l[i], r[i - j + 8], acc[q][j][i]);
+          }
+        }
+      } else {
+        // concat lanes, same product form: left copy = cl[w] * [w - d >= 0], right copy = 1 * cr[w - d]
+        const bool left = lane < HG + CC / 2;
+        const int cc = 2 * (lane - HG - (left ? 0 : CC / 2));
+        const bool live = lane < HG + CC;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          float l[4] = {1.f, 1.f, 1.f, 1.f}, r[12];
+          if (left) {
+            const float4 l4 = live ? cLq[(cc + q) * LW4 + wq] : make_float4(0.f, 0.f, 0.f, 0.f);
+            l[0] = l4.x; l[1] = l4.y; l[2] = l4.z; l[3] = l4.w;
+#pragma unroll
+            for (int kk = 0; kk < 12; ++kk) r[kk] = (u0 + ub + kk >= 0) ? 1.f : 0.f;
+          } else {
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4* rp = cRq + (cc + q) * UW4 + (ub >> 2);
+            const float4 r0 = live ? rp[0] : z4, r1 = live ? rp[1] : z4, r2 = live ? rp[2] : z4;
+            r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w; r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
+            r[8] = r2.x; r[9] = r2.y; r[10] = r2.z; r[11] = r2.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[q][j][i] = l[i] * r[i - j + 8];
+        }
+      }
+      if (2 * lane < CV) {
+        __nv_bfloat16* rowp = vol + ((((size_t)b * D + d0 + dt) * H + h) * W + (w0 + wt)) * CV + 2 * lane;
+        const size_t dstep = HW * CV;
+        const int nj = min(8, dcount - dt);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j < nj) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint32_t hw, lw;
+              vol_split2b(acc[0][j][i] * lane_scale, acc[1][j][i] * lane_scale, hw, lw);
+              *reinterpret_cast<uint32_t*>(rowp + i * CV) = hw;
+              if (PLANES == 2) *reinterpret_cast<uint32_t*>(rowp + plane_stride + i * CV) = lw;
+            }
+          }
+          rowp += dstep;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      const unsigned old = atomicAdd(&cnt[buf], 1u);
+      if (old == V3_SLOTS - 1) {                        // last tile of this item: the buffer is free, refill it
+        __threadfence_block();
+        cnt[buf] = 0;
+        if (k + 2 < my_items && !(dbg & 2)) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          issue(k + 2);
+        } else if (k + 2 < my_items) {
+          v_mbar_expect_tx(&full[buf], 0);              // (timing probe: no loads)
+        }
+      }
+    }
+  }
+}
+
+typedef CUresult (*VolEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static VolEncodeFn vol_get_encode() {
+  static VolEncodeFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<VolEncodeFn>(sym);
+  }
+  return fn;
+}
+
+// features [B][G*CPG][H][W] fp32 as (8 | G/2 (+ batch) | 2 | W/8 | CPG*H), box = (8, G/2, 2, octets, 1), SWIZZLE_32B
+static bool vol_feature_map(CUtensorMap* m, const float* p, int B, int G, int CPG, int H, int W, int octets) {
+  VolEncodeFn enc = vol_get_encode();
+  if (!enc) return false;
+  const cuuint64_t HW = (cuuint64_t)H * W;
+  cuuint64_t dims[5] = {8, (cuuint64_t)(G / 2) * B, 2, (cuuint64_t)(W / 8), (cuuint64_t)CPG * H};
+  cuuint64_t strides[4] = {2 * (cuuint64_t)CPG * HW * 4, (cuuint64_t)CPG * HW * 4, 32, (cuuint64_t)W * 4};
+  cuuint32_t box[5] = {8, (cuuint32_t)(G / 2), 2, (cuuint32_t)octets, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(p), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// concat features [B][CC][H][W] fp32 as (W | CC*B | H), box = (cols, CC, 1)
+static bool vol_concat_map(CUtensorMap* m, const float* p, int B, int CC, int H, int W, int cols) {
+  VolEncodeFn enc = vol_get_encode();
+  if (!enc) return false;
+  const cuuint64_t HW = (cuuint64_t)H * W;
+  cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)CC * B, (cuuint64_t)H};
+  cuuint64_t strides[2] = {HW * 4, (cuuint64_t)W * 4};
+  cuuint32_t box[3] = {(cuuint32_t)cols, (cuuint32_t)CC, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int g_vol_sms = 0;
+static int g_volume_v2 = 1;   // bit0: use the TMA-staged kernel; bits 1..2: timing probes (skip compute / skip staging)
+template <int G, int CPG, int CC, int CV>
+static int launch_volume3(const float* gl, const float* gr, const float* cl, const float* cr, void* vol, int B, int D,
+                          int H, int W, int planes, cudaStream_t st) {
+  using Cfg = Vol3Cfg<G, CPG, CC>;
+  static_assert(G % 2 == 0 && G / 2 + CC <= 32 && CV >= G + 2 * CC && CV <= 64 && Cfg::SMEM_BYTES <= 227 * 1024 &&
+                Cfg::R_BYTES % 128 == 0 && Cfg::L_BYTES % 128 == 0 && Cfg::CR_BYTES % 128 == 0 && Cfg::CL_BYTES % 128 == 0,
+                "shape");
+  if (!g_vol_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_vol_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_vol_sms <= 0) g_vol_sms = 148;
+  }
+  VolMaps maps;
+  if (!vol_feature_map(&maps.r, gr, B, G, CPG, H, W, V2_UW / 8) || !vol_feature_map(&maps.l, gl, B, G, CPG, H, W, V2_TW / 8) ||
+      !vol_concat_map(&maps.cr, cr, B, CC, H, W, V2_UW) || !vol_concat_map(&maps.cl, cl, B, CC, H, W, V2_TW))
+    return DCA_ERR_LAUNCH;
+  const int wtiles = (W + V2_TW - 1) / V2_TW, dchunks = (D + V2_DC - 1) / V2_DC;
+  const long long items = (long long)wtiles * dchunks * H * B;
+  if (items * V3_SLOTS >= (1ll << 31)) return DCA_ERR_UNSUPPORTED;
+  const int grid = (int)(items < g_vol_sms ? items : g_vol_sms);
+  if (planes == 2) {
+    auto kern = volume_fused3_kernel<2, G, CPG, CC, CV>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    kern<<<grid, V3_THREADS, Cfg::SMEM_BYTES, st>>>(maps, (__nv_bfloat16*)vol, B, D, H, W, g_volume_v2 >> 1);
+  } else {
+    auto kern = volume_fused3_kernel<1, G, CPG, CC, CV>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    kern<<<grid, V3_THREADS, Cfg::SMEM_BYTES, st>>>(maps, (__nv_bfloat16*)vol, B, D, H, W, g_volume_v2 >> 1);
+  }
+  DCA_RETURN_IF_LAUNCH_FAILED();
+  return DCA_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Reference-API variants: fp32 NCDHW outputs, exactly the tensors build_gwc_volume /
 // build_concat_volume return.  CTA = one (b, group, h) row staged in smem, lane = column,
@@ -242,6 +568,9 @@ concat_volume_ncdhw_kernel(const float* __restrict__ cl, const float* __restrict
 
 using namespace dca;
 
+// 1 (default) = 16-byte-staged pair kernel for the DCANet shapes, 0 = generic kernel everywhere (A/B timing, tests)
+extern "C" int dca_volume_set_v2(int on) { g_volume_v2 = on; return DCA_OK; }
+
 extern "C" int dca_volume_gwc_concat(const float* gwc_l, const float* gwc_r, const float* cat_l, const float* cat_r,
                                      void* vol, int B, int C, int G, int Cc, int D, int H, int W, int Cv, int planes,
                                      void* stream) {
@@ -249,6 +578,9 @@ extern "C" int dca_volume_gwc_concat(const float* gwc_l, const float* gwc_r, con
   if (C % G != 0 || (Cc > 0 && (!cat_l || !cat_r)) || Cc < 0) return DCA_ERR_ARG;
   if (Cv < G + 2 * Cc || Cv > 64 || (Cv % 8) != 0 || (planes != 1 && planes != 2)) return DCA_ERR_ARG;
   const int cpg = C / G, gp = G + 1, UW = VOL_TW + VOL_DC - 1;
+  if ((W % 8) == 0 && Cc == 12 && C == 320 && (g_volume_v2 & 1)) {      // DCANet's shape and the 20-group point of config 4's sweep (8 groups x 40 channels does not fit two buffers)
+    if (G == 40 && Cv == 64) return launch_volume3<40, 8, 12, 64>(gwc_l, gwc_r, cat_l, cat_r, vol, B, D, H, W, planes, (cudaStream_t)stream);
+  }
   size_t smem = ((size_t)cpg * (VOL_TW + UW) * gp + (size_t)Cc * (VOL_TW + UW)) * sizeof(float);
   if (smem > 220 * 1024) return DCA_ERR_UNSUPPORTED;
   const int wtiles = (W + VOL_TW - 1) / VOL_TW, dchunks = (D + VOL_DC - 1) / VOL_DC;

@@ -107,6 +107,9 @@ int dca_pack_weights_tc2d(const float* w, int Co, int Ci, void* out, int planes,
 long long dca_pack_weights_tc2d_bytes(int Co, int Ci, int planes);
 /* k3 s1 main loop selector: 1 = halo'd slab reuse (default), 0 = one TMA box per tap. */
 int dca_tc_set_halo(int on);
+/* 1 (default): DCANet-shaped volumes (C=320, Cc=12, G in {8,20,40}, W % 4 == 0) use the 16-byte-staged group-pair
+   kernel; 0: the generic kernel everywhere (A/B timing and tests). */
+int dca_volume_set_v2(int on);
 /* halo kernel tuning: taps interleaved over ngrp (1,2,4) independent TMEM accumulator groups; lo_sep = own block for lo*Whi. */
 int dca_tc_set_tuning(int ngrp, int lo_sep);
 

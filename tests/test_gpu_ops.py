@@ -32,7 +32,9 @@ def rnd(*shape, seed=0):
 
 @pytest.mark.parametrize("B,C,G,Cc,H,W,D,planes", [
     (2, 320, 40, 12, 3, 37, 12, 2), (1, 320, 40, 12, 2, 64, 48, 2), (1, 320, 40, 12, 2, 50, 60, 1),
-    (1, 320, 8, 12, 2, 33, 24, 2), (1, 320, 20, 12, 2, 20, 7, 2), (1, 64, 8, 0, 2, 16, 4, 2)])
+    (1, 320, 8, 12, 2, 33, 24, 2), (1, 320, 20, 12, 2, 20, 7, 2), (1, 64, 8, 0, 2, 16, 4, 2),
+    (2, 320, 40, 12, 3, 40, 52, 2), (1, 320, 40, 12, 2, 72, 48, 1), (1, 320, 8, 12, 2, 36, 24, 2),
+    (1, 320, 20, 12, 2, 28, 96, 2)])
 def test_fused_volume(B, C, G, Cc, H, W, D, planes):
     d, E, O = _mods()
     L, R = rnd(B, C, H, W, seed=1), rnd(B, C, H, W, seed=2)
