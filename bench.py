@@ -269,9 +269,9 @@ def main():
             ach = fl / (conv_ms * 1e-3) / 1e12
             kernel_name = "conv3d_tc" if (E.Options.use_tc and pc.w_tc is not None and E.tc_supported(E.K3S1, 32, 32)) \
                 else "conv_direct_kernel<32,16> (CUDA-core fp32)"
-            tr = ncu_traffic("conv_tc_halo_kernel<32, 32, %d>" % P) if kernel_name == "conv3d_tc" else None
+            tr = ncu_traffic("conv_tc_march_kernel<32, %d>" % P) if kernel_name == "conv3d_tc" else None
             issued = 3.0 if (P == 2 and kernel_name == "conv3d_tc") else 1.0
-            roof = {"kernel": f"{kernel_name} k3 s1 32->32 @ {maxdisp // 4}x{H4}x{W4}", "bound": "tensor",
+            roof = {"kernel": f"{kernel_name} (conv_tc_march_kernel, tcgen05) k3 s1 32->32 @ {maxdisp // 4}x{H4}x{W4}", "bound": "tensor",
                     "achieved": ach, "peak": tf_sust, "unit": "TFLOP/s", "frac": ach / tf_sust,
                     "traffic": tr["bytes"] if tr else None,
                     "peak_source": f"{src} (bf16 sustained; burst {tf_burst})", "ms_per_launch": conv_ms,
@@ -293,10 +293,10 @@ def main():
             torch.cuda.synchronize()
             vol_ms = a.elapsed_time(b_) / n_it
             vb = workloads.volume_bytes(H, W, maxdisp, P) * B
-            extra["roofline_volume"] = {"kernel": "volume_fused_kernel", "bound": "hbm",
+            extra["roofline_volume"] = {"kernel": "volume_fused3_kernel (TMA-staged)", "bound": "hbm",
                                         "achieved": vb / (vol_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                                         "frac": vb / (vol_ms * 1e-3) / 1e9 / hbm,
-                                        "traffic": (ncu_traffic("volume_fused_kernel") or {}).get("bytes"),
+                                        "traffic": (ncu_traffic("volume_fused3_kernel") or {}).get("bytes"),
                                         "ms_per_launch": vol_ms, "algorithmic_bytes_per_launch": vb,
                                         "peak_source": src}
 
