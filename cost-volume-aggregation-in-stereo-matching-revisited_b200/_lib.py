@@ -36,6 +36,7 @@ SIGNATURES = {
     "dca_pack_weights_tc2d_bytes": [_c_int] * 3,
     "dca_tc_set_halo": [_c_int],
     "dca_volume_set_v2": [_c_int],
+    "dca_attention_set_team": [_c_int],
     "dca_tc_set_tuning": [_c_int, _c_int],
     "dca_avgpool3d": [_vp, _vp] + [_c_int] * 6 + [_vp],
     "dca_class_stats": [_vp, _vp, _vp, _vp] + [_c_int] * 4 + [_vp],

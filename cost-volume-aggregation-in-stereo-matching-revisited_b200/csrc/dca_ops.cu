@@ -136,12 +136,12 @@ __device__ __forceinline__ void at_split2(float a, float b, uint32_t& hi, uint32
 // src: bf16 pair [2][rows][AT_PITCH]; Wm: weight pair [2][32][AT_PITCH]; MT = number of 16-row tiles.
 // dst_pair != nullptr: result written as a bf16 pair (input of the next projection);
 // dst_f32  != nullptr: result written as fp32 [rows][32].
-template <int MT>
+// MT = 16-row tiles this warp computes, starting at row0; ROWS = rows of the whole buffer (plane pitch).
+template <int MT, int ROWS>
 __device__ __forceinline__ void warp_project_mma(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ Wm,
                                                  const float* __restrict__ ss, bool affine_act,
                                                  __nv_bfloat16* __restrict__ dst_pair, float* __restrict__ dst_f32,
-                                                 int lane) {
-  constexpr int ROWS = 16 * MT;
+                                                 int lane, int row0 = 0) {
   float acc[MT][4][4];
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt)
@@ -167,7 +167,7 @@ __device__ __forceinline__ void warp_project_mma(const __nv_bfloat16* __restrict
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
       uint32_t ah[4], al[4];
-      const uint32_t off = (uint32_t)(((mt * 16 + a_row) * AT_PITCH + kt * 16 + a_col) * 2);
+      const uint32_t off = (uint32_t)(((row0 + mt * 16 + a_row) * AT_PITCH + kt * 16 + a_col) * 2);
       ldsm_x4(s_src + off, ah[0], ah[1], ah[2], ah[3]);
       ldsm_x4(s_src + ROWS * AT_PITCH * 2 + off, al[0], al[1], al[2], al[3]);
 #pragma unroll
@@ -189,7 +189,7 @@ __device__ __forceinline__ void warp_project_mma(const __nv_bfloat16* __restrict
     for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
       for (int hrow = 0; hrow < 2; ++hrow) {
-        const int row = mt * 16 + g + hrow * 8;
+        const int row = row0 + mt * 16 + g + hrow * 8;
         float v0 = acc[mt][nt][hrow * 2] * sc0 + sh0, v1 = acc[mt][nt][hrow * 2 + 1] * sc1 + sh1;
         if (affine_act) { v0 = v0 > 0.f ? v0 : 0.1f * v0; v1 = v1 > 0.f ? v1 : 0.1f * v1; }
         if (dst_f32) *reinterpret_cast<float2*>(dst_f32 + row * AT_C + col) = make_float2(v0, v1);
@@ -206,8 +206,11 @@ __device__ __forceinline__ void warp_project_mma(const __nv_bfloat16* __restrict
 }
 
 // DT = compile-time disparity count (24 at KITTI/SceneFlow: scores stay in registers, two-pass softmax); 0 = runtime D
-template <int PLANES, int MT, int DT>
-__global__ void __launch_bounds__(256)
+// WPP = warps per pixel: 1 = a warp walks a pixel alone; 2 = a TEAM of two warps shares a pixel's buffers (each computes
+// 16 of the 32 projection rows, half of the attention items and half of the stores; phases are separated by a 64-thread
+// named barrier), which doubles the resident warps for the same shared memory: the kernel is latency bound.
+template <int PLANES, int MT, int DT, int WPP>
+__global__ void __launch_bounds__(256 * WPP)
 disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ cls, const float* __restrict__ e,
                       const float* __restrict__ S, const float* __restrict__ wts, int has_wa,
                       __nv_bfloat16* __restrict__ y, int B, int D, int H, int Wd, int pad) {
@@ -218,7 +221,16 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
   extern __shared__ __align__(16) uint8_t smem_at[];
   __nv_bfloat16* Wsm = reinterpret_cast<__nv_bfloat16*>(smem_at);               // [7][2][32][AT_PITCH]
   float* ss = reinterpret_cast<float*>(smem_at + AT_NMAT * 2 * AT_WPLANE * 2);   // 6 x (scale[32], shift[32])
-  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  static_assert(WPP == 1 || (WPP == 2 && MT == 2 && DT > 0), "team mode: 32 rows, compile-time D");
+  const int lane = threadIdx.x & 31;
+  const int warps = (blockDim.x >> 5) / WPP, warp = (threadIdx.x >> 5) / WPP;    // teams per CTA, this warp's team
+  const int wip = (threadIdx.x >> 5) % WPP;                                      // warp index inside the team
+  constexpr int MTW = MT / WPP;                                                  // projection tiles per warp
+  const int row0 = wip * 16 * MTW;
+  auto team_sync = [&]() {
+    if (WPP == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1 + warp), "r"(32 * WPP) : "memory");
+  };
   uint8_t* wbase = smem_at + AT_NMAT * 2 * AT_WPLANE * 2 + 6 * 64 * 4 + (size_t)warp * (3 * PAIR * 2 + 3 * FBUF * 4);
   __nv_bfloat16* P0 = reinterpret_cast<__nv_bfloat16*>(wbase);
   __nv_bfloat16* P1 = P0 + PAIR;
@@ -236,7 +248,7 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
   }
   for (int i = threadIdx.x; i < 6 * 64; i += blockDim.x) ss[i] = __ldg(wts + AT_NMAT * AT_C * AT_C + i);
   // zero this warp's buffers once: rows [D, ROWS) are never loaded and must stay finite
-  for (int i = lane; i < (3 * PAIR * 2 + 3 * FBUF * 4) / 4; i += 32) reinterpret_cast<uint32_t*>(wbase)[i] = 0u;
+  for (int i = lane + 32 * wip; i < (3 * PAIR * 2 + 3 * FBUF * 4) / 4; i += 32 * WPP) reinterpret_cast<uint32_t*>(wbase)[i] = 0u;
   __syncthreads();
   const __nv_bfloat16* Wq0 = Wsm, *Wq1 = Wsm + 2 * AT_WPLANE, *Wk0 = Wsm + 4 * AT_WPLANE, *Wk1 = Wsm + 6 * AT_WPLANE,
                       *Wv = Wsm + 8 * AT_WPLANE, *Wo = Wsm + 10 * AT_WPLANE, *Wa = Wsm + 12 * AT_WPLANE;
@@ -248,7 +260,7 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
     const int kp = cls[pix];
     const float wp = e[pix] / S[(size_t)b * D + kp];
     // ---- x (already hi/lo in HBM) -> P0 verbatim; key = x * (1 + [d == kp] w_p) -> P1 (re-split on that plane) ----
-    for (int d0 = 0; d0 < D; d0 += 8) {
+    for (int d0 = 8 * wip; d0 < D; d0 += 8 * WPP) {
       const int d = d0 + (lane >> 2), q = lane & 3;
       if (d < D) {
         const size_t off = (((size_t)b * D + d) * HW + p) * AT_C + q * 8;
@@ -271,25 +283,28 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
         *reinterpret_cast<uint4*>(P1 + ROWS * AT_PITCH + d * AT_PITCH + q * 8) = kl;
       }
     }
-    __syncwarp();
-    warp_project_mma<MT>(P0, Wq0, ss + 0 * 64, true, P2, nullptr, lane);
-    warp_project_mma<MT>(P2, Wq1, ss + 1 * 64, true, nullptr, F0, lane);     // q  -> F0 (fp32)
-    warp_project_mma<MT>(P1, Wk0, ss + 2 * 64, true, P2, nullptr, lane);
-    warp_project_mma<MT>(P2, Wk1, ss + 3 * 64, true, nullptr, F1, lane);     // k  -> F1
-    warp_project_mma<MT>(P1, Wv, ss + 4 * 64, true, nullptr, F2, lane);      // v  -> F2
+    team_sync();
+    // (projections are row-wise: a warp only ever reads the rows it wrote itself, so no team barrier in between)
+    warp_project_mma<MTW, ROWS>(P0, Wq0, ss + 0 * 64, true, P2, nullptr, lane, row0);
+    warp_project_mma<MTW, ROWS>(P2, Wq1, ss + 1 * 64, true, nullptr, F0, lane, row0);     // q  -> F0 (fp32)
+    warp_project_mma<MTW, ROWS>(P1, Wk0, ss + 2 * 64, true, P2, nullptr, lane, row0);
+    warp_project_mma<MTW, ROWS>(P2, Wk1, ss + 3 * 64, true, nullptr, F1, lane, row0);     // k  -> F1
+    warp_project_mma<MTW, ROWS>(P1, Wv, ss + 4 * 64, true, nullptr, F2, lane, row0);      // v  -> F2
+    team_sync();
     // ---- attention: item = (dq, head), 4 heads x D queries; a lane owns up to 2*MT items and walks the keys ONCE
     //      for all of them (independent online-softmax chains interleave -> ILP); ctx -> P0 as a bf16 pair ----
     if (DT > 0) {
       // scores of a lane's items stay in registers: pass 1 = all dot products + running max, pass 2 = exp2 and P.V
-      constexpr int NI = (4 * (DT > 0 ? DT : 1) + 31) / 32;
+      constexpr int NI = (4 * (DT > 0 ? DT : 1) + 32 * WPP - 1) / (32 * WPP);
       constexpr int DK = DT > 0 ? DT : 1;
-      const int hd = lane & 3;
+      // item = (dq, head) = ((lane + 32 r) * WPP + wip): a team splits the items by parity
+      const int hd = (lane * WPP + wip) & 3;
       float sc[NI][DK], mx[NI];
       {
         float4 qa[NI], qb[NI];
 #pragma unroll
         for (int r = 0; r < NI; ++r) {
-          const int dq = min((lane + 32 * r) >> 2, ROWS - 1);
+          const int dq = min(((lane + 32 * r) * WPP + wip) >> 2, ROWS - 1);
           qa[r] = *reinterpret_cast<const float4*>(F0 + dq * AT_C + hd * 8);
           qb[r] = *reinterpret_cast<const float4*>(F0 + dq * AT_C + hd * 8 + 4);
           qa[r].x *= qscale; qa[r].y *= qscale; qa[r].z *= qscale; qa[r].w *= qscale;
@@ -331,7 +346,7 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
       }
 #pragma unroll
       for (int r = 0; r < NI; ++r) {
-        const int item = lane + 32 * r;
+        const int item = (lane + 32 * r) * WPP + wip;
         if (item < 4 * D) {
           const int dq = item >> 2;
           const float il = 1.f / ls[r];
@@ -395,16 +410,17 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
         }
       }
     }
-    __syncwarp();
+    team_sync();
     const float* res;
     if (has_wa) {
-      warp_project_mma<MT>(P0, Wo, ss + 5 * 64, true, P1, nullptr, lane);    // aug_down -> P1
-      warp_project_mma<MT>(P1, Wa, nullptr, false, nullptr, F0, lane);       // t = Wa . aug_down -> F0
+      warp_project_mma<MTW, ROWS>(P0, Wo, ss + 5 * 64, true, P1, nullptr, lane, row0);    // aug_down -> P1
+      warp_project_mma<MTW, ROWS>(P1, Wa, nullptr, false, nullptr, F0, lane, row0);       // t = Wa . aug_down -> F0
       res = F0;
     } else {
-      warp_project_mma<MT>(P0, Wo, ss + 5 * 64, true, nullptr, F0, lane);
+      warp_project_mma<MTW, ROWS>(P0, Wo, ss + 5 * 64, true, nullptr, F0, lane, row0);
       res = F0;
     }
+    team_sync();
     // ---- store [d][32] rows: lane = (row, chunk).  pad = 1 writes into a tensor with a replicated 1-voxel border
     //      ([D+2][H+2][W+2], what the trilinear-x2 "up2" GEMM consumes) ----
     const int ph = p / Wd, pw = p - ph * Wd;
@@ -413,7 +429,7 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
       // h/w borders are replicated; the up2 GEMM (kind 2) then only interpolates bilinearly in (h, w)
       const int Dz = 2 * D, Hp2 = H + 2, Wp2 = Wd + 2;
       const size_t oplane = (size_t)B * Dz * Hp2 * Wp2 * AT_C;
-      for (int z0 = 0; z0 < Dz; z0 += 8) {
+      for (int z0 = 8 * wip; z0 < Dz; z0 += 8 * WPP) {
         const int z = z0 + (lane >> 2), q = lane & 3;
         if (z < Dz) {
           const int i = z >> 1;
@@ -437,12 +453,12 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
           }
         }
       }
-      __syncwarp();
+      team_sync();
       continue;
     }
     const int Dp2 = D + 2 * pad, Hp2 = H + 2 * pad, Wp2 = Wd + 2 * pad;
     const size_t oplane = (size_t)B * Dp2 * Hp2 * Wp2 * AT_C;
-    for (int d0 = 0; d0 < D; d0 += 8) {
+    for (int d0 = 8 * wip; d0 < D; d0 += 8 * WPP) {
       const int d = d0 + (lane >> 2), q = lane & 3;
       if (d < D) {
         float f[8];
@@ -469,7 +485,7 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
         }
       }
     }
-    __syncwarp();
+    team_sync();
   }
 }
 
@@ -809,6 +825,10 @@ extern "C" int dca_class_stats(const float* logits, int* cls, float* e, float* S
   return DCA_OK;
 }
 
+static int g_attention_team = 1;
+// 1 (default): two warps per pixel for D/8 == 24; 0: one warp per pixel (A/B timing)
+extern "C" int dca_attention_set_team(int on) { g_attention_team = on ? 1 : 0; return DCA_OK; }
+
 extern "C" int dca_disp_attention(const void* x, const int* cls, const float* e, const float* S, const float* weights,
                                   int has_wa, void* y, int pad, int planes, int B, int C, int D, int H, int W,
                                   void* stream) {
@@ -826,16 +846,18 @@ extern "C" int dca_disp_attention(const void* x, const int* cls, const float* e,
   int grid = (B * HW + warps - 1) / warps;
   if (grid > 148) grid = 148;            // persistent: one CTA per SM pays the weight-staging prologue once
   cudaStream_t st = (cudaStream_t)stream;
-#define DCA_AT_LAUNCH2(P_, MT_, DT_)                                                                             \
+#define DCA_AT_LAUNCH2(P_, MT_, DT_, WPP_)                                                                       \
   do {                                                                                                           \
-    auto kern = disp_attention_kernel<P_, MT_, DT_>;                                                                \
+    auto kern = disp_attention_kernel<P_, MT_, DT_, WPP_>;                                                          \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
-    kern<<<grid, warps * 32, smem, st>>>((const __nv_bfloat16*)x, cls, e, S, weights, has_wa, (__nv_bfloat16*)y, B, \
-                                         D, H, W, pad);                                                          \
+    kern<<<grid, warps * 32 * WPP_, smem, st>>>((const __nv_bfloat16*)x, cls, e, S, weights, has_wa,              \
+                                                (__nv_bfloat16*)y, B, D, H, W, pad);                             \
   } while (0)
-#define DCA_AT_LAUNCH(P_, MT_) DCA_AT_LAUNCH2(P_, MT_, 0)
-  if (D == 24) {
-    if (planes == 2) DCA_AT_LAUNCH2(2, 2, 24); else DCA_AT_LAUNCH2(1, 2, 24);
+#define DCA_AT_LAUNCH(P_, MT_) DCA_AT_LAUNCH2(P_, MT_, 0, 1)
+  if (D == 24 && g_attention_team) {
+    if (planes == 2) DCA_AT_LAUNCH2(2, 2, 24, 2); else DCA_AT_LAUNCH2(1, 2, 24, 2);
+  } else if (D == 24) {
+    if (planes == 2) DCA_AT_LAUNCH2(2, 2, 24, 1); else DCA_AT_LAUNCH2(1, 2, 24, 1);
   } else if (planes == 2) {
     if (MT == 1) DCA_AT_LAUNCH(2, 1); else if (MT == 2) DCA_AT_LAUNCH(2, 2); else if (MT == 3) DCA_AT_LAUNCH(2, 3); else DCA_AT_LAUNCH(2, 4);
   } else {

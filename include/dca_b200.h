@@ -110,6 +110,8 @@ int dca_tc_set_halo(int on);
 /* 1 (default): DCANet-shaped volumes (C=320, Cc=12, G in {8,20,40}, W % 4 == 0) use the 16-byte-staged group-pair
    kernel; 0: the generic kernel everywhere (A/B timing and tests). */
 int dca_volume_set_v2(int on);
+/* 1 (default): dca_disp_attention runs two warps per pixel when D/8 == 24; 0: one warp per pixel (A/B timing). */
+int dca_attention_set_team(int on);
 /* halo kernel tuning: taps interleaved over ngrp (1,2,4) independent TMEM accumulator groups; lo_sep = own block for lo*Whi. */
 int dca_tc_set_tuning(int ngrp, int lo_sep);
 
