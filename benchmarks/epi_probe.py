@@ -24,7 +24,10 @@ def main():
     nb4 = lib.dca_pack_weights_tc_bytes(32, 32, 4, P)
     w4 = torch.zeros(nb4, dtype=torch.uint8, device="cuda")
     sc = torch.ones(32, device="cuda"); sh = torch.zeros(32, device="cuda")
+    pc27 = E.PackedCout1(torch.randn(1, 32, 3, 3, 3, device="cuda") * .1, P)
+    Pbuf = torch.empty((27, 48 * 96 * 312), dtype=torch.float32, device="cuda")
     cases = {
+        "conv1_taps@1/4": lambda: d._lib.call("dca_conv1_taps_tc", x4.ptr, P, pc27.w_tc.data_ptr(), Pbuf.data_ptr(), 27, 1, 48, 96, 312, E._stream()),
         "k1_linear_32_32@1/4": lambda: E.conv(x4, pc1, E.K1, E.ACT_NONE),
         "s2_32_64@1/4": lambda: E.conv(x4, pcs2, E.K3S2, E.ACT_RELU),
         "up2_deconv64+side": lambda: E.up2(0, x8, x4, w28, sc, sh, E.ACT_RELU, 64, 24, 48, 156),

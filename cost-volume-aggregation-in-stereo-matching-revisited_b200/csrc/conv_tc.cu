@@ -201,10 +201,10 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
 }
 // (a, b) -> packed bf16x2 hi and bf16x2 lo (= bf16 of the remainders)
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  const float2 hf = __bfloat1622float2(h);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);          // a -> low half, b -> high half
   hi = *reinterpret_cast<const uint32_t*>(&h);
+  // hi -> fp32 by shift / mask (the __bfloat1622float2 form compiles to two PRMT + two SHF)
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 __device__ __forceinline__ void add_raw16(float* v, const uint4* raw, int planes) {   // raw[0..1] hi, raw[2..3] lo
@@ -276,12 +276,14 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
     const bool valid = (ty < p.Ht) && (tx < p.Wt) && (oz < p.Do) && (oy < p.Ho) && (ox < p.Wo);
     const size_t vox = (((size_t)b * p.Do + oz) * p.Ho + oy) * p.Wo + ox;
     int bb = b, uD = p.Do, uH = p.Ho, uW = p.Wo;
-    if (p.linear) {                   // recover the real voxel coordinates from the linear index
-      size_t r2 = vox;
-      ox = (int)(r2 % p.rW); r2 /= p.rW;
-      oy = (int)(r2 % p.rH); r2 /= p.rH;
-      oz = (int)(r2 % p.rD);
-      bb = (int)(r2 / p.rD);
+    if (p.linear && p.up != nullptr) {   // only the fused-upsample term needs the real voxel coordinates of a linear tile
+      // (32-bit arithmetic: the 64-bit div/mod chain that used to sit here cost ~2000 cycles per tile and bounded every
+      //  linear 1x1x1 launch; linear tiles index fewer than 2^31 voxels by construction)
+      unsigned r2 = (unsigned)vox;
+      const unsigned q1 = r2 / (unsigned)p.rW; ox = (int)(r2 - q1 * (unsigned)p.rW);
+      const unsigned q2 = q1 / (unsigned)p.rH; oy = (int)(q1 - q2 * (unsigned)p.rH);
+      const unsigned q3 = q2 / (unsigned)p.rD; oz = (int)(q2 - q3 * (unsigned)p.rD);
+      bb = (int)q3;
       uD = p.rD; uH = p.rH; uW = p.rW;
     }
     const size_t off0 = vox * (size_t)p.ldc + p.co_base + half * 16;   // first chunk's 16 channels of this thread
@@ -350,8 +352,16 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
             for (int j = 0; j < 16; ++j) v[j] += upv[j];
           }   // (the fused upsample is only used with COUT == 32)
         }
+        {
+          const float4* sc4 = reinterpret_cast<const float4*>(s_scale + cb);     // (16-float aligned: 4 LDS.128 each)
+          const float4* sh4 = reinterpret_cast<const float4*>(s_shift + cb);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = v[j] * s_scale[cb + j] + s_shift[cb + j];
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 a = sc4[j4], c = sh4[j4];
+            v[4 * j4 + 0] = fmaf(v[4 * j4 + 0], a.x, c.x); v[4 * j4 + 1] = fmaf(v[4 * j4 + 1], a.y, c.y);
+            v[4 * j4 + 2] = fmaf(v[4 * j4 + 2], a.z, c.z); v[4 * j4 + 3] = fmaf(v[4 * j4 + 3], a.w, c.w);
+          }
+        }
         if (p.res_pre) {
           if (c0 != 0) load_raw16(pre_raw, p.res_pre, p.res_plane, p.planes_res, off);
           add_raw16(v, pre_raw, p.planes_res);
@@ -363,11 +373,14 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
           add_raw16(v, post_raw, p.planes_res);
         }
         if (p.out_f32 == 2) {                 // fp32 CHANNEL-major output [Cout][nvox] (per-tap partial sums of the 32->1 convs)
-          float* yf = reinterpret_cast<float*>(p.y);
           const size_t nvox = (size_t)p.B * p.Do * p.Ho * p.Wo;
+          float* yf = reinterpret_cast<float*>(p.y) + (size_t)(p.co_base + cb) * nvox + vox;   // one 64-bit product per tile
+          const int nval = p.cout_valid - (p.co_base + cb);
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (p.co_base + cb + j < p.cout_valid) yf[(size_t)(p.co_base + cb + j) * nvox + vox] = v[j];
+          for (int j = 0; j < 16; ++j) {
+            if (j < nval) *yf = v[j];
+            yf += nvox;
+          }
         } else if (p.out_f32) {               // fp32 channels-last output (mask logits of the propagation net)
           float* yf = reinterpret_cast<float*>(p.y) + off;
 #pragma unroll
@@ -455,6 +468,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
+      // single-tap launches (1x1x1 convs, per-tap GEMMs): every stage slot always holds the same weight tile, so it is
+      // loaded only on the first pass over the ring (148 SMs re-reading one 4 KB tile per 128 voxels is an L2 hot spot)
+      const bool one_tap = (p.ntaps == 1 && p.ncls == 1);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int r = tile;
         const int cls = r % p.ncls; r /= p.ncls;
@@ -464,14 +480,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         const int b = r / p.Dt;
         for (int t = p.cls_tap0[cls]; t < p.cls_tap0[cls + 1]; ++t) {
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+          const bool need_w = !(one_tap && ph != 0);
+          mbar_expect_tx(&full[s], need_w ? Cfg::STAGE_BYTES : PLANES * Cfg::A_BYTES);
           uint8_t* st = stage_base + (size_t)s * Cfg::STAGE_BYTES;
           const CUtensorMap* am = &maps.a[p.tap_map[t]];
           const int cw = tw * TC_TW + p.tap_off[t][2], chh = th * TC_TH + p.tap_off[t][1], cd = td + p.tap_off[t][0];
 #pragma unroll
           for (int pl = 0; pl < PLANES; ++pl)
             tma_load_5d(st + pl * Cfg::A_BYTES, am, &full[s], 0, cw, chh, cd, pl * p.B + b);
-          tma_load_2d(st + PLANES * Cfg::A_BYTES, &maps.w, &full[s], 0, p.tap_w[t] * Cfg::B_ROWS);
+          if (need_w) tma_load_2d(st + PLANES * Cfg::A_BYTES, &maps.w, &full[s], 0, p.tap_w[t] * Cfg::B_ROWS);
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -1537,7 +1554,7 @@ extern "C" int dca_conv3d_tc(int mode, const void* x, int planes_in, const void*
     return DCA_ERR_UNSUPPORTED;
   }
   const long long nvox = (long long)B * Di * Hi * Wi;
-  if (mode == 3 && (nvox % 8) == 0 && nvox / 8 < (1ll << 31)) {
+  if (mode == 3 && (nvox % 8) == 0 && nvox < (1ll << 31)) {
     // 1x1x1 conv: the voxel order is irrelevant, so tile the flat voxel index (8 x nvox/8 view): each tile is 128
     // consecutive voxels = one contiguous 8/16 KB burst per plane instead of sixteen 512-byte rows
     const int rows = (int)(nvox / 8);
