@@ -221,13 +221,21 @@ __device__ __forceinline__ void add_raw16(float* v, const uint4* raw, int planes
     }
   }
 }
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): a thread's 16 channels of one plane are exactly one 32-byte
+// sector, so one instruction moves a whole sector instead of two half-sector requests
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t* w) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
 __device__ __forceinline__ void load_raw16(uint4* raw, const __nv_bfloat16* base, size_t plane, int planes, size_t off) {
-  raw[0] = *reinterpret_cast<const uint4*>(base + off);
-  raw[1] = *reinterpret_cast<const uint4*>(base + off + 8);
-  if (planes == 2) {
-    raw[2] = *reinterpret_cast<const uint4*>(base + plane + off);
-    raw[3] = *reinterpret_cast<const uint4*>(base + plane + off + 8);
-  }
+  ldg256(base + off, raw[0], raw[1]);
+  if (planes == 2) ldg256(base + plane + off, raw[2], raw[3]);
 }
 
 template <int COUT, int PLANES>
@@ -398,12 +406,8 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
               hw[j] = *reinterpret_cast<const uint32_t*>(&hq);
             }
           }
-          *reinterpret_cast<uint4*>(p.y + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          *reinterpret_cast<uint4*>(p.y + off + 8) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-          if (PLANES == 2 && p.planes_out == 2) {
-            *reinterpret_cast<uint4*>(p.y + p.y_plane + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-            *reinterpret_cast<uint4*>(p.y + p.y_plane + off + 8) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
-          }
+          stg256(p.y + off, hw);
+          if (PLANES == 2 && p.planes_out == 2) stg256(p.y + p.y_plane + off, lw);
         }
       }
     }
