@@ -30,9 +30,10 @@ avgpool3d_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict_
     int oh = (int)(r % Ho); r /= Ho;
     int od = (int)(r % Do);
     int b = (int)(r / Do);
-    float acc[8];
+    // packed fp32x2 adds (sm_100 FADD2): the kernel is issue bound on the bf16 unpack + accumulate stream
+    float2 acc2[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int k = 0; k < 4; ++k) acc2[k] = make_float2(0.f, 0.f);
     for (int dz = -1; dz <= 1; ++dz) {
       int iz = 2 * od + dz;
       if (iz < 0 || iz >= Di) continue;
@@ -43,15 +44,24 @@ avgpool3d_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict_
         for (int dx = -1; dx <= 1; ++dx) {
           int ix = 2 * ow + dx;
           if (ix < 0 || ix >= Wi) continue;
+          const size_t off = ((((size_t)b * Di + iz) * Hi + iy) * Wi + ix) * C + c8 * 8;
+          const uint4 hv = *reinterpret_cast<const uint4*>(x + off);
           float f[8];
-          load8<PLANES>(x, xin_plane, ((((size_t)b * Di + iz) * Hi + iy) * Wi + ix) * C + c8 * 8, f);
+          unpack8(hv, f);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc[k] += f[k];
+          for (int k = 0; k < 4; ++k) acc2[k] = __fadd2_rn(acc2[k], make_float2(f[2 * k], f[2 * k + 1]));
+          if (PLANES == 2) {
+            const uint4 lv = *reinterpret_cast<const uint4*>(x + xin_plane + off);
+            unpack8(lv, f);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc2[k] = __fadd2_rn(acc2[k], make_float2(f[2 * k], f[2 * k + 1]));
+          }
         }
       }
     }
+    float acc[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] *= (1.0f / 27.0f);
+    for (int k = 0; k < 4; ++k) { acc[2 * k] = acc2[k].x * (1.0f / 27.0f); acc[2 * k + 1] = acc2[k].y * (1.0f / 27.0f); }
     store8<PLANES>(y, yout_plane, ((((size_t)b * Do + od) * Ho + oh) * Wo + ow) * C + c8 * 8, acc);
   }
 }
