@@ -241,10 +241,9 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
     if (WPP == 1) __syncwarp();
     else asm volatile("bar.sync %0, %1;" ::"r"(1 + warp), "r"(32 * WPP) : "memory");
   };
-  uint8_t* wbase = smem_at + AT_NMAT * 2 * AT_WPLANE * 2 + 6 * 64 * 4 + (size_t)warp * (3 * PAIR * 2 + 3 * FBUF * 4);
-  __nv_bfloat16* P0 = reinterpret_cast<__nv_bfloat16*>(wbase);
-  __nv_bfloat16* P1 = P0 + PAIR;
-  __nv_bfloat16* P2 = P1 + PAIR;
+  uint8_t* wbase = smem_at + AT_NMAT * 2 * AT_WPLANE * 2 + 6 * 64 * 4 + (size_t)warp * (2 * PAIR * 2 + 3 * FBUF * 4);
+  __nv_bfloat16* P0 = reinterpret_cast<__nv_bfloat16*>(wbase);     // x, then key (row k_p rescaled in place), then ctx
+  __nv_bfloat16* P2 = P0 + PAIR;                                   // intermediate of the two-layer projections
   float* F0 = reinterpret_cast<float*>(P2 + PAIR);
   float* F1 = F0 + FBUF;
   float* F2 = F1 + FBUF;
@@ -258,7 +257,7 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
   }
   for (int i = threadIdx.x; i < 6 * 64; i += blockDim.x) ss[i] = __ldg(wts + AT_NMAT * AT_C * AT_C + i);
   // zero this warp's buffers once: rows [D, ROWS) are never loaded and must stay finite
-  for (int i = lane + 32 * wip; i < (3 * PAIR * 2 + 3 * FBUF * 4) / 4; i += 32 * WPP) reinterpret_cast<uint32_t*>(wbase)[i] = 0u;
+  for (int i = lane + 32 * wip; i < (2 * PAIR * 2 + 3 * FBUF * 4) / 4; i += 32 * WPP) reinterpret_cast<uint32_t*>(wbase)[i] = 0u;
   __syncthreads();
   const __nv_bfloat16* Wq0 = Wsm, *Wq1 = Wsm + 2 * AT_WPLANE, *Wk0 = Wsm + 4 * AT_WPLANE, *Wk1 = Wsm + 6 * AT_WPLANE,
                       *Wv = Wsm + 8 * AT_WPLANE, *Wo = Wsm + 10 * AT_WPLANE, *Wa = Wsm + 12 * AT_WPLANE;
@@ -269,7 +268,7 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
     const int b = pix / HW, p = pix % HW;
     const int kp = cls[pix];
     const float wp = e[pix] / S[(size_t)b * D + kp];
-    // ---- x (already hi/lo in HBM) -> P0 verbatim; key = x * (1 + [d == kp] w_p) -> P1 (re-split on that plane) ----
+    // ---- x (already hi/lo in HBM) -> P0 verbatim ----
     for (int d0 = 8 * wip; d0 < D; d0 += 8 * WPP) {
       const int d = d0 + (lane >> 2), q = lane & 3;
       if (d < D) {
@@ -279,27 +278,31 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
         if (PLANES == 2) l = *reinterpret_cast<const uint4*>(x + plane + off);
         *reinterpret_cast<uint4*>(P0 + d * AT_PITCH + q * 8) = h;
         *reinterpret_cast<uint4*>(P0 + ROWS * AT_PITCH + d * AT_PITCH + q * 8) = l;
-        uint4 kh = h, kl = l;
-        if (d == kp) {
-          float f[8], g2[8];
-          unpack8(h, f); unpack8(l, g2);
-          const float ks = 1.f + wp;
-          uint32_t hw[4], lw[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) at_split2((f[2 * j] + g2[2 * j]) * ks, (f[2 * j + 1] + g2[2 * j + 1]) * ks, hw[j], lw[j]);
-          kh = make_uint4(hw[0], hw[1], hw[2], hw[3]); kl = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-        }
-        *reinterpret_cast<uint4*>(P1 + d * AT_PITCH + q * 8) = kh;
-        *reinterpret_cast<uint4*>(P1 + ROWS * AT_PITCH + d * AT_PITCH + q * 8) = kl;
       }
     }
     team_sync();
     // (projections are row-wise: a warp only ever reads the rows it wrote itself, so no team barrier in between)
     warp_project_mma<MTW, ROWS>(P0, Wq0, ss + 0 * 64, true, P2, nullptr, lane, row0);
     warp_project_mma<MTW, ROWS>(P2, Wq1, ss + 1 * 64, true, nullptr, F0, lane, row0);     // q  -> F0 (fp32)
-    warp_project_mma<MTW, ROWS>(P1, Wk0, ss + 2 * 64, true, P2, nullptr, lane, row0);
+    // key = x * (1 + [d == k_p] w_p): only row k_p differs from x, so it is rescaled (and re-split) in place by the warp
+    // that owns the row; the query projections above were the last readers of the plain row
+    if (kp >= row0 && kp < row0 + 16 * MTW && lane < 4) {
+      __nv_bfloat16* rh = P0 + kp * AT_PITCH + lane * 8;
+      __nv_bfloat16* rl = rh + ROWS * AT_PITCH;
+      float f[8], g2[8];
+      unpack8(*reinterpret_cast<const uint4*>(rh), f);
+      unpack8(*reinterpret_cast<const uint4*>(rl), g2);
+      const float ks = 1.f + wp;
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) at_split2((f[2 * j] + g2[2 * j]) * ks, (f[2 * j + 1] + g2[2 * j + 1]) * ks, hw[j], lw[j]);
+      *reinterpret_cast<uint4*>(rh) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      *reinterpret_cast<uint4*>(rl) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+    __syncwarp();
+    warp_project_mma<MTW, ROWS>(P0, Wk0, ss + 2 * 64, true, P2, nullptr, lane, row0);
     warp_project_mma<MTW, ROWS>(P2, Wk1, ss + 3 * 64, true, nullptr, F1, lane, row0);     // k  -> F1
-    warp_project_mma<MTW, ROWS>(P1, Wv, ss + 4 * 64, true, nullptr, F2, lane, row0);      // v  -> F2
+    warp_project_mma<MTW, ROWS>(P0, Wv, ss + 4 * 64, true, nullptr, F2, lane, row0);      // v  -> F2
     team_sync();
     // ---- attention: item = (dq, head), 4 heads x D queries; a lane owns up to 2*MT items and walks the keys ONCE
     //      for all of them (independent online-softmax chains interleave -> ILP); ctx -> P0 as a bf16 pair ----
@@ -423,8 +426,8 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
     team_sync();
     const float* res;
     if (has_wa) {
-      warp_project_mma<MTW, ROWS>(P0, Wo, ss + 5 * 64, true, P1, nullptr, lane, row0);    // aug_down -> P1
-      warp_project_mma<MTW, ROWS>(P1, Wa, nullptr, false, nullptr, F0, lane, row0);       // t = Wa . aug_down -> F0
+      warp_project_mma<MTW, ROWS>(P0, Wo, ss + 5 * 64, true, P2, nullptr, lane, row0);    // aug_down -> P2
+      warp_project_mma<MTW, ROWS>(P2, Wa, nullptr, false, nullptr, F0, lane, row0);       // t = Wa . aug_down -> F0
       res = F0;
     } else {
       warp_project_mma<MTW, ROWS>(P0, Wo, ss + 5 * 64, true, nullptr, F0, lane, row0);
@@ -848,7 +851,7 @@ extern "C" int dca_disp_attention(const void* x, const int* cls, const float* e,
   const int MT = (D + 15) / 16;
   if (MT > 4) return DCA_ERR_UNSUPPORTED;
   const size_t wbytes = (size_t)AT_NMAT * 2 * AT_WPLANE * 2 + 6 * 64 * 4;
-  const size_t per_warp = (size_t)3 * (2 * 16 * MT * AT_PITCH) * 2 + (size_t)3 * (16 * MT * AT_C) * 4;
+  const size_t per_warp = (size_t)2 * (2 * 16 * MT * AT_PITCH) * 2 + (size_t)3 * (16 * MT * AT_C) * 4;   // per pixel in flight
   int warps = 8;
   while (warps > 1 && wbytes + warps * per_warp > 224 * 1024) --warps;
   const size_t smem = wbytes + warps * per_warp;
