@@ -742,6 +742,170 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 
 
 // =====================================================================================================
+// Stride-2 3x3x3 conv, Cin = 32 -> Cout = 64 (Multi_Aggregation.conv1, cva.py:16-17) on halo slabs.
+// The per-tap kernel above needs 27 element-strided TMA boxes per tile and plane and is L2->SMEM bound (0.96 GB per
+// launch at KITTI).  Here the input is viewed as PAIRS of w-adjacent voxels, [.., W/2, 64 = 2 x 32 channels], i.e. rows
+// of 128 bytes (SWIZZLE_128B).  One box [64, 9 pairs, 33 rows] per input plane (3 per tile) then serves all nine
+// (kh, kw) taps through shifted UMMA descriptors:
+//     tap (kh, kw) of output (ho, wo) reads input row 2ho + kh - 1 and column 2wo + kw - 1
+//       = slab row 2*ho_l + kh (8-row groups 2 x 9 pair-rows apart: SBO = 2304 B),
+//         pair wo_l + (kw == 0 ? 0 : 1) and the EVEN voxel of the pair for kw == 1, the ODD one otherwise:
+//         the odd voxel is simply K-offset +64 bytes inside the 128-byte row.
+// Weights (27 x 8 KB in parity precision) stream per tap through an 8-deep ring.
+// =====================================================================================================
+template <int PLANES>
+struct S2Cfg {
+  static constexpr int CIN = 32, COUT = 64;
+  static constexpr int PW = TC_TW + 1, PH = 2 * TC_TH + 1;                  // slab: 9 pairs x 33 rows of 128 bytes
+  static constexpr int SLAB_BYTES = PW * PH * 128;
+  static constexpr int SLAB_PITCH = (SLAB_BYTES + 1023) / 1024 * 1024;
+  static constexpr int A_SLOT = PLANES * SLAB_PITCH;
+  static constexpr int A_SLOTS = PLANES == 2 ? 2 : 4;
+  static constexpr int B_ROWS = PLANES * COUT;
+  static constexpr int B_BYTES = B_ROWS * CIN * 2;                          // one tap
+  static constexpr int W_SLOTS = 8;
+  static constexpr int TMEM_COLS = 2 * PLANES * COUT;
+  static constexpr int SMEM_BYTES = A_SLOTS * A_SLOT + W_SLOTS * B_BYTES + 1024 + 256 + 2 * COUT * 4;
+};
+
+template <int PLANES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_s2slab_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+  using Cfg = S2Cfg<PLANES>;
+  constexpr int COUT = Cfg::COUT;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_base = smem;
+  uint8_t* w_base = smem + Cfg::A_SLOTS * Cfg::A_SLOT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_base + Cfg::W_SLOTS * Cfg::B_BYTES);
+  uint64_t* afull = bars;                       // [A_SLOTS]
+  uint64_t* aempty = afull + Cfg::A_SLOTS;      // [A_SLOTS]
+  uint64_t* wfull = aempty + Cfg::A_SLOTS;      // [W_SLOTS]
+  uint64_t* wempty = wfull + Cfg::W_SLOTS;      // [W_SLOTS]
+  uint64_t* tfull = wempty + Cfg::W_SLOTS;      // [2]
+  uint64_t* tempty = tfull + 2;                 // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_scale = reinterpret_cast<float*>(w_base + Cfg::W_SLOTS * Cfg::B_BYTES + 256);
+  float* s_shift = s_scale + COUT;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.B * p.Dt * p.tiles_h * p.tiles_w;
+
+  if (threadIdx.x < COUT) {
+    s_scale[threadIdx.x] = p.scale ? p.scale[threadIdx.x] : 1.f;
+    s_shift[threadIdx.x] = p.shift ? p.shift[threadIdx.x] : 0.f;
+  }
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
+    for (int i = 0; i < Cfg::W_SLOTS; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&maps.a[0]);
+    prefetch_tmap(&maps.w);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int r = tile;
+        const int tw = r % p.tiles_w; r /= p.tiles_w;
+        const int th = r % p.tiles_h; r /= p.tiles_h;
+        const int td = r % p.Dt;
+        const int b = r / p.Dt;
+        for (int kd = 0; kd < 3; ++kd) {
+          mbar_wait(&aempty[sa], pa ^ 1);
+          mbar_expect_tx(&afull[sa], PLANES * Cfg::SLAB_BYTES);
+#pragma unroll
+          for (int pl = 0; pl < PLANES; ++pl)
+            tma_load_5d(a_base + sa * Cfg::A_SLOT + pl * Cfg::SLAB_PITCH, &maps.a[0], &afull[sa], 0, tw * TC_TW - 1,
+                        2 * th * TC_TH - 1, 2 * td + kd - 1, pl * p.B + b);
+          if (++sa == Cfg::A_SLOTS) { sa = 0; pa ^= 1; }
+          for (int t9 = 0; t9 < 9; ++t9) {
+            mbar_wait(&wempty[sw], pw ^ 1);
+            mbar_expect_tx(&wfull[sw], Cfg::B_BYTES);
+            tma_load_2d(w_base + sw * Cfg::B_BYTES, &maps.w, &wfull[sw], 0, (kd * 9 + t9) * Cfg::B_ROWS);
+            if (++sw == Cfg::W_SLOTS) { sw = 0; pw ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    {
+      const bool leader = elect_one();
+      constexpr uint32_t idesc_full = make_idesc(TC_M, PLANES * COUT);
+      constexpr uint32_t idesc_half = make_idesc(TC_M, COUT);
+      constexpr uint64_t DA = desc_const<128>(2 * Cfg::PW * 128);      // pair rows, 8-row groups two slab rows apart
+      constexpr uint64_t DB = desc_const<64>(8 * 64);                  // weights: dense 64-byte rows
+      constexpr uint32_t NACC = PLANES * COUT;
+      const uint32_t a_u32 = smem_u32(a_base), w_u32 = smem_u32(w_base);
+      uint32_t sa = 0, pa = 0, sw = 0, pw = 0, it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1;
+        mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + acc * NACC;
+#pragma unroll 1
+        for (int kd = 0; kd < 3; ++kd) {
+          mbar_wait(&afull[sa], pa);
+          tc_fence_after();
+          const uint64_t da_slab = DA + ((a_u32 + sa * Cfg::A_SLOT) >> 4);
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              mbar_wait(&wfull[sw], pw);
+              tc_fence_after();
+              const uint64_t db_tap = DB + ((w_u32 + sw * Cfg::B_BYTES) >> 4);
+              const int a_off = (kh * Cfg::PW + (kw == 0 ? 0 : 1)) * 128 + (kw == 1 ? 0 : 64);
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const uint64_t da = da_slab + (uint64_t)((a_off + k * 32) >> 4);
+                const uint64_t db = db_tap + (uint64_t)((k * 32) >> 4);
+                const uint32_t accum = (kd == 0 && kh == 0 && kw == 0 && k == 0) ? 0u : 1u;
+                if (leader) {
+                  umma_bf16(d_addr, da, db, idesc_full, accum);
+                  if (PLANES == 2) umma_bf16(d_addr, da + (uint64_t)(Cfg::SLAB_PITCH >> 4), db, idesc_half, 1u);
+                }
+              }
+              __syncwarp();
+              if (leader) umma_commit(&wempty[sw]);
+              if (++sw == Cfg::W_SLOTS) { sw = 0; pw ^= 1; }
+            }
+          }
+          __syncwarp();
+          if (leader) umma_commit(&aempty[sa]);
+          if (++sa == Cfg::A_SLOTS) { sa = 0; pa ^= 1; }
+        }
+        if (leader) umma_commit(&tfull[acc]);
+        __syncwarp();
+      }
+    }
+  } else {
+    tc_epilogue<COUT, PLANES>(p, total_tiles, tmem_base, tfull, tempty, s_scale, s_shift, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// =====================================================================================================
 // "up2" kernel: outputs at TWICE the resolution of the main input, 8 output parity classes per low-res
 // tile, every class a short list of taps that all read the SAME halo'd slabs of the low-res tile:
 //   kind 0  ConvTranspose3d k3 s2 p1 op1 (o = 2i - 1 + k): slabs dz in {0,1}, tap offsets in {0,1}^3,
@@ -1252,6 +1416,7 @@ static bool make_w_map(CUtensorMap* m, const void* base, int Cin, int rows, int 
 }
 
 static int g_use_halo = 1;
+static int g_use_s2slab = 1;
 static int g_ngrp = 1, g_lo_sep = 0;
 static int g_dbg = 0;
 
@@ -1271,6 +1436,25 @@ static int launch_tc(const TcMaps& maps, const TcParams& p, cudaStream_t st) {
   const int grid = total < g_num_sms ? total : g_num_sms;
   TcParams q = p; fill_recips(q);
   conv_tc_kernel<CIN, COUT, PLANES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, q);
+  DCA_RETURN_IF_LAUNCH_FAILED();
+  return DCA_OK;
+}
+
+template <int PLANES>
+static int launch_tc_s2slab(const TcMaps& maps, const TcParams& p, cudaStream_t st) {
+  using Cfg = S2Cfg<PLANES>;
+  static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "smem plan");
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  cudaFuncSetAttribute(conv_tc_s2slab_kernel<PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  const int total = p.B * p.Dt * p.tiles_h * p.tiles_w;
+  const int grid = total < g_num_sms ? total : g_num_sms;
+  TcParams q = p; fill_recips(q);
+  conv_tc_s2slab_kernel<PLANES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, q);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }
@@ -1463,7 +1647,7 @@ extern "C" int dca_up2_tc(int kind, const void* x, int planes, const void* side,
 }
 
 // 1 = halo-slab main loop for k3 s1 (default), 0 = one TMA box per tap (v1)
-extern "C" int dca_tc_set_halo(int on) { g_use_halo = on ? 1 : 0; return DCA_OK; }
+extern "C" int dca_tc_set_halo(int on) { g_use_halo = on & 1; g_use_s2slab = (on & 2) ? 0 : 1; return DCA_OK; }
 // accumulator interleave (1,2,4) and separate lo block (0/1) of the halo kernel
 extern "C" int dca_tc_set_tuning(int ngrp, int lo_sep) {
   if (ngrp != 1 && ngrp != 2 && ngrp != 4) return DCA_ERR_ARG;
@@ -1587,6 +1771,17 @@ extern "C" int dca_conv3d_tc(int mode, const void* x, int planes_in, const void*
       }
     }
     return run();
+  }
+  if (mode == 1 && g_use_s2slab && Cin == 32 && Cout == 64 && (Wi % 2) == 0) {
+    // halo slabs over the (w-pair x 64 channel) view of the input: dims (64, W/2, H, D, planes*B)
+    if (!make_act_map(&maps.a[0], x, 64, Wi / 2, Hi, Di, P * B, (size_t)64, (size_t)Wi * Cin, sD, sB, TC_TW + 1, 2 * TC_TH + 1))
+      return DCA_ERR_LAUNCH;
+    for (int i = 1; i < 9; ++i) maps.a[i] = maps.a[0];
+    p.Dt = Do; p.Ht = Ho; p.Wt = Wo; p.out_stride = 1; p.ntaps = 27; p.ncls = 1;
+    p.cls_tap0[0] = 0; p.cls_tap0[1] = 27;
+    p.tiles_w = (p.Wt + TC_TW - 1) / TC_TW;
+    p.tiles_h = (p.Ht + TC_TH - 1) / TC_TH;
+    return P == 2 ? launch_tc_s2slab<2>(maps, p, st) : launch_tc_s2slab<1>(maps, p, st);
   }
   if (mode == 1) {
     // stride 2: output o reads input 2o + k - 1.  Tap k reads the parity view q = (k != 1) of that axis at
