@@ -934,14 +934,18 @@ struct Up2Cfg {
   static constexpr int SLAB_BYTES = HB_W * HB_H * ROWB;
   static constexpr int SLAB_PITCH = (SLAB_BYTES + 1023) / 1024 * 1024;
   static constexpr int SLAB_SET = NSLAB * PLANES * SLAB_PITCH;      // slabs x planes
-  static constexpr int A_BYTES = TC_M * ROWB;                        // one plane of a side box
+  static constexpr int A_BYTES = TC_M * 128;                         // one plane of a side box: 128 w-PAIR rows of 128 B
   static constexpr int SIDE_SLOT = PLANES * A_BYTES;
   static constexpr int B_ROWS = PLANES * COUT;
   static constexpr int B_BYTES = B_ROWS * ROWB;
-  static constexpr int W_SLOTS = 6;
   static constexpr int SIDE_SLOTS = 2;
-  static constexpr int FIXED = SIDE_SLOTS * SIDE_SLOT + W_SLOTS * B_BYTES + 1024 + 512 + 2 * COUT * 4;
-  static constexpr int NBUF = (2 * SLAB_SET + FIXED <= 225 * 1024) ? 2 : 1;
+  static constexpr int OTHER = SIDE_SLOTS * SIDE_SLOT + 1024 + 512 + 2 * COUT * 4;
+  static constexpr int NBUF = (2 * SLAB_SET + OTHER + 6 * B_BYTES <= 225 * 1024) ? 2 : 1;
+  // weight ring: whatever is left, 6..12 taps deep (the streamed 64->32 parity taps are 8 KB each and one tap is only
+  // ~200 tensor-pipe cycles of work, so the ring depth is the L2 latency the MMA warp can ride out)
+  static constexpr int W_FIT = (225 * 1024 - NBUF * SLAB_SET - OTHER) / B_BYTES;
+  static constexpr int W_SLOTS = W_FIT > 12 ? 12 : (W_FIT < 6 ? 6 : W_FIT);
+  static constexpr int FIXED = OTHER + W_SLOTS * B_BYTES;
   static constexpr int TMEM_COLS = 2 * PLANES * COUT < 32 ? 32 : 2 * PLANES * COUT;
   static constexpr int SMEM_BYTES = NBUF * SLAB_SET + FIXED;
 };
@@ -1019,12 +1023,14 @@ conv_tc_up2_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const 
                         tw * TC_TW, th * TC_TH, td + u.slab_dz[sl], pl * p.B + b);
         if (++sb == Cfg::NBUF) { sb = 0; pb ^= 1; }
         for (int cls = 0; cls < p.ncls; ++cls) {
-          if (u.has_side) {
+          if (u.has_side && (cls & 1) == 0) {
+            // one box of 128-byte w-PAIR rows serves both x parities (classes cls, cls+1): contiguous full-line
+            // requests instead of two element-strided boxes of 64-byte pieces
             mbar_wait(&dempty[sd], pd ^ 1);
             mbar_expect_tx(&dfull[sd], PLANES * Cfg::A_BYTES);
 #pragma unroll
             for (int pl = 0; pl < PLANES; ++pl)
-              tma_load_5d(side_base + sd * Cfg::SIDE_SLOT + pl * Cfg::A_BYTES, &maps.a[1 + cls], &dfull[sd], 0,
+              tma_load_5d(side_base + sd * Cfg::SIDE_SLOT + pl * Cfg::A_BYTES, &maps.a[1 + (cls >> 1)], &dfull[sd], 0,
                           tw * TC_TW, th * TC_TH, td, pl * p.B + b);
             if (++sd == Cfg::SIDE_SLOTS) { sd = 0; pd ^= 1; }
           }
@@ -1082,13 +1088,15 @@ conv_tc_up2_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const 
             }
           }
           if (u.has_side) {
-            mbar_wait(&dfull[sd], pd);
+            if ((cls & 1) == 0) mbar_wait(&dfull[sd], pd);      // the pair box of classes (cls, cls+1)
             if (!u.wres) mbar_wait(&wfull[sw], pw);
             tc_fence_after();
-            const uint64_t da0 = DD + ((side_u32 + sd * Cfg::SIDE_SLOT) >> 4);
+            // A = pair rows (SWIZZLE_128B, dense); the odd-x class reads the second voxel of each pair: K-offset +64 B
+            constexpr uint64_t DS = desc_const<128>(8 * 128);
+            const uint64_t da0 = DS + ((side_u32 + sd * Cfg::SIDE_SLOT + (uint32_t)(cls & 1) * 64u) >> 4);
             const uint64_t db0 = DD + ((w_u32 + (u.wres ? (uint32_t)u.side_widx : sw) * Cfg::B_BYTES) >> 4);
 #pragma unroll
-            for (int k = 0; k < CIN / 16; ++k) {
+            for (int k = 0; k < 2; ++k) {                        // the side input has 32 channels
               if (leader) {
                 umma_bf16(d_addr, da0 + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc_full, (t1 > t0 || k > 0) ? 1u : 0u);
                 if (PLANES == 2)
@@ -1096,9 +1104,9 @@ conv_tc_up2_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const 
               }
             }
             __syncwarp();
-            if (leader) { if (!u.wres) umma_commit(&wempty[sw]); umma_commit(&dempty[sd]); }
+            if (leader) { if (!u.wres) umma_commit(&wempty[sw]); if (cls & 1) umma_commit(&dempty[sd]); }
             if (!u.wres) { if (++sw == Cfg::W_SLOTS) { sw = 0; pw ^= 1; } }
-            if (++sd == Cfg::SIDE_SLOTS) { sd = 0; pd ^= 1; }
+            if (cls & 1) { if (++sd == Cfg::SIDE_SLOTS) { sd = 0; pd ^= 1; } }
           }
           if (leader) umma_commit(&tfull[acc]);
           __syncwarp();
@@ -1532,7 +1540,7 @@ extern "C" int dca_up2_tc(int kind, const void* x, int planes, const void* side,
                           int B, int Cin, int Dl, int Hl, int Wl, void* stream) {
   if (!x || !w_tc || !y || B <= 0 || planes < 1 || planes > 2 || Dl <= 0 || Hl <= 0 || Wl <= 0) return DCA_ERR_ARG;
   if (kind < 0 || kind > 2 || (kind >= 1 && (!side || Cin != 32)) || (Cin != 32 && Cin != 64)) return DCA_ERR_UNSUPPORTED;
-  if (side && (side_c <= 0 || side_c > Cin || (side_c % 8) != 0)) return DCA_ERR_ARG;
+  if (side && side_c != 32) return DCA_ERR_UNSUPPORTED;       // the side input is read as 128-byte w-pair rows
   cudaStream_t st = (cudaStream_t)stream;
   const int P = planes, Cout = 32;
   // kind 2: x is already at the OUTPUT depth (Dl = output depth); only H and W double
@@ -1560,12 +1568,13 @@ extern "C" int dca_up2_tc(int kind, const void* x, int planes, const void* side,
     return DCA_ERR_LAUNCH;
   for (int i = 1; i < 9; ++i) maps.a[i] = maps.a[0];
   if (side) {
-    const size_t qW = side_c, qH = (size_t)Wo * side_c, qD = (size_t)Ho * Wo * side_c, qB = (size_t)Do * Ho * Wo * side_c;
-    for (int pc = 0; pc < p.ncls; ++pc) {
-      const int pz = (kind == 2) ? 0 : (pc >> 2) & 1, py = (pc >> 1) & 1, px = pc & 1;
-      const __nv_bfloat16* base = (const __nv_bfloat16*)side + pz * qD + py * qH + px * qW;
-      if (!make_act_map(&maps.a[1 + pc], base, side_c, Wl, Hl, Dl, P * B, 2 * qW, 2 * qH, (kind == 2 ? 1 : 2) * qD, qB, TC_TW,
-                        TC_TH, Cin))
+    // w-PAIR views of the side input, one per (z, y) parity: dims (64 = 2 voxels x 32 channels, Wl, Hl, Dl, planes*B)
+    const size_t qH = (size_t)Wo * side_c, qD = (size_t)Ho * Wo * side_c, qB = (size_t)Do * Ho * Wo * side_c;
+    for (int pq = 0; pq < p.ncls / 2; ++pq) {
+      const int pz = (kind == 2) ? 0 : (pq >> 1) & 1, py = pq & 1;
+      const __nv_bfloat16* base = (const __nv_bfloat16*)side + pz * qD + py * qH;
+      if (!make_act_map(&maps.a[1 + pq], base, 64, Wl, Hl, Dl, P * B, (size_t)64, 2 * qH, (kind == 2 ? 1 : 2) * qD, qB, TC_TW,
+                        TC_TH, 64))
         return DCA_ERR_LAUNCH;
     }
     u.has_side = 1;

@@ -63,6 +63,23 @@ def test_hot_path_config1_matches_oracle():
     assert float((pv2.cpu() - refpv).abs().max()) < 1e-2 * float(refpv.abs().max())
 
 
+def test_hot_path_kitti_full_size_matches_oracle():
+    """BASELINE config[1] at FULL size (384x1248, maxdisp 192): the production call (no intermediate tensors kept)
+    against the oracle run live on the host CPU; same tolerance as config 1."""
+    import dcanet_b200 as d
+    O, feats, sd = _config1(H4=96, W4=312, maxdisp=192, seed=2)
+    with torch.no_grad():
+        ref4, refpv = O.hot_path(sd, *feats, maxdisp=192)
+    net = _load_into(d.GwcNet(192), sd).cuda().eval()
+    with torch.no_grad():
+        pred4, pv2 = net.hot_path(*[f.cuda() for f in feats])
+    dd = (pred4.cpu() - ref4).abs()
+    print("KITTI full-size parity: max %.4f mean %.5f px" % (float(dd.max()), float(dd.mean())))
+    assert pred4.shape == (1, 1, 384, 1248) and pv2.shape == (1, 24, 48, 156)
+    assert float(dd.max()) <= TOL_MAX and float(dd.mean()) <= TOL_MEAN
+    assert float((pv2.cpu() - refpv).abs().max()) < 1e-2 * float(refpv.abs().max())
+
+
 def test_fast_mode_tracks_bf16_emulated_oracle():
     """precision="fast" (single bf16 operands) is judged against the oracle run with bf16-rounded conv
     operands (SURVEY 7 hard part 2): same rounding points, so only summation order differs."""
