@@ -16,6 +16,7 @@ _f = ctypes.c_float
 # name -> argtypes (return type is int unless listed in _RESTYPES)
 SIGNATURES = {
     "dca_version": [],
+    "dca_plane_format": [],
     "dca_volume_gwc_concat": [_vp, _vp, _vp, _vp, _vp] + [_c_int] * 9 + [_vp],
     "dca_build_gwc_volume_f32": [_vp, _vp, _vp] + [_c_int] * 6 + [_vp],
     "dca_build_concat_volume_f32": [_vp, _vp, _vp] + [_c_int] * 5 + [_vp],

@@ -168,24 +168,20 @@ conv_direct_kernel(const ConvDirectParams p) {
       size_t off = vox * p.Cout + co;
       if (p.res_pre) {
         uint2 hv = *reinterpret_cast<const uint2*>(p.res_pre + off);
-        r[0] += __uint_as_float(hv.x << 16); r[1] += __uint_as_float(hv.x & 0xffff0000u);
-        r[2] += __uint_as_float(hv.y << 16); r[3] += __uint_as_float(hv.y & 0xffff0000u);
+        { const float2 a_ = h16x2_to_f2(hv.x), b_ = h16x2_to_f2(hv.y); r[0] += a_.x; r[1] += a_.y; r[2] += b_.x; r[3] += b_.y; }
         if (p.planes_res == 2) {
           uint2 lv = *reinterpret_cast<const uint2*>(p.res_pre + p.res_plane + off);
-          r[0] += __uint_as_float(lv.x << 16); r[1] += __uint_as_float(lv.x & 0xffff0000u);
-          r[2] += __uint_as_float(lv.y << 16); r[3] += __uint_as_float(lv.y & 0xffff0000u);
+          { const float2 a_ = h16x2_to_f2(lv.x), b_ = h16x2_to_f2(lv.y); r[0] += a_.x; r[1] += a_.y; r[2] += b_.x; r[3] += b_.y; }
         }
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) r[j] = apply_act(r[j], p.act);
       if (p.res_post) {
         uint2 hv = *reinterpret_cast<const uint2*>(p.res_post + off);
-        r[0] += __uint_as_float(hv.x << 16); r[1] += __uint_as_float(hv.x & 0xffff0000u);
-        r[2] += __uint_as_float(hv.y << 16); r[3] += __uint_as_float(hv.y & 0xffff0000u);
+        { const float2 a_ = h16x2_to_f2(hv.x), b_ = h16x2_to_f2(hv.y); r[0] += a_.x; r[1] += a_.y; r[2] += b_.x; r[3] += b_.y; }
         if (p.planes_res == 2) {
           uint2 lv = *reinterpret_cast<const uint2*>(p.res_post + p.res_plane + off);
-          r[0] += __uint_as_float(lv.x << 16); r[1] += __uint_as_float(lv.x & 0xffff0000u);
-          r[2] += __uint_as_float(lv.y << 16); r[3] += __uint_as_float(lv.y & 0xffff0000u);
+          { const float2 a_ = h16x2_to_f2(lv.x), b_ = h16x2_to_f2(lv.y); r[0] += a_.x; r[1] += a_.y; r[2] += b_.x; r[3] += b_.y; }
         }
       }
       uint32_t h[4], l[4];

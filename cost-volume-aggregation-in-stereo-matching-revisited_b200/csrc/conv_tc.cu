@@ -13,8 +13,11 @@
 // Precision (SURVEY 7 hard part 2):
 //   planes == 2 ("parity"): x = hi + lo, W = Whi + Wlo (all bf16).  Per K-step
 //        MMA#1  A=hi, B=[Whi;Wlo] (N = 2*Cout)  -> cols [0,Cout) += hi*Whi, cols [Cout,2Cout) += hi*Wlo
-//        MMA#2  A=lo, B=[Whi]     (N = Cout)    -> cols [0,Cout) += lo*Whi
-//     and the epilogue adds the two column halves: ~16-bit operand significand, fp32 accumulate.
+//        MMA#2  A=lo, B=[Whi]     (N = Cout)    -> cols [Cout,2Cout) += lo*Whi
+//     and the epilogue adds the two column halves.  The small correction terms (hi*Wlo, lo*Whi) share one block so that
+//     the main block sees one third of the accumulation steps: the tensor core TRUNCATES its fp32 accumulator toward
+//     zero at every MMA (measured: a systematic -1.5e-8 relative per step, benchmarks/tc_bias_probe.py), which is the
+//     dominant error of this path, and the truncation of the correction block is 2^-11 smaller.
 //   planes == 1 ("fast"): one MMA, plain bf16 operands.
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected lane),
 //   warps 2-9 = epilogue (TMEM -> registers -> [+ fused trilinear x2 term] -> BN scale/shift, residuals,
@@ -29,6 +32,7 @@ namespace dca {
 
 constexpr int TC_TW = 8, TC_TH = 16, TC_M = 128;
 constexpr int TC_THREADS = 320;       // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int MARCH_CORR = 256;       // march kernel, parity precision: TMEM column offset of the correction accumulators
 constexpr int TC_MAX_TAPS = 36;       // 27 + one fused 1x1x1 side tap per transposed-conv parity class
 
 struct TcMaps {
@@ -166,7 +170,9 @@ __host__ __device__ constexpr uint64_t desc_const(uint32_t sbo_bytes) {
 }
 // instruction descriptor, kind::f16: D=f32 (bit4), A=B=bf16 (bits 7,10), K-major both, N>>3 @17, M>>4 @24
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  // A/B format field: 0 = fp16, 1 = bf16 (DCA_F16_PLANES selects the plane format, dca_common.cuh)
+  return (1u << 4) | ((uint32_t)(DCA_F16_PLANES ? 0 : 1) << 7) | ((uint32_t)(DCA_F16_PLANES ? 0 : 1) << 10) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // n / d and n % d for 0 <= n < 2^24 with a precomputed float reciprocal (exact after one correction step);
@@ -200,13 +206,7 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
       ::"r"(taddr), "r"(z) : "memory");
 }
 // (a, b) -> packed bf16x2 hi and bf16x2 lo (= bf16 of the remainders)
-__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);          // a -> low half, b -> high half
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  // hi -> fp32 by shift / mask (the __bfloat1622float2 form compiles to two PRMT + two SHF)
-  const __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) { split_pair(a, b, hi, lo); }
 __device__ __forceinline__ void add_raw16(float* v, const uint4* raw, int planes) {   // raw[0..1] hi, raw[2..3] lo
   float f[8];
 #pragma unroll
@@ -272,7 +272,10 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
     if (mn && mj == 0) {
       // new work item: clear this thread's slice of the accumulator window, then tell the MMA warp (tempty[0])
       const uint32_t zaddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * 16;
-      for (int jj = 0; jj < mn; ++jj) tmem_st16_zero(zaddr + 32 * jj);
+      for (int jj = 0; jj < mn; ++jj) {
+        tmem_st16_zero(zaddr + 32 * jj);
+        if (PLANES == 2) tmem_st16_zero(zaddr + MARCH_CORR + 32 * jj);     // correction block (hi.Wlo + lo.Whi)
+      }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
@@ -335,9 +338,9 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
       uint32_t rh[16];
       float v[16];
       tmem_ld16(taddr + c0, rh);
-      if (PLANES == 2 && !mn) {          // (march mode sums hi.Whi + hi.Wlo + lo.Whi into ONE column block)
+      if (PLANES == 2) {                 // main block + correction block (march mode: MARCH_CORR columns further)
         uint32_t rl[16];
-        tmem_ld16(taddr + COUT + c0, rl);
+        tmem_ld16(taddr + (mn ? (uint32_t)MARCH_CORR : (uint32_t)COUT) + c0, rl);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rh[j]) + __uint_as_float(rl[j]);
@@ -402,8 +405,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const __nv_bfloat162 hq = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-              hw[j] = *reinterpret_cast<const uint32_t*>(&hq);
+              hw[j] = f2_to_h16x2(v[2 * j], v[2 * j + 1]);
             }
           }
           stg256(p.y + off, hw);
@@ -524,7 +526,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             if (leader) {
               umma_bf16(d_addr, da0 + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc_full, (t > t_first || k > 0) ? 1u : 0u);
               if (PLANES == 2)
-                umma_bf16(d_addr, da0 + (uint64_t)((Cfg::A_BYTES >> 4) + k * 2), db0 + (uint64_t)(k * 2), idesc_half, 1u);
+                umma_bf16(d_addr + COUT, da0 + (uint64_t)((Cfg::A_BYTES >> 4) + k * 2), db0 + (uint64_t)(k * 2), idesc_half, 1u);
             }
           }
           __syncwarp();
@@ -710,7 +712,7 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 const uint32_t accum = (kh == 0 && kw == 0 && k == 0) ? (kd != 0 ? 1u : 0u) : 1u;
                 if (leader && !(p.dbg & 2)) {
                   umma_bf16(d_addr, da, db, idesc_full, accum);
-                  if (PLANES == 2) umma_bf16(d_addr, da + (uint64_t)(Cfg::SLAB_PITCH >> 4), db, idesc_half, 1u);
+                  if (PLANES == 2) umma_bf16(d_addr + COUT, da + (uint64_t)(Cfg::SLAB_PITCH >> 4), db, idesc_half, 1u);
                 }
               }
             }
@@ -877,7 +879,7 @@ conv_tc_s2slab_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 const uint32_t accum = (kd == 0 && kh == 0 && kw == 0 && k == 0) ? 0u : 1u;
                 if (leader) {
                   umma_bf16(d_addr, da, db, idesc_full, accum);
-                  if (PLANES == 2) umma_bf16(d_addr, da + (uint64_t)(Cfg::SLAB_PITCH >> 4), db, idesc_half, 1u);
+                  if (PLANES == 2) umma_bf16(d_addr + COUT, da + (uint64_t)(Cfg::SLAB_PITCH >> 4), db, idesc_half, 1u);
                 }
               }
               __syncwarp();
@@ -1078,7 +1080,7 @@ conv_tc_up2_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const 
               if (leader) {
                 umma_bf16(d_addr, da0 + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc_full, (t > t0 || k > 0) ? 1u : 0u);
                 if (PLANES == 2)
-                  umma_bf16(d_addr, da0 + (uint64_t)((Cfg::SLAB_PITCH >> 4) + k * 2), db0 + (uint64_t)(k * 2), idesc_half, 1u);
+                  umma_bf16(d_addr + COUT, da0 + (uint64_t)((Cfg::SLAB_PITCH >> 4) + k * 2), db0 + (uint64_t)(k * 2), idesc_half, 1u);
               }
             }
             if (!u.wres) {
@@ -1100,7 +1102,7 @@ conv_tc_up2_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const 
               if (leader) {
                 umma_bf16(d_addr, da0 + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc_full, (t1 > t0 || k > 0) ? 1u : 0u);
                 if (PLANES == 2)
-                  umma_bf16(d_addr, da0 + (uint64_t)((Cfg::A_BYTES >> 4) + k * 2), db0 + (uint64_t)(k * 2), idesc_half, 1u);
+                  umma_bf16(d_addr + COUT, da0 + (uint64_t)((Cfg::A_BYTES >> 4) + k * 2), db0 + (uint64_t)(k * 2), idesc_half, 1u);
               }
             }
             __syncwarp();
@@ -1137,7 +1139,8 @@ conv_tc_up2_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const 
 // d'+1, d', d'-1, which sit side by side in TMEM: output plane j of the chunk owns columns 32*(n-1-j), so every
 // slab's three targets are one contiguous 96-column window that slides down by 32 columns per plane.
 // Per tap the activation tile is read from shared memory once instead of three times (the per-tile kernels are
-// SMEM-operand bound at N = 32/64).  Parity precision issues hi.Whi, hi.Wlo and lo.Whi into the SAME columns.
+// SMEM-operand bound at N = 32/64).  Parity precision issues hi.Whi into the main window and hi.Wlo, lo.Whi into a
+// second window MARCH_CORR columns further (so a chunk is at most 8 planes).
 // The window is zeroed by the epilogue warps before an item starts (every MMA accumulates), each finished plane
 // is announced through its own mbarrier, and the epilogue drains it while the MMA warp keeps marching.
 // =====================================================================================================
@@ -1158,7 +1161,7 @@ struct MarchCfg {
   static constexpr int W_SLOTS = WRES ? 1 : W_SLOTS_STR;
   static constexpr int W_BYTES_TOTAL = WRES ? 9 * TAP_BYTES : W_SLOTS * TAP_BYTES;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int MAXN = 16;
+  static constexpr int MAXN = PLANES == 2 ? 8 : 16;          // parity: main + correction accumulators = 2 x 32 columns per plane
   static constexpr int SMEM_BYTES = A_SLOTS * A_SLOT + W_BYTES_TOTAL + 1024 + 512 + 2 * COUT * 4;
 };
 
@@ -1290,9 +1293,9 @@ conv_tc_march_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 const uint64_t da = da_slab + (uint64_t)(((kh * HB_W + kw) * Cfg::ROWB + k * 32) >> 4);
                 if (leader && live) {
                   umma_bf16(d_addr, da, db_hi + (uint64_t)(k * 2), idesc, 1u);
-                  if (PLANES == 2) {
-                    umma_bf16(d_addr, da, db_lo + (uint64_t)(k * 2), idesc, 1u);
-                    umma_bf16(d_addr, da + (uint64_t)(Cfg::SLAB_PITCH >> 4), db_hi + (uint64_t)(k * 2), idesc, 1u);
+                  if (PLANES == 2) {     // the two small terms accumulate in their own block (truncation bias, see the header)
+                    umma_bf16(d_addr + MARCH_CORR, da, db_lo + (uint64_t)(k * 2), idesc, 1u);
+                    umma_bf16(d_addr + MARCH_CORR, da + (uint64_t)(Cfg::SLAB_PITCH >> 4), db_hi + (uint64_t)(k * 2), idesc, 1u);
                   }
                 }
               }
@@ -1405,7 +1408,7 @@ static bool make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, 
   cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   CUtensorMapSwizzle sw = (box_c * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
+  return enc(m, (DCA_F16_PLANES ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 5, const_cast<void*>(base), dims, strides, box, es,
              CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -1418,7 +1421,7 @@ static bool make_w_map(CUtensorMap* m, const void* base, int Cin, int rows, int 
   cuuint32_t box[2] = {(cuuint32_t)Cin, (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1, 1};
   CUtensorMapSwizzle sw = (Cin * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+  return enc(m, (DCA_F16_PLANES ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 2, const_cast<void*>(base), dims, strides, box, es,
              CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -1959,7 +1962,8 @@ extern "C" int dca_conv3d_tc_march(const void* x, int planes, const void* w_marc
   p.y = (__nv_bfloat16*)y; p.y_plane = p.res_plane; p.planes_out = P; p.act = act;
   p.npart = 1; p.ngrp = 1; p.dbg = g_dbg;
   p.ldc = Cout; p.cout_valid = Cout;
-  const int n = D < 16 ? D : 16;
+  const int nmax = P == 2 ? 8 : 16;            // planes per work item (TMEM: 512 columns)
+  const int n = D < nmax ? D : nmax;
   p.march_n = n;
   p.Dt = (D + n - 1) / n;                      // depth chunks
   p.Ht = H; p.Wt = W; p.out_stride = 1; p.ncls = 1;

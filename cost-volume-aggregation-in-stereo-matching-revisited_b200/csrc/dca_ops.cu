@@ -130,18 +130,17 @@ __device__ __forceinline__ void ldsm_x4(uint32_t saddr, uint32_t& r0, uint32_t& 
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(saddr));
 }
 __device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+#if DCA_F16_PLANES
+#define DCA_MMA_TYPES "f16.f16"
+#else
+#define DCA_MMA_TYPES "bf16.bf16"
+#endif
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32." DCA_MMA_TYPES ".f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
                "{%0, %1, %2, %3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void at_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  const float2 hf = __bfloat1622float2(h);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
+__device__ __forceinline__ void at_split2(float a, float b, uint32_t& hi, uint32_t& lo) { split_pair(a, b, hi, lo); }
 
 // src: bf16 pair [2][rows][AT_PITCH]; Wm: weight pair [2][32][AT_PITCH]; MT = number of 16-row tiles.
 // dst_pair != nullptr: result written as a bf16 pair (input of the next projection);
@@ -735,8 +734,8 @@ planes_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ x, int planes, float* _
     const int c = (int)((i / V) % C);
     const int b = (int)(i / (V * C));
     const size_t off = ((size_t)b * V + v) * Cp + c;
-    float r = __bfloat162float(x[off]);
-    if (planes == 2) r += __bfloat162float(x[plane + off]);
+    float r = h16_bits_to_float(__bfloat16_as_ushort(x[off]));
+    if (planes == 2) r += h16_bits_to_float(__bfloat16_as_ushort(x[plane + off]));
     y[i] = r;
   }
 }
@@ -966,4 +965,6 @@ extern "C" int dca_fold_bn(const float* gamma, const float* beta, const float* m
   return DCA_OK;
 }
 
-extern "C" int dca_version(void) { return 100; }
+extern "C" int dca_version(void) { return 101; }
+// 16-bit format of the cost planes and operand packs this build was compiled for: 1 = IEEE fp16 (default), 0 = bf16
+extern "C" int dca_plane_format(void) { return DCA_F16_PLANES ? 1 : 0; }

@@ -34,13 +34,7 @@ __device__ __forceinline__ void cp_async4(float* dst, const float* src, bool val
                : "memory");
 }
 
-__device__ __forceinline__ void vol_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  const float2 hf = __bfloat1622float2(h);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
+__device__ __forceinline__ void vol_split2(float a, float b, uint32_t& hi, uint32_t& lo) { split_pair(a, b, hi, lo); }
 
 // CVT = compile-time channel pitch of the volume (64 for DCANet's 40 groups + 2x12 concat); 0 = runtime Cv.
 // GT / CPGT = compile-time group count / channels per group (40 / 8 for DCANet); 0 = runtime.  With them fixed
@@ -196,13 +190,7 @@ volume_fused_kernel(const float* __restrict__ gl, const float* __restrict__ gr,
 // =====================================================================================================
 constexpr int V2_TW = 16, V2_DC = 48, V2_UW = 64;    // columns / disparities per item, right window (incl. 1 spare column)
 
-// packed bf16x2 split with plain bit operations for the hi -> fp32 expansion (shift / mask instead of PRMT pairs)
-__device__ __forceinline__ void vol_split2b(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);          // a -> low half, b -> high half
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
+__device__ __forceinline__ void vol_split2b(float a, float b, uint32_t& hi, uint32_t& lo) { split_pair(a, b, hi, lo); }
 
 // Persistent CTAs (one per SM, 12 warps), TMA-staged and double buffered:
 //   * the transposition to [c][u/8][slot][8] is done by the TMA unit: the fp32 NCHW feature map is described as a 5-D

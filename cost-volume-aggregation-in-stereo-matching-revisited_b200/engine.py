@@ -4,8 +4,8 @@ torch is used for device memory (torch.empty on the current device), the current
 nothing else: every arithmetic step below is a call into libdca_b200.so.  No ATen compute op, no
 cuDNN/cuBLAS, no CPU fallback.
 
-Data layout in HBM ("cost planes"): channels-last bf16 `[planes][B][D][H][W][C]`;
-planes=2 ("parity": hi + lo bf16, ~16-bit significand) or planes=1 ("fast": plain bf16).
+Data layout in HBM ("cost planes"): channels-last 16-bit `[planes][B][D][H][W][C]` (fp16 by default, see plane_dtype());
+planes=2 ("parity": hi + lo, 22-bit significand) or planes=1 ("fast": a single 16-bit plane).
 """
 from __future__ import annotations
 
@@ -16,6 +16,11 @@ from . import _lib
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 K3S1, K3S2, T3S2, K1, C2D3 = 0, 1, 2, 3, 4
 BN_EPS = 1e-5
+
+
+def plane_dtype():
+    """torch dtype of the 16-bit cost planes of the loaded library (fp16 by default, bf16 if built with DCA_F16_PLANES=0)."""
+    return torch.float16 if _lib.load().dca_plane_format() == 1 else torch.bfloat16
 
 
 def _ptr(t):
@@ -38,7 +43,7 @@ class Planes:
 
     def __init__(self, B, D, H, W, C, planes, device, t=None):
         self.B, self.D, self.H, self.W, self.C, self.planes = B, D, H, W, C, planes
-        self.t = t if t is not None else torch.empty((planes, B, D, H, W, C), dtype=torch.bfloat16, device=device)
+        self.t = t if t is not None else torch.empty((planes, B, D, H, W, C), dtype=plane_dtype(), device=device)
 
     @property
     def ptr(self):

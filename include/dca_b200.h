@@ -36,6 +36,9 @@ extern "C" {
 #define DCA_CONV_2D3 4   /* Conv2d 3x3 s1 p1, Di==1  (gwcnet_dca_g.py:112-115) */
 
 int dca_version(void);
+/* 16-bit element format of the cost planes / tensor-core operand packs of this build: 1 = IEEE fp16 (default; hi + lo
+ * = 22 significand bits), 0 = bf16 (compile with -DDCA_F16_PLANES=0; 16 bits, 8 more exponent bits). */
+int dca_plane_format(void);
 
 /* (1) volume construction -------------------------------------------------------------------- */
 /* Fused replacement of build_gwc_volume (submodule.py:157-167) + build_concat_volume (:134-145)

@@ -49,17 +49,24 @@ def round_mantissa(x: torch.Tensor, bits: Optional[int]) -> torch.Tensor:
         return x
     if bits == 7:
         return x.to(torch.bfloat16).to(torch.float32)
+    if bits == 10:      # IEEE fp16 (the default 16-bit plane format of the CUDA path), including its exponent range
+        return x.to(torch.float16).to(torch.float32)
     drop = 23 - bits
     i = x.contiguous().view(torch.int32)
     bias = ((i >> drop) & 1) + ((1 << (drop - 1)) - 1)
     return (((i + bias) >> drop) << drop).view(torch.float32)
 
 
-def split_bf16(x: torch.Tensor):
-    """hi = bf16(x), lo = bf16(x - hi): what the CUDA path stores for every activation/weight."""
-    hi = x.to(torch.bfloat16)
-    lo = (x - hi.to(torch.float32)).to(torch.bfloat16)
+def split_h16(x: torch.Tensor, dtype=torch.float16):
+    """hi = h16(x), lo = h16(x - hi): what the CUDA path stores for every activation/weight (fp16 planes by default,
+    bf16 when the library is built with DCA_F16_PLANES=0)."""
+    hi = x.to(dtype)
+    lo = (x - hi.to(torch.float32)).to(dtype)
     return hi, lo
+
+
+def split_bf16(x: torch.Tensor):
+    return split_h16(x, torch.bfloat16)
 
 
 # --------------------------------------------------------------------------------------------

@@ -93,12 +93,12 @@ def test_conv_family_direct(mode, ci, co, shape, planes):
         conv = torch.nn.Conv3d(ci, co, k, stride=s, padding=k // 2, bias=False)
     xin = x
     if planes == 1:   # compare like with like: fast mode sees bf16-rounded activations
-        xin = x.to(torch.bfloat16).float()
+        xin = x.to(E.plane_dtype()).float()
     with torch.no_grad():
         ref0 = bn(conv(xin))
     res1, res2 = rnd(*ref0.shape, seed=7), rnd(*ref0.shape, seed=8)
     if planes == 1:
-        res1, res2 = res1.to(torch.bfloat16).float(), res2.to(torch.bfloat16).float()
+        res1, res2 = res1.to(E.plane_dtype()).float(), res2.to(E.plane_dtype()).float()
     ref = F.relu(ref0 + res1) + res2
     emode = {"k3s1": E.K3S1, "k3s2": E.K3S2, "t3s2": E.T3S2, "k1": E.K1}[mode]
     pc = E.PackedConv(conv.weight.cuda(), bn.cuda(), transposed=(mode == "t3s2"))
@@ -128,14 +128,14 @@ def test_conv_family_tcgen05(mode, ci, co, shape, planes):
     w = conv.weight.data
     xin = x
     if planes == 1:   # fast mode: bf16 operands on both sides
-        xin = x.to(torch.bfloat16).float()
-        conv.weight.data = w.to(torch.bfloat16).float()
+        xin = x.to(E.plane_dtype()).float()
+        conv.weight.data = w.to(E.plane_dtype()).float()
     with torch.no_grad():
         ref0 = bn(conv(xin))
     conv.weight.data = w
     res1, res2 = rnd(*ref0.shape, seed=27), rnd(*ref0.shape, seed=28)
     if planes == 1:
-        res1, res2 = res1.to(torch.bfloat16).float(), res2.to(torch.bfloat16).float()
+        res1, res2 = res1.to(E.plane_dtype()).float(), res2.to(E.plane_dtype()).float()
     ref = F.relu(ref0 + res1) + res2
     emode = {"k3s1": E.K3S1, "k3s2": E.K3S2, "t3s2": E.T3S2, "k1": E.K1}[mode]
     pc = E.PackedConv(conv.weight.cuda(), bn.cuda(), transposed=(mode == "t3s2"))
@@ -186,14 +186,14 @@ def test_conv_marching_kernel(ci, shape, planes):
     w = conv.weight.data
     xin = x
     if planes == 1:
-        xin = x.to(torch.bfloat16).float()
-        conv.weight.data = w.to(torch.bfloat16).float()
+        xin = x.to(E.plane_dtype()).float()
+        conv.weight.data = w.to(E.plane_dtype()).float()
     with torch.no_grad():
         ref0 = bn(conv(xin))
     conv.weight.data = w
     res1, res2 = rnd(*ref0.shape, seed=37), rnd(*ref0.shape, seed=38)
     if planes == 1:
-        res1, res2 = res1.to(torch.bfloat16).float(), res2.to(torch.bfloat16).float()
+        res1, res2 = res1.to(E.plane_dtype()).float(), res2.to(E.plane_dtype()).float()
     ref = F.relu(ref0 + res1) + res2
     pc = E.PackedConv(conv.weight.cuda(), bn.cuda())
     assert pc.pack_tc(planes) and pc.w_march is not None
@@ -221,12 +221,12 @@ def test_prop_convs_on_tcgen05(planes):
     gin = g
     w1, w2 = c1.weight.data.clone(), c2.weight.data.clone()
     if planes == 1:
-        gin = g.to(torch.bfloat16).float()
-        c1.weight.data, c2.weight.data = w1.to(torch.bfloat16).float(), w2.to(torch.bfloat16).float()
+        gin = g.to(E.plane_dtype()).float()
+        c1.weight.data, c2.weight.data = w1.to(E.plane_dtype()).float(), w2.to(E.plane_dtype()).float()
     with torch.no_grad():
         mid = F.relu(bn(c1(gin)))
         if planes == 1:
-            mid = mid.to(torch.bfloat16).float()
+            mid = mid.to(E.plane_dtype()).float()
         ref = c2(mid)
     c1.weight.data, c2.weight.data = w1, w2
     gp = E.Planes.from_ncdhw(g.cuda(), planes)
@@ -243,7 +243,7 @@ def test_avgpool_and_planes_roundtrip():
     xp = E.Planes.from_ncdhw(x.cuda(), 2)
     close(xp.to_ncdhw(), x, 2e-5, "roundtrip")
     close(E.avgpool(xp).to_ncdhw(), F.avg_pool3d(x, 3, 2, 1), 3e-5, "avgpool")
-    close(E.Planes.from_ncdhw(x.cuda(), 1).to_ncdhw(), x.to(torch.bfloat16).float(), 1e-7, "bf16 roundtrip")
+    close(E.Planes.from_ncdhw(x.cuda(), 1).to_ncdhw(), x.to(E.plane_dtype()).float(), 1e-7, "16-bit roundtrip")
 
 
 def test_class_stats_exact_mask():
