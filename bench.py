@@ -277,7 +277,7 @@ def main():
                     "peak_source": f"{src} (bf16 sustained; burst {tf_burst})", "ms_per_launch": conv_ms,
                     "algorithmic_flops_per_launch": fl,
                     "issued_tflops": ach * issued,
-                    "note": ("parity precision issues 3 bf16 MMAs per algorithmic MAC (hi*Whi, hi*Wlo, lo*Whi); "
+                    "note": ("parity precision issues 3 16-bit (kind::f16, same rate as bf16) MMAs per algorithmic MAC (hi*Whi, hi*Wlo, lo*Whi); "
                              "`achieved` counts algorithmic FLOPs only") if issued > 1 else "",
                     "ncu": tr}
             # volume kernel (HBM bound)
@@ -310,8 +310,8 @@ def main():
         line = {"metric": METRIC, "value": pairs / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
                 "warmup": Wm, "ms_per_step": total_ms / K, "p50_ms_per_pair": statistics.median(step_ms) / B,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16x2 split operands (hi+lo), fp32 accumulate" if args.precision == "parity"
-                else "bf16 operands, fp32 accumulate",
+                "dtype": "f16x2 split operands (hi+lo fp16 planes, 22-bit significand), fp32 accumulate" if args.precision == "parity"
+                else "f16 operands, fp32 accumulate",
                 "data": "synthetic",
                 "config": {"workload": args.config, "H": H, "W": W, "maxdisp": maxdisp, "batch_per_gpu": B,
                            "groups": 40, "precision": args.precision, "parallelism": f"pairs sharded over {world} GPU(s), no collective",

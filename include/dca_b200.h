@@ -10,8 +10,9 @@
  *   - returns DCA_OK (0) or a negative error code.
  * The caller (Python via ctypes) owns all buffers.
  *
- * "cost planes" = channels-last bf16 tensor [planes][B][D][H][W][C]; plane 0 = bf16(x),
- * plane 1 = bf16(x - plane0) (only when planes == 2, the parity precision mode).
+ * "cost planes" = channels-last 16-bit tensor [planes][B][D][H][W][C]; plane 0 = h16(x),
+ * plane 1 = h16(x - plane0) (only when planes == 2, the parity precision mode); h16 = IEEE fp16 unless the library
+ * was built with -DDCA_F16_PLANES=0 (bf16), see dca_plane_format().
  */
 #ifndef DCA_B200_H
 #define DCA_B200_H

@@ -63,11 +63,13 @@ def test_hot_path_config1_matches_oracle():
     assert float((pv2.cpu() - refpv).abs().max()) < 1e-2 * float(refpv.abs().max())
 
 
-def test_hot_path_kitti_full_size_matches_oracle():
+@pytest.mark.parametrize("seed", [2, 3])
+def test_hot_path_kitti_full_size_matches_oracle(seed):
     """BASELINE config[1] at FULL size (384x1248, maxdisp 192): the production call (no intermediate tensors kept)
-    against the oracle run live on the host CPU; same tolerance as config 1."""
+    against the oracle run live on the host CPU; same tolerance as config 1.  (Seed 3 is the input on which the bf16
+    planes / single-accumulator version of the kernels exceeded the per-pixel tolerance)"""
     import dcanet_b200 as d
-    O, feats, sd = _config1(H4=96, W4=312, maxdisp=192, seed=2)
+    O, feats, sd = _config1(H4=96, W4=312, maxdisp=192, seed=seed)
     with torch.no_grad():
         ref4, refpv = O.hot_path(sd, *feats, maxdisp=192)
     net = _load_into(d.GwcNet(192), sd).cuda().eval()
