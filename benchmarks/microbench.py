@@ -86,20 +86,6 @@ def main():
             print(json.dumps(conv_case(E.T3S2, 64, 32, q8, planes)), flush=True)
             print(json.dumps(conv_case(E.K1, 32, 32, q4, planes)), flush=True)
         print(json.dumps(conv_case(E.K3S1, 32, 32, q4, 2, tc=False)), flush=True)
-    if "tune" in args.what:
-        for planes in (2, 1):
-            for ngrp, lo_sep in ((1, 0), (2, 0), (4, 0), (1, 1), (2, 1)):
-                if planes == 1 and lo_sep:
-                    continue
-                d._lib.call("dca_tc_set_tuning", ngrp, lo_sep)
-                for (ci, co, dims) in ((32, 32, q4), (64, 32, q4), (64, 64, q8)):
-                    try:
-                        r = conv_case(E.K3S1, ci, co, dims, planes, check=True)
-                    except Exception as ex:
-                        r = {"err": str(ex)[:80]}
-                    r.update(ngrp=ngrp, lo_sep=lo_sep)
-                    print(json.dumps(r), flush=True)
-        d._lib.call("dca_tc_set_tuning", 1, 0)
     if "dbg" in args.what:
         for planes in (2, 1):
             for dbg in (0, 1, 2, 3):

@@ -66,9 +66,6 @@ struct TcParams {
   int linear;                      // 1x1x1 convs: tiles are 128 CONSECUTIVE voxels (8 KB bursts); rB/rD/rH/rW = real dims
   int rB, rD, rH, rW;
   int dbg;       // diagnostics: bit0 = skip epilogue stores, bit1 = skip MMAs (timing experiments only)
-  int npart;     // accumulator column blocks (each Cout wide) the epilogue sums
-  int ngrp;      // halo kernel: taps are interleaved over ngrp independent accumulator groups
-  int lo_sep;    // halo kernel, parity: lo*Whi goes to its own column block
 };
 
 static inline void fill_recips(TcParams& p) {
@@ -1428,7 +1425,6 @@ static bool make_w_map(CUtensorMap* m, const void* base, int Cin, int rows, int 
 
 static int g_use_halo = 1;
 static int g_use_s2slab = 1;
-static int g_ngrp = 1, g_lo_sep = 0;
 static int g_dbg = 0;
 
 template <int CIN, int COUT, int PLANES>
@@ -1558,7 +1554,7 @@ extern "C" int dca_up2_tc(int kind, const void* x, int planes, const void* side,
   p.res_post = (const __nv_bfloat16*)res_post;
   p.res_plane = (size_t)B * Do * Ho * Wo * Cout; p.planes_res = planes_res;
   p.y = (__nv_bfloat16*)y; p.y_plane = p.res_plane; p.planes_out = P; p.act = act;
-  p.npart = P; p.ngrp = 1; p.dbg = g_dbg;
+  p.dbg = g_dbg;
   p.ldc = Cout; p.cout_valid = Cout;
   p.Dt = Dl; p.Ht = Hl; p.Wt = Wl; p.out_stride = 2; p.ncls = (kind == 2) ? 4 : 8; p.cls_inner = 1;
   if (kind == 2) p.out_stride_d = 1;
@@ -1661,10 +1657,11 @@ extern "C" int dca_up2_tc(int kind, const void* x, int planes, const void* side,
 // 1 = halo-slab main loop for k3 s1 (default), 0 = one TMA box per tap (v1)
 extern "C" int dca_tc_set_halo(int on) { g_use_halo = on & 1; g_use_s2slab = (on & 2) ? 0 : 1; return DCA_OK; }
 // accumulator interleave (1,2,4) and separate lo block (0/1) of the halo kernel
-extern "C" int dca_tc_set_tuning(int ngrp, int lo_sep) {
-  if (ngrp != 1 && ngrp != 2 && ngrp != 4) return DCA_ERR_ARG;
-  g_ngrp = ngrp; g_lo_sep = lo_sep ? 1 : 0;
-  g_dbg = lo_sep >> 4;   // timing experiments: (lo_sep >> 4) & 1 skip stores, & 2 skip MMAs
+// timing probes of the tcgen05 kernels: (flags >> 4) & 1 skips the epilogue math + stores, & 2 the MMAs of the halo kernel
+// (the first argument is reserved and must be 1)
+extern "C" int dca_tc_set_tuning(int reserved, int flags) {
+  if (reserved != 1) return DCA_ERR_ARG;
+  g_dbg = (flags >> 4) & 3;
   return DCA_OK;
 }
 
@@ -1710,7 +1707,7 @@ extern "C" int dca_conv3d_tc(int mode, const void* x, int planes_in, const void*
   p.res_pre = (const __nv_bfloat16*)res_pre; p.res_post = (const __nv_bfloat16*)res_post;
   p.res_plane = (size_t)B * Do * Ho * Wo * Cout; p.planes_res = planes_res;
   p.y = (__nv_bfloat16*)y; p.y_plane = p.res_plane; p.planes_out = planes_out; p.act = act;
-  p.npart = P; p.ngrp = 1; p.lo_sep = 0; p.dbg = g_dbg;
+  p.dbg = g_dbg;
   p.up = (const __nv_bfloat16*)up; p.planes_up = planes_up;
   p.nslab = 3; p.slab_dz[0] = -1; p.slab_dz[1] = 0; p.slab_dz[2] = 1;
   p.ldc = Cout; p.cout_valid = Cout;
@@ -1886,7 +1883,7 @@ extern "C" int dca_conv2d_tc(const void* x, int planes, const void* w_tc2d, cons
     p.B = B; p.Do = 1; p.Ho = H; p.Wo = W;
     p.scale = scale ? scale + j * 64 : nullptr; p.shift = shift ? shift + j * 64 : nullptr;
     p.y = (__nv_bfloat16*)y; p.y_plane = (size_t)B * H * W * Cout; p.res_plane = p.y_plane; p.planes_res = 1;
-    p.planes_out = P; p.act = act; p.npart = P; p.ngrp = 1; p.dbg = g_dbg;
+    p.planes_out = P; p.act = act; p.dbg = g_dbg;
     p.ldc = Cout; p.co_base = j * 64; p.cout_valid = Cout; p.out_f32 = out_f32;
     p.nslab = nslab; p.slab_c0[0] = 0; p.slab_c0[1] = 64; p.slab_dz[0] = p.slab_dz[1] = 0;
     p.Dt = 1; p.Ht = H; p.Wt = W; p.out_stride = 1; p.ntaps = 9 * nslab; p.ncls = 1;
@@ -1920,7 +1917,7 @@ extern "C" int dca_conv1_taps_tc(const void* x, int planes, const void* w_tc, fl
   for (int i = 1; i < 9; ++i) maps.a[i] = maps.a[0];
   if (!make_w_map(&maps.w, w_tc, Cin, Pn * Cout, Pn * Cout)) return DCA_ERR_LAUNCH;
   p.B = 1; p.Do = 1; p.Ho = rows; p.Wo = 8;
-  p.y = (__nv_bfloat16*)P; p.planes_out = Pn; p.act = 0; p.npart = Pn; p.ngrp = 1; p.dbg = g_dbg;
+  p.y = (__nv_bfloat16*)P; p.planes_out = Pn; p.act = 0; p.dbg = g_dbg;
   p.ldc = Cout; p.cout_valid = ntap; p.out_f32 = 2;
   p.nslab = 3;
   p.Dt = 1; p.Ht = rows; p.Wt = 8; p.out_stride = 1; p.ncls = 1;
@@ -1960,7 +1957,7 @@ extern "C" int dca_conv3d_tc_march(const void* x, int planes, const void* w_marc
   p.res_pre = (const __nv_bfloat16*)res_pre; p.res_post = (const __nv_bfloat16*)res_post;
   p.res_plane = (size_t)B * D * H * W * Cout; p.planes_res = planes_res;
   p.y = (__nv_bfloat16*)y; p.y_plane = p.res_plane; p.planes_out = P; p.act = act;
-  p.npart = 1; p.ngrp = 1; p.dbg = g_dbg;
+  p.dbg = g_dbg;
   p.ldc = Cout; p.cout_valid = Cout;
   const int nmax = P == 2 ? 8 : 16;            // planes per work item (TMEM: 512 columns)
   const int n = D < nmax ? D : nmax;

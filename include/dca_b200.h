@@ -116,8 +116,9 @@ int dca_tc_set_halo(int on);
 int dca_volume_set_v2(int on);
 /* 1 (default): dca_disp_attention runs two warps per pixel when D/8 == 24; 0: one warp per pixel (A/B timing). */
 int dca_attention_set_team(int on);
-/* halo kernel tuning: taps interleaved over ngrp (1,2,4) independent TMEM accumulator groups; lo_sep = own block for lo*Whi. */
-int dca_tc_set_tuning(int ngrp, int lo_sep);
+/* timing probes of the tcgen05 kernels: (flags >> 4) & 1 skips the epilogue math + stores, & 2 the MMAs of the halo
+ * kernel; `reserved` must be 1. */
+int dca_tc_set_tuning(int reserved, int flags);
 
 /* (2) DCA module ------------------------------------------------------------------------------- */
 int dca_avgpool3d(const void* x, void* y, int planes, int B, int C, int Di, int Hi, int Wi, void* stream);
