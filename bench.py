@@ -68,7 +68,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in line.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.03)
 
     def summary(self):
         sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
