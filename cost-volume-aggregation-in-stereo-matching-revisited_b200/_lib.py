@@ -39,6 +39,7 @@ SIGNATURES = {
     "dca_volume_set_v2": [_c_int],
     "dca_attention_set_team": [_c_int],
     "dca_tc_set_tuning": [_c_int, _c_int],
+    "dca_tc_set_trunc_comp": [_f],
     "dca_avgpool3d": [_vp, _vp] + [_c_int] * 6 + [_vp],
     "dca_class_stats": [_vp, _vp, _vp, _vp] + [_c_int] * 4 + [_vp],
     "dca_disp_attention": [_vp, _vp, _vp, _vp, _vp, _c_int, _vp] + [_c_int] * 7 + [_vp],

@@ -63,6 +63,7 @@ struct TcParams {
   float inv_tiles_w, inv_tiles_h, inv_Dt, inv_ncls;   // reciprocals for the epilogue's tile decode (fast_divmod)
   int march_n;                     // > 0: depth-marching kernel, a work item = march_n consecutive output planes
   int cls_inner;                   // epilogue/work order: CTA owns whole tiles, classes inside (up2 kernel)
+  float cls_comp[8];               // per class: 1 + kappa * (MMA steps accumulated into the main block), see fill_comp()
   int linear;                      // 1x1x1 convs: tiles are 128 CONSECUTIVE voxels (8 KB bursts); rB/rD/rH/rW = real dims
   int rB, rD, rH, rW;
   int dbg;       // diagnostics: bit0 = skip epilogue stores, bit1 = skip MMAs (timing experiments only)
@@ -75,6 +76,13 @@ static inline void fill_recips(TcParams& p) {
   const int nc = p.march_n > 0 ? p.march_n : (p.ncls > 0 ? p.ncls : 1);
   p.inv_ncls = 1.0f / (float)nc;
 }
+
+// The tensor core truncates its fp32 accumulator toward zero at every MMA: a conv output comes out smaller by a
+// systematic kappa = 1.56e-8 (relative) per accumulation step of its main column block (measured on B200 with
+// benchmarks/tc_bias_probe.py: -8.5e-7 after 54 steps, -1.66e-6 after 108; the correction block is 2^-11 smaller and
+// needs nothing).  The epilogue multiplies the main block by 1 + kappa * steps.  dca_tc_set_trunc_comp(0) disables it.
+static float g_trunc_kappa = 1.56e-8f;
+static inline void fill_comp(TcParams& p, int cls, int steps) { p.cls_comp[cls] = 1.0f + g_trunc_kappa * (float)steps; }
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -328,6 +336,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
     if (mn) mbar_wait(&tfull[mj], (uint32_t)(mwi & 1));
     else mbar_wait(&tfull[acc], (it >> 1) & 1);
     tc_fence_after();
+    const float comp = p.cls_comp[cls];      // undo the accumulator's truncation shrink of the main block
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * 16 +
                            (mn ? (uint32_t)(32 * (mn - 1 - mj)) : acc * (uint32_t)(PLANES * COUT));
 #pragma unroll 1
@@ -340,11 +349,11 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
         tmem_ld16(taddr + (mn ? (uint32_t)MARCH_CORR : (uint32_t)COUT) + c0, rl);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rh[j]) + __uint_as_float(rl[j]);
+        for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(rh[j]), comp, __uint_as_float(rl[j]));
       } else {
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rh[j]);
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rh[j]) * comp;
       }
       if (c0 + 32 >= COUT && !mn) {    // all TMEM reads of this tile are done: hand the buffer back
         tc_fence_before();
@@ -1358,6 +1367,7 @@ static int launch_tc_march(const TcMaps& maps, const TcParams& p, cudaStream_t s
   const int total = p.B * p.Dt * p.tiles_h * p.tiles_w;
   const int grid = total < g_num_sms ? total : g_num_sms;
   TcParams q = p; fill_recips(q);
+  for (int c = 0; c < 8; ++c) fill_comp(q, c, 27 * (CIN / 16));
   conv_tc_march_kernel<CIN, PLANES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, q);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
@@ -1442,6 +1452,8 @@ static int launch_tc(const TcMaps& maps, const TcParams& p, cudaStream_t st) {
   const int total = p.B * p.Dt * p.tiles_h * p.tiles_w * p.ncls;
   const int grid = total < g_num_sms ? total : g_num_sms;
   TcParams q = p; fill_recips(q);
+  for (int c = 0; c < 8; ++c)
+    fill_comp(q, c, (c < q.ncls ? (int)q.cls_tap0[c + 1] - (int)q.cls_tap0[c] : 0) * (CIN / 16));
   conv_tc_kernel<CIN, COUT, PLANES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, q);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
@@ -1461,6 +1473,7 @@ static int launch_tc_s2slab(const TcMaps& maps, const TcParams& p, cudaStream_t 
   const int total = p.B * p.Dt * p.tiles_h * p.tiles_w;
   const int grid = total < g_num_sms ? total : g_num_sms;
   TcParams q = p; fill_recips(q);
+  for (int c = 0; c < 8; ++c) fill_comp(q, c, 27 * 2);
   conv_tc_s2slab_kernel<PLANES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, q);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
@@ -1482,6 +1495,7 @@ static int launch_tc_halo(const TcMaps& maps, const TcParams& p, cudaStream_t st
   const int total = p.B * p.Dt * p.tiles_h * p.tiles_w;
   const int grid = total < g_num_sms ? total : g_num_sms;
   TcParams q = p; fill_recips(q);
+  for (int c = 0; c < 8; ++c) fill_comp(q, c, q.nslab * 9 * (CIN / 16));
   conv_tc_halo_kernel<CIN, COUT, PLANES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, q);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
@@ -1519,6 +1533,8 @@ static int launch_up2(const TcMaps& maps, const TcParams& p, const Up2Params& u,
   const int total = p.B * p.Dt * p.tiles_h * p.tiles_w;
   const int grid = total < g_num_sms ? total : g_num_sms;
   TcParams q = p; fill_recips(q);
+  for (int c = 0; c < 8; ++c)
+    fill_comp(q, c, (c < q.ncls ? (int)u.cls_tap0[c + 1] - (int)u.cls_tap0[c] : 0) * (CIN / 16) + (u.has_side ? 2 : 0));
   conv_tc_up2_kernel<CIN, PLANES, NSLAB><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, q, u);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
@@ -1655,6 +1671,9 @@ extern "C" int dca_up2_tc(int kind, const void* x, int planes, const void* side,
 }
 
 // 1 = halo-slab main loop for k3 s1 (default), 0 = one TMA box per tap (v1)
+// kappa of the accumulator-truncation compensation (default 1.56e-8 per MMA step; 0 = off)
+extern "C" int dca_tc_set_trunc_comp(float kappa) { g_trunc_kappa = kappa; return DCA_OK; }
+
 extern "C" int dca_tc_set_halo(int on) { g_use_halo = on & 1; g_use_s2slab = (on & 2) ? 0 : 1; return DCA_OK; }
 // accumulator interleave (1,2,4) and separate lo block (0/1) of the halo kernel
 // timing probes of the tcgen05 kernels: (flags >> 4) & 1 skips the epilogue math + stores, & 2 the MMAs of the halo kernel

@@ -137,6 +137,7 @@ class Options:
     cout1_on_tc = True            # 32->1 convs: tensor-core per-tap GEMM + shifted sum instead of the CUDA-core kernel
     prop_on_tc = True             # the two 3x3 Conv2d of PropgationNet_4x on the halo-slab tcgen05 kernel
     up2_bilinear = True           # fuse stage: depth interpolation in the attention store, bilinear 4-class GEMM
+    fp32_stages = frozenset()     # diagnostics: stages whose convs run on the fp32 CUDA-core kernel: {'dres', 'cva', 'cls3'}
     use_up2 = True                # class-wise halo-slab kernel for the transposed conv and the trilinear fuse stage
 
 
@@ -526,19 +527,24 @@ def hot_path_forward(pk: PackedHotPath, gwc_l, gwc_r, cat_l, cat_r, g, keep=None
     D4 = pk.maxdisp // 4
     vol = fused_volume(_f32c(gwc_l), _f32c(gwc_r), _f32c(cat_l) if cat_l is not None else None,
                        _f32c(cat_r) if cat_r is not None else None, D4, pk.num_groups, P)
+    tc0 = Options.use_tc
+    Options.use_tc = tc0 and "dres" not in Options.fp32_stages
     c = conv(vol, pk.dres0_0, K3S1, ACT_RELU)
     c = conv(c, pk.dres0_2, K3S1, ACT_RELU)
     r = conv(c, pk.dres1_0, K3S1, ACT_RELU)
     cost0 = conv(r, pk.dres1_2, K3S1, ACT_NONE, res_post=c)
+    Options.use_tc = tc0 and "cva" not in Options.fp32_stages
     k1 = {} if keep is not None else None
     k2 = {} if keep is not None else None
     k3 = {} if keep is not None else None
     _, out1 = cva_forward(pk.cva[0], cost0, res_post=cost0, keep=k1)
     logits2, out2 = cva_forward(pk.cva[1], out1, keep=k2)
     _, out3 = cva_forward(pk.cva[2], out2, keep=k3)
+    Options.use_tc = tc0 and "cls3" not in Options.fp32_stages
     h = conv(out3, pk.cls3_0, K3S1, ACT_RELU)
     logits = conv_cout1_any(h, pk.cls3_2)
     pred_q = softmax_regress(logits)
+    Options.use_tc = tc0
     gp = Planes.from_ncdhw(_f32c(g), planes=P)
     if Options.use_tc and Options.prop_on_tc:
         m1 = conv2d_tc(gp, pk.prop0_tc, ACT_RELU)

@@ -119,6 +119,10 @@ int dca_attention_set_team(int on);
 /* timing probes of the tcgen05 kernels: (flags >> 4) & 1 skips the epilogue math + stores, & 2 the MMAs of the halo
  * kernel; `reserved` must be 1. */
 int dca_tc_set_tuning(int reserved, int flags);
+/* The tensor core truncates its fp32 accumulator toward zero at every MMA (measured: a systematic -1.56e-8 relative per
+ * accumulation step).  The tcgen05 conv epilogues multiply the main accumulator block by 1 + kappa * steps; this sets
+ * kappa (default 1.56e-8f, 0 = off). */
+int dca_tc_set_trunc_comp(float kappa);
 
 /* (2) DCA module ------------------------------------------------------------------------------- */
 int dca_avgpool3d(const void* x, void* y, int planes, int B, int C, int Di, int Hi, int Wi, void* stream);
