@@ -137,6 +137,7 @@ class Options:
     cout1_on_tc = True            # 32->1 convs: tensor-core per-tap GEMM + shifted sum instead of the CUDA-core kernel
     prop_on_tc = True             # the two 3x3 Conv2d of PropgationNet_4x on the halo-slab tcgen05 kernel
     up2_bilinear = True           # fuse stage: depth interpolation in the attention store, bilinear 4-class GEMM
+    prop_side_stream = True       # guidance branch of PropgationNet_4x (independent of the cost volume) on a second stream
     fp32_stages = frozenset()     # diagnostics: stages whose convs run on the fp32 CUDA-core kernel: {'dres', 'cva', 'cls3'}
     use_up2 = True                # class-wise halo-slab kernel for the transposed conv and the trilinear fuse stage
 
@@ -519,12 +520,53 @@ class PackedHotPath:
             pc.pack_tc(planes)
 
 
+_SIDE_STREAMS = {}
+
+
+def _prop_mask(pk, g, P):
+    """PropgationNet_4x.conv on the guidance features (gwcnet_dca_g.py:112-115,119): fp32 channels-last mask logits."""
+    gp = Planes.from_ncdhw(g, planes=P)
+    if Options.use_tc and Options.prop_on_tc:
+        m1 = conv2d_tc(gp, pk.prop0_tc, ACT_RELU)
+        return conv2d_tc(m1, pk.prop2_tc, ACT_NONE, out_fp32=True)
+    m1 = conv(gp, pk.prop0, C2D3, ACT_RELU)
+    return conv(m1, pk.prop2, C2D3, ACT_NONE, out_fp32=True)
+
+
+def _prop_mask_start(pk, g, P):
+    """The mask branch only depends on the guidance features, so it is issued on a second stream at the start of the
+    forward: its 5 short launches (234 tiles each) fill SMs that the cost-volume kernels leave idle at their tails."""
+    if not Options.prop_side_stream:
+        return (None, pk, g, P)
+    main = torch.cuda.current_stream()
+    dev = g.device.index
+    side = _SIDE_STREAMS.get(dev)
+    if side is None:
+        side = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=g.device)
+    side.wait_stream(main)                 # g (and the previous forward) are ready
+    g.record_stream(side)
+    with torch.cuda.stream(side):
+        mask = _prop_mask(pk, g, P)
+    return (side, mask, main, None)
+
+
+def _prop_mask_wait(job):
+    if job[0] is None:
+        _, pk, g, P = job
+        return _prop_mask(pk, g, P)
+    side, mask, main, _ = job
+    main.wait_stream(side)
+    mask.record_stream(main)
+    return mask
+
+
 def hot_path_forward(pk: PackedHotPath, gwc_l, gwc_r, cat_l, cat_r, g, keep=None):
     """Feature maps -> (pred4 [B,1,H,W], prob_volume2 logits [B,D8,H8,W8]).
     Mirrors GwcNet.forward (eval) of the reference, models/gwcnet_dca_g.py:216-240,282."""
     _require_cuda(gwc_l, gwc_r, cat_l, cat_r, g)
     P = pk.planes
     D4 = pk.maxdisp // 4
+    side_job = _prop_mask_start(pk, _f32c(g), P)
     vol = fused_volume(_f32c(gwc_l), _f32c(gwc_r), _f32c(cat_l) if cat_l is not None else None,
                        _f32c(cat_r) if cat_r is not None else None, D4, pk.num_groups, P)
     tc0 = Options.use_tc
@@ -545,13 +587,7 @@ def hot_path_forward(pk: PackedHotPath, gwc_l, gwc_r, cat_l, cat_r, g, keep=None
     logits = conv_cout1_any(h, pk.cls3_2)
     pred_q = softmax_regress(logits)
     Options.use_tc = tc0
-    gp = Planes.from_ncdhw(_f32c(g), planes=P)
-    if Options.use_tc and Options.prop_on_tc:
-        m1 = conv2d_tc(gp, pk.prop0_tc, ACT_RELU)
-        mask = conv2d_tc(m1, pk.prop2_tc, ACT_NONE, out_fp32=True)
-    else:
-        m1 = conv(gp, pk.prop0, C2D3, ACT_RELU)
-        mask = conv(m1, pk.prop2, C2D3, ACT_NONE, out_fp32=True)
+    mask = _prop_mask_wait(side_job)
     pred4 = convex_upsample(mask, pred_q)
     if keep is not None:
         keep.update(volume=vol, dres0=c, cost0=cost0, out1=out1, cva1=k1, cva2=k2, cva3=k3,
