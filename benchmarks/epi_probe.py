@@ -34,7 +34,7 @@ def main():
         "up2_deconv64+side+res": lambda: E.up2(0, x8, x4, w28, sc, sh, E.ACT_RELU, 64, 24, 48, 156, res_post=r4),
         "up2_bilinear_fuse": lambda: E.up2(2, t8, x4, w4, sc, sh, E.ACT_NONE, 32, 48, 48, 156),
     }
-    for dbg in (0, 1):
+    for dbg in (0, 1, 2, 3):
         d._lib.call("dca_tc_set_tuning", 1, dbg << 4)
         for k, fn in cases.items():
             print(json.dumps({"case": k, "dbg": dbg, "ms": round(timeit(fn, 20), 4)}), flush=True)

@@ -1083,7 +1083,7 @@ conv_tc_up2_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const 
             const uint64_t db0 = DD + ((w_u32 + (u.wres ? (uint32_t)tp.widx : sw) * Cfg::B_BYTES) >> 4);
 #pragma unroll
             for (int k = 0; k < CIN / 16; ++k) {
-              if (leader) {
+              if (leader && !(p.dbg & 2)) {
                 umma_bf16(d_addr, da0 + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc_full, (t > t0 || k > 0) ? 1u : 0u);
                 if (PLANES == 2)
                   umma_bf16(d_addr + COUT, da0 + (uint64_t)((Cfg::SLAB_PITCH >> 4) + k * 2), db0 + (uint64_t)(k * 2), idesc_half, 1u);
@@ -1105,7 +1105,7 @@ conv_tc_up2_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const 
             const uint64_t db0 = DD + ((w_u32 + (u.wres ? (uint32_t)u.side_widx : sw) * Cfg::B_BYTES) >> 4);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {                        // the side input has 32 channels
-              if (leader) {
+              if (leader && !(p.dbg & 2)) {
                 umma_bf16(d_addr, da0 + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc_full, (t1 > t0 || k > 0) ? 1u : 0u);
                 if (PLANES == 2)
                   umma_bf16(d_addr + COUT, da0 + (uint64_t)((Cfg::A_BYTES >> 4) + k * 2), db0 + (uint64_t)(k * 2), idesc_half, 1u);

@@ -117,7 +117,7 @@ int dca_volume_set_v2(int on);
 /* 1 (default): dca_disp_attention runs two warps per pixel when D/8 == 24; 0: one warp per pixel (A/B timing). */
 int dca_attention_set_team(int on);
 /* timing probes of the tcgen05 kernels: (flags >> 4) & 1 skips the epilogue math + stores, & 2 the MMAs of the halo
- * kernel; `reserved` must be 1. */
+ * and up2 kernels; `reserved` must be 1. */
 int dca_tc_set_tuning(int reserved, int flags);
 /* The tensor core truncates its fp32 accumulator toward zero at every MMA (measured: a systematic -1.56e-8 relative per
  * accumulation step).  The tcgen05 conv epilogues multiply the main accumulator block by 1 + kappa * steps; this sets
