@@ -141,6 +141,16 @@ __device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, uint32_t b
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ void at_split2(float a, float b, uint32_t& hi, uint32_t& lo) { split_pair(a, b, hi, lo); }
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t saddr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(saddr));
+}
+// m16n8k8: A = {a0 (rows 0-7), a1 (rows 8-15)}, B = {b0}
+__device__ __forceinline__ void mma_k8(float* c, uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32." DCA_MMA_TYPES ".f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(b0));
+}
 
 // src: bf16 pair [2][rows][AT_PITCH]; Wm: weight pair [2][32][AT_PITCH]; MT = number of 16-row tiles.
 // dst_pair != nullptr: result written as a bf16 pair (input of the next projection);
@@ -218,8 +228,11 @@ __device__ __forceinline__ void warp_project_mma(const __nv_bfloat16* __restrict
 // WPP = warps per pixel: 1 = a warp walks a pixel alone; 2 = a TEAM of two warps shares a pixel's buffers (each computes
 // 16 of the 32 projection rows, half of the attention items and half of the stores; phases are separated by a 64-thread
 // named barrier), which doubles the resident warps for the same shared memory: the kernel is latency bound.
-template <int PLANES, int MT, int DT, int WPP>
-__global__ void __launch_bounds__(256 * WPP)
+// CORE = 1 (team mode, D/8 == 24): the attention core itself also runs on mma.sync -- S = q k^T per head as m16n8k8
+// tiles (3 split terms), softmax on the accumulator fragments, P V as m16n8k16 tiles with P re-split to hi/lo in
+// registers -- instead of one fp32 FMA chain per (query, head) item with broadcast LDS.128 reads of k and v.
+template <int PLANES, int MT, int DT, int WPP, int CORE>
+__global__ void __launch_bounds__(CORE ? 576 : 256 * WPP)
 disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ cls, const float* __restrict__ e,
                       const float* __restrict__ S, const float* __restrict__ wts, int has_wa,
                       __nv_bfloat16* __restrict__ y, int B, int D, int H, int Wd, int pad) {
@@ -231,6 +244,8 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
   __nv_bfloat16* Wsm = reinterpret_cast<__nv_bfloat16*>(smem_at);               // [7][2][32][AT_PITCH]
   float* ss = reinterpret_cast<float*>(smem_at + AT_NMAT * 2 * AT_WPLANE * 2);   // 6 x (scale[32], shift[32])
   static_assert(WPP == 1 || (WPP == 2 && MT == 2 && DT > 0), "team mode: 32 rows, compile-time D");
+  static_assert(CORE == 0 || (WPP == 2 && DT == 24), "mma core: two warps x 16 query rows, 24 keys");
+  constexpr int TEAM_BYTES = CORE ? 4 * PAIR * 2 : 2 * PAIR * 2 + 3 * FBUF * 4;
   const int lane = threadIdx.x & 31;
   const int warps = (blockDim.x >> 5) / WPP, warp = (threadIdx.x >> 5) / WPP;    // teams per CTA, this warp's team
   const int wip = (threadIdx.x >> 5) % WPP;                                      // warp index inside the team
@@ -240,9 +255,13 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
     if (WPP == 1) __syncwarp();
     else asm volatile("bar.sync %0, %1;" ::"r"(1 + warp), "r"(32 * WPP) : "memory");
   };
-  uint8_t* wbase = smem_at + AT_NMAT * 2 * AT_WPLANE * 2 + 6 * 64 * 4 + (size_t)warp * (2 * PAIR * 2 + 3 * FBUF * 4);
+  uint8_t* wbase = smem_at + AT_NMAT * 2 * AT_WPLANE * 2 + 6 * 64 * 4 + (size_t)warp * TEAM_BYTES;
   __nv_bfloat16* P0 = reinterpret_cast<__nv_bfloat16*>(wbase);     // x, then key (row k_p rescaled in place), then ctx
   __nv_bfloat16* P2 = P0 + PAIR;                                   // intermediate of the two-layer projections
+  // CORE = 0: q, k, v as fp32 (F0, F1, F2).  CORE = 1: q, k as hi/lo pairs (Pq, Pk), v in P2 (free after the key
+  // projections); the fp32 result buffer F0 then aliases Pq, which is dead once the core is done.
+  __nv_bfloat16* Pq = P2 + PAIR;
+  __nv_bfloat16* Pk = Pq + PAIR;
   float* F0 = reinterpret_cast<float*>(P2 + PAIR);
   float* F1 = F0 + FBUF;
   float* F2 = F1 + FBUF;
@@ -256,7 +275,7 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
   }
   for (int i = threadIdx.x; i < 6 * 64; i += blockDim.x) ss[i] = __ldg(wts + AT_NMAT * AT_C * AT_C + i);
   // zero this warp's buffers once: rows [D, ROWS) are never loaded and must stay finite
-  for (int i = lane + 32 * wip; i < (2 * PAIR * 2 + 3 * FBUF * 4) / 4; i += 32 * WPP) reinterpret_cast<uint32_t*>(wbase)[i] = 0u;
+  for (int i = lane + 32 * wip; i < TEAM_BYTES / 4; i += 32 * WPP) reinterpret_cast<uint32_t*>(wbase)[i] = 0u;
   __syncthreads();
   const __nv_bfloat16* Wq0 = Wsm, *Wq1 = Wsm + 2 * AT_WPLANE, *Wk0 = Wsm + 4 * AT_WPLANE, *Wk1 = Wsm + 6 * AT_WPLANE,
                       *Wv = Wsm + 8 * AT_WPLANE, *Wo = Wsm + 10 * AT_WPLANE, *Wa = Wsm + 12 * AT_WPLANE;
@@ -282,7 +301,8 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
     team_sync();
     // (projections are row-wise: a warp only ever reads the rows it wrote itself, so no team barrier in between)
     warp_project_mma<MTW, ROWS>(P0, Wq0, ss + 0 * 64, true, P2, nullptr, lane, row0);
-    warp_project_mma<MTW, ROWS>(P2, Wq1, ss + 1 * 64, true, nullptr, F0, lane, row0);     // q  -> F0 (fp32)
+    if (CORE) warp_project_mma<MTW, ROWS>(P2, Wq1, ss + 1 * 64, true, Pq, nullptr, lane, row0);   // q -> Pq (hi/lo)
+    else warp_project_mma<MTW, ROWS>(P2, Wq1, ss + 1 * 64, true, nullptr, F0, lane, row0);        // q -> F0 (fp32)
     // key = x * (1 + [d == k_p] w_p): only row k_p differs from x, so it is rescaled (and re-split) in place by the warp
     // that owns the row; the query projections above were the last readers of the plain row
     if (kp >= row0 && kp < row0 + 16 * MTW && lane < 4) {
@@ -300,11 +320,87 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
     }
     __syncwarp();
     warp_project_mma<MTW, ROWS>(P0, Wk0, ss + 2 * 64, true, P2, nullptr, lane, row0);
-    warp_project_mma<MTW, ROWS>(P2, Wk1, ss + 3 * 64, true, nullptr, F1, lane, row0);     // k  -> F1
-    warp_project_mma<MTW, ROWS>(P0, Wv, ss + 4 * 64, true, nullptr, F2, lane, row0);      // v  -> F2
+    if (CORE) warp_project_mma<MTW, ROWS>(P2, Wk1, ss + 3 * 64, true, Pk, nullptr, lane, row0);   // k -> Pk
+    else warp_project_mma<MTW, ROWS>(P2, Wk1, ss + 3 * 64, true, nullptr, F1, lane, row0);        // k -> F1
+    if (CORE) warp_project_mma<MTW, ROWS>(P0, Wv, ss + 4 * 64, true, P2, nullptr, lane, row0);    // v -> P2
+    else warp_project_mma<MTW, ROWS>(P0, Wv, ss + 4 * 64, true, nullptr, F2, lane, row0);         // v -> F2
     team_sync();
     // ---- attention: item = (dq, head), 4 heads x D queries; a lane owns up to 2*MT items and walks the keys ONCE
     //      for all of them (independent online-softmax chains interleave -> ILP); ctx -> P0 as a bf16 pair ----
+    if (CORE) {
+      // ---- tensor-core attention core: this warp owns query rows [row0, row0 + 16); keys 0..23 = three n-tiles ----
+      const uint32_t s_q = (uint32_t)__cvta_generic_to_shared(Pq), s_k = (uint32_t)__cvta_generic_to_shared(Pk),
+                     s_v = (uint32_t)__cvta_generic_to_shared(P2);
+      constexpr uint32_t LO = (uint32_t)(ROWS * AT_PITCH * 2);       // byte offset of the lo plane
+      const int g = lane >> 2, t2 = (lane & 3) * 2;
+      const int mrow = lane & 7, mid = lane >> 3;                    // ldmatrix: lane -> (row in matrix, matrix index)
+#pragma unroll 1
+      for (int hd = 0; hd < 4; ++hd) {
+        // A = q[row0 + 0..15][hd*8 .. +8): matrices (hi rows 0-7, hi rows 8-15, lo rows 0-7, lo rows 8-15)
+        uint32_t qh0, qh1, ql0, ql1;
+        ldsm_x4(s_q + (uint32_t)(((row0 + (mid & 1) * 8 + mrow) * AT_PITCH + hd * 8) * 2) + (mid >> 1) * LO, qh0, qh1, ql0, ql1);
+        // B = k[key][hd*8 .. +8) for key blocks 0-7, 8-15, 16-23 (the 4th matrix, rows 24-31, is not used)
+        uint32_t kh[4], kl[4];
+        const uint32_t koff = (uint32_t)(((mid * 8 + mrow) * AT_PITCH + hd * 8) * 2);
+        ldsm_x4(s_k + koff, kh[0], kh[1], kh[2], kh[3]);
+        ldsm_x4(s_k + LO + koff, kl[0], kl[1], kl[2], kl[3]);
+        float sc[3][4];
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) {
+          sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+          mma_k8(sc[nt], qh0, qh1, kh[nt]);
+          mma_k8(sc[nt], qh0, qh1, kl[nt]);
+          mma_k8(sc[nt], ql0, ql1, kh[nt]);
+        }
+        // softmax over the 24 keys of rows g (values [nt][0..1]) and g + 8 ([nt][2..3]), log2 domain
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) sc[nt][i] *= qscale;
+          m0 = fmaxf(m0, fmaxf(sc[nt][0], sc[nt][1]));
+          m1 = fmaxf(m1, fmaxf(sc[nt][2], sc[nt][3]));
+        }
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        float l0 = 0.f, l1 = 0.f;
+        uint32_t ph[3][2], pl[3][2];                                 // P as packed hi / lo pairs: [n-tile][row g / g+8]
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) {
+          const float p0 = fast_exp2(sc[nt][0] - m0), p1 = fast_exp2(sc[nt][1] - m0);
+          const float p2 = fast_exp2(sc[nt][2] - m1), p3 = fast_exp2(sc[nt][3] - m1);
+          l0 += p0 + p1; l1 += p2 + p3;
+          at_split2(p0, p1, ph[nt][0], pl[nt][0]);
+          at_split2(p2, p3, ph[nt][1], pl[nt][1]);
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        // B = v^T: transposed 8x8 blocks of v[key][hd*8 .. +8) for key blocks 0-7, 8-15, 16-23, 24-31 (finite padding)
+        uint32_t vh[4], vl[4];
+        ldsm_x4_trans(s_v + koff, vh[0], vh[1], vh[2], vh[3]);
+        ldsm_x4_trans(s_v + LO + koff, vl[0], vl[1], vl[2], vl[3]);
+        float cx[4] = {0.f, 0.f, 0.f, 0.f};
+        {
+          const uint32_t a_hi[4] = {ph[0][0], ph[0][1], ph[1][0], ph[1][1]}, a_lo[4] = {pl[0][0], pl[0][1], pl[1][0], pl[1][1]};
+          mma_bf16(cx, a_hi, vh[0], vh[1]);
+          mma_bf16(cx, a_hi, vl[0], vl[1]);
+          mma_bf16(cx, a_lo, vh[0], vh[1]);
+          const uint32_t b_hi[4] = {ph[2][0], ph[2][1], 0u, 0u}, b_lo[4] = {pl[2][0], pl[2][1], 0u, 0u};
+          mma_bf16(cx, b_hi, vh[2], vh[3]);
+          mma_bf16(cx, b_hi, vl[2], vl[3]);
+          mma_bf16(cx, b_lo, vh[2], vh[3]);
+        }
+        const float i0 = 1.f / l0, i1 = 1.f / l1;
+        uint32_t h0, lo0, h1, lo1;
+        at_split2(cx[0] * i0, cx[1] * i0, h0, lo0);
+        at_split2(cx[2] * i1, cx[3] * i1, h1, lo1);
+        __nv_bfloat16* c0p = P0 + (row0 + g) * AT_PITCH + hd * 8 + t2;
+        *reinterpret_cast<uint32_t*>(c0p) = h0;
+        *reinterpret_cast<uint32_t*>(c0p + ROWS * AT_PITCH) = lo0;
+        *reinterpret_cast<uint32_t*>(c0p + 8 * AT_PITCH) = h1;
+        *reinterpret_cast<uint32_t*>(c0p + 8 * AT_PITCH + ROWS * AT_PITCH) = lo1;
+      }
+    } else
     if (DT > 0) {
       // scores of a lane's items stay in registers: pass 1 = all dot products + running max, pass 2 = exp2 and P.V
       constexpr int NI = (4 * (DT > 0 ? DT : 1) + 32 * WPP - 1) / (32 * WPP);
@@ -838,8 +934,8 @@ extern "C" int dca_class_stats(const float* logits, int* cls, float* e, float* S
 }
 
 static int g_attention_team = 1;
-// 1 (default): two warps per pixel for D/8 == 24; 0: one warp per pixel (A/B timing)
-extern "C" int dca_attention_set_team(int on) { g_attention_team = on ? 1 : 0; return DCA_OK; }
+// D/8 == 24: 1 (default) = two warps per pixel + mma.sync attention core, 2 = two warps + fp32 FMA core, 0 = one warp
+extern "C" int dca_attention_set_team(int on) { g_attention_team = on; return DCA_OK; }
 
 extern "C" int dca_disp_attention(const void* x, const int* cls, const float* e, const float* S, const float* weights,
                                   int has_wa, void* y, int pad, int planes, int B, int C, int D, int H, int W,
@@ -850,26 +946,30 @@ extern "C" int dca_disp_attention(const void* x, const int* cls, const float* e,
   const int MT = (D + 15) / 16;
   if (MT > 4) return DCA_ERR_UNSUPPORTED;
   const size_t wbytes = (size_t)AT_NMAT * 2 * AT_WPLANE * 2 + 6 * 64 * 4;
-  const size_t per_warp = (size_t)2 * (2 * 16 * MT * AT_PITCH) * 2 + (size_t)3 * (16 * MT * AT_C) * 4;   // per pixel in flight
-  int warps = 8;
+  const bool core = (D == 24 && g_attention_team == 1);          // tensor-core attention core: 4 hi/lo pair buffers per team
+  const size_t pair_bytes = (size_t)(2 * 16 * MT * AT_PITCH) * 2;
+  const size_t per_warp = core ? 4 * pair_bytes : 2 * pair_bytes + (size_t)3 * (16 * MT * AT_C) * 4;   // per pixel in flight
+  int warps = core ? 9 : 8;
   while (warps > 1 && wbytes + warps * per_warp > 224 * 1024) --warps;
   const size_t smem = wbytes + warps * per_warp;
   const int HW = H * W;
   int grid = (B * HW + warps - 1) / warps;
   if (grid > 148) grid = 148;            // persistent: one CTA per SM pays the weight-staging prologue once
   cudaStream_t st = (cudaStream_t)stream;
-#define DCA_AT_LAUNCH2(P_, MT_, DT_, WPP_)                                                                       \
+#define DCA_AT_LAUNCH2(P_, MT_, DT_, WPP_, CORE_)                                                                      \
   do {                                                                                                           \
-    auto kern = disp_attention_kernel<P_, MT_, DT_, WPP_>;                                                          \
+    auto kern = disp_attention_kernel<P_, MT_, DT_, WPP_, CORE_>;                                                          \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
     kern<<<grid, warps * 32 * WPP_, smem, st>>>((const __nv_bfloat16*)x, cls, e, S, weights, has_wa,              \
                                                 (__nv_bfloat16*)y, B, D, H, W, pad);                             \
   } while (0)
-#define DCA_AT_LAUNCH(P_, MT_) DCA_AT_LAUNCH2(P_, MT_, 0, 1)
-  if (D == 24 && g_attention_team) {
-    if (planes == 2) DCA_AT_LAUNCH2(2, 2, 24, 2); else DCA_AT_LAUNCH2(1, 2, 24, 2);
+#define DCA_AT_LAUNCH(P_, MT_) DCA_AT_LAUNCH2(P_, MT_, 0, 1, 0)
+  if (D == 24 && g_attention_team == 1) {          // two warps per pixel, tensor-core attention core
+    if (planes == 2) DCA_AT_LAUNCH2(2, 2, 24, 2, 1); else DCA_AT_LAUNCH2(1, 2, 24, 2, 1);
+  } else if (D == 24 && g_attention_team == 2) {   // two warps per pixel, fp32 FMA core
+    if (planes == 2) DCA_AT_LAUNCH2(2, 2, 24, 2, 0); else DCA_AT_LAUNCH2(1, 2, 24, 2, 0);
   } else if (D == 24) {
-    if (planes == 2) DCA_AT_LAUNCH2(2, 2, 24, 1); else DCA_AT_LAUNCH2(1, 2, 24, 1);
+    if (planes == 2) DCA_AT_LAUNCH2(2, 2, 24, 1, 0); else DCA_AT_LAUNCH2(1, 2, 24, 1, 0);
   } else if (planes == 2) {
     if (MT == 1) DCA_AT_LAUNCH(2, 1); else if (MT == 2) DCA_AT_LAUNCH(2, 2); else if (MT == 3) DCA_AT_LAUNCH(2, 3); else DCA_AT_LAUNCH(2, 4);
   } else {

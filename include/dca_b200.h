@@ -114,7 +114,8 @@ int dca_tc_set_halo(int on);
 /* 1 (default): DCANet-shaped volumes (C=320, Cc=12, G in {8,20,40}, W % 4 == 0) use the 16-byte-staged group-pair
    kernel; 0: the generic kernel everywhere (A/B timing and tests). */
 int dca_volume_set_v2(int on);
-/* 1 (default): dca_disp_attention runs two warps per pixel when D/8 == 24; 0: one warp per pixel (A/B timing). */
+/* dca_disp_attention at D/8 == 24: 1 (default) two warps per pixel + mma.sync attention core, 2 two warps + fp32 FMA
+ * core, 0 one warp per pixel (A/B timing). */
 int dca_attention_set_team(int on);
 /* timing probes of the tcgen05 kernels: (flags >> 4) & 1 skips the epilogue math + stores, & 2 the MMAs of the halo
  * and up2 kernels; `reserved` must be 1. */
