@@ -282,11 +282,42 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
   const size_t plane = (size_t)B * D * HW * AT_C;
   const float qscale = 0.35355339059327373f * 1.4426950408889634f;   // 8^-0.5 * log2(e): scores in the log2 domain
 
+  // CORE mode: the rows of the NEXT pixel (and its class / weight) are fetched into registers while this one is processed
+  uint4 pf_h[2], pf_l[2];
+  int pf_kp = 0;
+  float pf_e = 0.f;
+  auto prefetch = [&](int pixn) {
+    if (pixn >= B * HW) return;
+    const int bn = pixn / HW, pn = pixn % HW;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int d = 8 * wip + 16 * r + (lane >> 2);
+      if (d < D) {
+        const size_t off = (((size_t)bn * D + d) * HW + pn) * AT_C + (lane & 3) * 8;
+        pf_h[r] = *reinterpret_cast<const uint4*>(x + off);
+        pf_l[r] = (PLANES == 2) ? *reinterpret_cast<const uint4*>(x + plane + off) : make_uint4(0, 0, 0, 0);
+      }
+    }
+    pf_kp = cls[pixn];
+    pf_e = e[pixn];
+  };
+  if (CORE) prefetch(blockIdx.x * warps + warp);
   for (int pix = blockIdx.x * warps + warp; pix < B * HW; pix += gridDim.x * warps) {
     const int b = pix / HW, p = pix % HW;
-    const int kp = cls[pix];
-    const float wp = e[pix] / S[(size_t)b * D + kp];
+    const int kp = CORE ? pf_kp : cls[pix];
+    const float wp = (CORE ? pf_e : e[pix]) / S[(size_t)b * D + kp];
     // ---- x (already hi/lo in HBM) -> P0 verbatim ----
+    if (CORE) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int d = 8 * wip + 16 * r + (lane >> 2), q = lane & 3;
+        if (d < D) {
+          *reinterpret_cast<uint4*>(P0 + d * AT_PITCH + q * 8) = pf_h[r];
+          *reinterpret_cast<uint4*>(P0 + ROWS * AT_PITCH + d * AT_PITCH + q * 8) = pf_l[r];
+        }
+      }
+      prefetch(pix + gridDim.x * warps);
+    } else
     for (int d0 = 8 * wip; d0 < D; d0 += 8 * WPP) {
       const int d = d0 + (lane >> 2), q = lane & 3;
       if (d < D) {
