@@ -9,6 +9,7 @@ A "step" is ONE stereo pair through the whole hot path at BASELINE.json's config
 Prints ONE JSON line on rank 0.
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -50,38 +51,70 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region, through NVML in this process (the library behind
+    nvidia-smi; `nvidia_ml_py`).  Spawning `nvidia-smi` itself is NOT harmless: its start-up takes driver locks and was
+    measured to stall the launch stream for 50-250 ms about once in five runs (value 66-260 pairs/s at an unchanged
+    p50 of 3.27 ms), so the process-spawning form is only the fallback when NVML cannot be imported."""
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu_index, [], False
+        self.gpu, self.samples, self.stop_flag = gpu_index, [], False
+        self.nvml, self.handle, self.max_mhz = None, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        try:
+            mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+            mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        self.samples.append((mhz, self.max_mhz, {name for bit, name in self.REASONS if mask & bit}))
+
+    def _sample_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                             capture_output=True, text=True, timeout=5).stdout
+        for line in out.strip().splitlines():
+            c = [v.strip() for v in line.split(",")]
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            self.samples.append((float(c[0]), float(c[1]), {n for n, v in zip(names, c[2:6]) if v.lower().startswith("active")}))
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.rows.append([c.strip() for c in line.split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.03)
+            time.sleep(0.05 if self.nvml is not None else 0.25)
+
+    def stop(self):
+        self.stop_flag = True
 
     def summary(self):
-        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        sm = [s[0] for s in self.samples]
+        mx = [s[1] for s in self.samples if s[1]]
         reasons = set()
-        for r in self.rows:
-            if len(r) > 8:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
-                                   r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+        for s in self.samples:
+            reasons |= s[2]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def cpu_reference_run(cfg, steps, warmup, budget_s=150.0):
@@ -206,6 +239,8 @@ def main():
         for i in range(Wm):
             net.hot_path(*dev_sets[i % nsets])
         d._lib.LAUNCHES = 0
+        gc.collect()
+        gc.disable()                     # no collector pause inside the timed regions
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
@@ -241,8 +276,9 @@ def main():
         e1.record(pipe.compute_stream)
         barrier()
         e2e_ms = e0.elapsed_time(e1)
+        gc.enable()
         if rank == 0:
-            sampler.stop_flag = True
+            sampler.stop()
 
         # ---------------- roofline of the dominant kernel: conv3d k3 s1 32->32 at 1/4 res ----------------
         roof = None
