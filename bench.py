@@ -61,6 +61,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.gpu, self.samples, self.stop_flag = gpu_index, [], False
         self.nvml, self.handle, self.max_mhz = None, None, None
+        self.interval = float(os.environ.get("DCA_BENCH_CLOCK_INTERVAL", "0.05"))
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -102,7 +103,7 @@ class ClockSampler(threading.Thread):
                     self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.05 if self.nvml is not None else 0.25)
+            time.sleep(self.interval if self.nvml is not None else max(0.25, self.interval))
 
     def stop(self):
         self.stop_flag = True
@@ -242,7 +243,7 @@ def main():
         gc.collect()
         gc.disable()                     # no collector pause inside the timed regions
         sampler = ClockSampler(local_rank)
-        if rank == 0:
+        if rank == 0 and sampler.interval > 0:
             sampler.start()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
         barrier()
@@ -345,6 +346,7 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": pairs / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
                 "warmup": Wm, "ms_per_step": total_ms / K, "p50_ms_per_pair": statistics.median(step_ms) / B,
+                "max_step_ms": max(step_ms), "max_step_index": step_ms.index(max(step_ms)),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16x2 split operands (hi+lo fp16 planes, 22-bit significand), fp32 accumulate" if args.precision == "parity"
                 else "f16 operands, fp32 accumulate",

@@ -9,6 +9,8 @@ planes=2 ("parity": hi + lo, 22-bit significand) or planes=1 ("fast": a single 1
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -137,7 +139,10 @@ class Options:
     cout1_on_tc = True            # 32->1 convs: tensor-core per-tap GEMM + shifted sum instead of the CUDA-core kernel
     prop_on_tc = True             # the two 3x3 Conv2d of PropgationNet_4x on the halo-slab tcgen05 kernel
     up2_bilinear = True           # fuse stage: depth interpolation in the attention store, bilinear 4-class GEMM
-    prop_side_stream = True       # guidance branch of PropgationNet_4x (independent of the cost volume) on a second stream
+    # guidance branch of PropgationNet_4x (independent of the cost volume) on a second stream: +2 % pairs/s when it
+    # works, but 2 of 10 bench runs then showed a single 8-100 ms step (cross-stream allocator traffic), 0 of 10 without
+    # it -- so it is opt-in (DCA_SIDE_STREAM=1)
+    prop_side_stream = os.environ.get("DCA_SIDE_STREAM", "0") == "1"
     fp32_stages = frozenset()     # diagnostics: stages whose convs run on the fp32 CUDA-core kernel: {'dres', 'cva', 'cls3'}
     use_up2 = True                # class-wise halo-slab kernel for the transposed conv and the trilinear fuse stage
 
