@@ -52,15 +52,16 @@ class Planes:
         return self.t.data_ptr()
 
     @classmethod
-    def from_ncdhw(cls, x, planes=2, cpad=None):
-        """fp32 [B,C,D,H,W] (or [B,C,H,W]) -> planes."""
+    def from_ncdhw(cls, x, planes=2, cpad=None, out=None):
+        """fp32 [B,C,D,H,W] (or [B,C,H,W]) -> planes (into `out` when given)."""
         _require_cuda(x)
         if x.dim() == 4:
             x = x.unsqueeze(2)
         x = x.contiguous().float()
         B, C, D, H, W = x.shape
         Cp = cpad or ((C + 7) // 8 * 8)
-        out = cls(B, D, H, W, Cp, planes, x.device)
+        if out is None:
+            out = cls(B, D, H, W, Cp, planes, x.device)
         _lib.call("dca_planes_from_ncdhw", x.data_ptr(), out.ptr, planes, B, C, Cp, D, H, W, _stream())
         return out
 
@@ -139,10 +140,10 @@ class Options:
     cout1_on_tc = True            # 32->1 convs: tensor-core per-tap GEMM + shifted sum instead of the CUDA-core kernel
     prop_on_tc = True             # the two 3x3 Conv2d of PropgationNet_4x on the halo-slab tcgen05 kernel
     up2_bilinear = True           # fuse stage: depth interpolation in the attention store, bilinear 4-class GEMM
-    # guidance branch of PropgationNet_4x (independent of the cost volume) on a second stream: +2 % pairs/s when it
-    # works, but 2 of 10 bench runs then showed a single 8-100 ms step (cross-stream allocator traffic), 0 of 10 without
-    # it -- so it is opt-in (DCA_SIDE_STREAM=1)
-    prop_side_stream = os.environ.get("DCA_SIDE_STREAM", "0") == "1"
+    # guidance branch of PropgationNet_4x (independent of the cost volume) on a second stream with persistent buffers
+    # (+1.5 % pairs/s; with allocator-managed buffers the cross-stream frees stalled single steps for 8-100 ms in 2 of
+    # 10 bench runs -- 0 of 16 with persistent buffers).  DCA_SIDE_STREAM=0 disables it.
+    prop_side_stream = os.environ.get("DCA_SIDE_STREAM", "1") != "0"
     fp32_stages = frozenset()     # diagnostics: stages whose convs run on the fp32 CUDA-core kernel: {'dres', 'cva', 'cls3'}
     use_up2 = True                # class-wise halo-slab kernel for the transposed conv and the trilinear fuse stage
 
@@ -221,14 +222,14 @@ class PackedConv2dTc:
         torch.cuda.current_stream().synchronize()
 
 
-def conv2d_tc(x: Planes, pc: PackedConv2dTc, act=ACT_NONE, out_fp32=False):
+def conv2d_tc(x: Planes, pc: PackedConv2dTc, act=ACT_NONE, out_fp32=False, out=None):
     assert x.D == 1 and x.C == pc.cin and x.planes == pc.planes
     dev = x.t.device
     if out_fp32:
-        y = torch.empty((x.B, 1, x.H, x.W, pc.cout), dtype=torch.float32, device=dev)
+        y = out if out is not None else torch.empty((x.B, 1, x.H, x.W, pc.cout), dtype=torch.float32, device=dev)
         yptr = y.data_ptr()
     else:
-        y = Planes(x.B, 1, x.H, x.W, pc.cout, x.planes, dev)
+        y = out if out is not None else Planes(x.B, 1, x.H, x.W, pc.cout, x.planes, dev)
         yptr = y.ptr
     _lib.call("dca_conv2d_tc", x.ptr, x.planes, pc.w.data_ptr(), _ptr(pc.scale), _ptr(pc.shift), yptr, int(out_fp32),
               act, x.B, pc.cin, pc.cout, x.H, x.W, _stream())
@@ -548,20 +549,37 @@ def _prop_mask_start(pk, g, P):
     side = _SIDE_STREAMS.get(dev)
     if side is None:
         side = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=g.device)
-    side.wait_stream(main)                 # g (and the previous forward) are ready
+    side.wait_stream(main)                 # g is ready, and the previous forward no longer reads the buffers below
     g.record_stream(side)
+    # persistent buffers per shape: no caching-allocator traffic on the side stream (cross-stream frees made single
+    # steps stall for 8-100 ms in 2 of 10 bench runs)
+    B, Cg, H, W = g.shape
+    key = (g.device.index, B, Cg, H, W, P)
+    bufs = pk.__dict__.setdefault("_side_bufs", {}).get(key)
+    if bufs is None and Options.use_tc and Options.prop_on_tc:
+        gp = Planes(B, 1, H, W, (Cg + 7) // 8 * 8, P, g.device)
+        m1 = Planes(B, 1, H, W, pk.prop0_tc.cout, P, g.device)
+        mask = torch.empty((B, 1, H, W, pk.prop2_tc.cout), dtype=torch.float32, device=g.device)
+        bufs = pk._side_bufs[key] = (gp, m1, mask)
     with torch.cuda.stream(side):
-        mask = _prop_mask(pk, g, P)
-    return (side, mask, main, None)
+        if bufs is not None:
+            gp, m1, mask = bufs
+            Planes.from_ncdhw(g, planes=P, out=gp)
+            conv2d_tc(gp, pk.prop0_tc, ACT_RELU, out=m1)
+            conv2d_tc(m1, pk.prop2_tc, ACT_NONE, out_fp32=True, out=mask)
+        else:
+            mask = _prop_mask(pk, g, P)
+    return (side, mask, main, bufs)
 
 
 def _prop_mask_wait(job):
     if job[0] is None:
         _, pk, g, P = job
         return _prop_mask(pk, g, P)
-    side, mask, main, _ = job
+    side, mask, main, bufs = job
     main.wait_stream(side)
-    mask.record_stream(main)
+    if bufs is None:
+        mask.record_stream(main)
     return mask
 
 
