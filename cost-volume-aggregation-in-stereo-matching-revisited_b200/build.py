@@ -15,6 +15,10 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 FLAGS = [f for f in FLAGS if f != "--use_fast_math=false"]
+# 16-bit plane format: fp16 by default; DCA_PLANE_FORMAT=bf16 python build.py --force builds the
+# bf16 variant (8 more exponent bits for un-normalised checkpoints, 60x the representation error)
+if os.environ.get("DCA_PLANE_FORMAT", "fp16").lower() == "bf16":
+    FLAGS.append("-DDCA_F16_PLANES=0")
 
 
 def _stale(target, deps):
