@@ -1,5 +1,5 @@
 """B200-native DCANet cost-volume hot path (feature maps -> disparity) behind the reference's module API."""
-from . import _lib, engine
+from . import _lib, engine, hshard
 from .cva import Multi_Aggregation, cva
 from .gwcnet_dca_g import GwcNet, feature_extraction, hourglass
 from .pipeline import HotPathPipeline
@@ -10,4 +10,4 @@ from .submodule import (PropgationNet_4x, build_concat_volume, build_cost_planes
 
 __all__ = ["GwcNet", "feature_extraction", "hourglass", "cva", "Multi_Aggregation", "SemanticLevelContext",
            "SelfAttentionBlock", "PropgationNet_4x", "build_gwc_volume", "build_concat_volume", "build_cost_planes",
-           "disparity_regression", "softmax_disparity_regression", "convbn", "convbn_3d", "engine", "HotPathPipeline"]
+           "disparity_regression", "softmax_disparity_regression", "convbn", "convbn_3d", "engine", "hshard", "HotPathPipeline"]
