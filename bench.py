@@ -155,6 +155,48 @@ def cpu_reference_run(cfg, steps, warmup, budget_s=150.0):
     return 1.0 / t_pair, t_pair * 1e3, cores, sample
 
 
+def run_hshard(args, d, net, dist, dev, rank, world, barrier, K, Wm):
+    """Single-pair H-sharded mode (BASELINE configs[4]): every step is ONE pair whose 1/4-res rows are split
+    over the ranks; the data path has a real exchange (halo rows with both neighbours after every k3 layer, one
+    [B, D/8] all-reduce per cva), so this is strong scaling.  Not part of the default run."""
+    assert dist is not None and world > 1, "--hshard needs torchrun with more than one rank"
+    H, W, maxdisp, B = workloads.CONFIGS[args.config]
+    hs = d.hshard
+    nsets = 2
+    slabs = []
+    for s in range(nsets):       # every rank builds the same seeded pair and keeps only the rows it owns
+        full = workloads.feature_maps(s, B, H // 4, W // 4)
+        slabs.append([hs.owned_rows(t, world, rank).to(dev) for t in full])
+        del full
+    with torch.no_grad():
+        for i in range(Wm):
+            net.hot_path_hsharded(*slabs[i % nsets], rank=rank, world=world)
+        d._lib.LAUNCHES = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(K):
+            net.hot_path_hsharded(*slabs[i % nsets], rank=rank, world=world)
+        e1.record()
+        barrier()
+    tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = float(tt[0])
+        r0, r1 = hs.row_partition(H // 4, world)[0]
+        print(json.dumps({
+            "metric": f"{args.config} pairs/s (one pair H-sharded over {world} GPUs)", "value": K * B / (ms * 1e-3),
+            "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f16x2 split operands, fp32 accumulate",
+            "data": "synthetic",
+            "config": {"workload": args.config, "H": H, "W": W, "maxdisp": maxdisp, "batch": B,
+                       "parallelism": f"rows of one pair over {world} ranks: {r1 - r0} quarter-res rows + 2 halo rows "
+                                      "per side each; NCCL send/recv halos, 3 all-reduces of [B, D/8]"},
+            "gpu_launches": d._lib.LAUNCHES}))
+    dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -166,6 +208,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tc", action="store_true", help="force the CUDA-core conv kernels")
     ap.add_argument("--breakdown", action="store_true", help="print per-entry-point GPU time of one forward and exit")
+    ap.add_argument("--hshard", action="store_true",
+                    help="configs[4] mode: ONE pair per step, its rows split over the N ranks (halo exchange + 3 "
+                         "all-reduces per forward, strong scaling); needs torchrun with N > 1")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -217,6 +262,9 @@ def main():
         if dist is not None:
             dist.barrier()
             torch.cuda.synchronize()
+
+    if args.hshard:
+        return run_hshard(args, d, net, dist, dev, rank, world, barrier, K, Wm)
 
     if args.breakdown:
         with torch.no_grad():
