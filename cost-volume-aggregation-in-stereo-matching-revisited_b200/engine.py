@@ -515,9 +515,13 @@ class PackedHotPath:
         self.num_groups = net.num_groups
         self.dres0_0 = pack_convbn(net.dres0[0]); self.dres0_2 = pack_convbn(net.dres0[2])
         self.dres1_0 = pack_convbn(net.dres1[0]); self.dres1_2 = pack_convbn(net.dres1[2])
-        self.cva = [PackedCva(m, planes) for m in (net.cva1, net.cva2, net.cva3)]
-        self.cls3_0 = pack_convbn(net.classif3[0])
-        self.cls3_2 = PackedCout1(net.classif3[2].weight, planes)
+        # stage-count variants (gwcnet_dca{0,1,2,4}_g.py): N cva stages, head = classif<N>, returned class logits = stage pv_stage
+        self.num_cva = getattr(net, "num_cva", 3)
+        self.pv_stage = getattr(net, "pv_stage", 2)
+        self.cva = [PackedCva(getattr(net, f"cva{i + 1}"), planes) for i in range(self.num_cva)]
+        head = getattr(net, f"classif{self.num_cva}")
+        self.cls3_0 = pack_convbn(head[0])
+        self.cls3_2 = PackedCout1(head[2].weight, planes)
         self.prop0 = pack_convbn(net.prop.conv[0])
         self.prop2 = PackedConv(net.prop.conv[2].weight)
         self.prop0_tc = PackedConv2dTc(net.prop.conv[0][0].weight, net.prop.conv[0][1], planes)
@@ -599,20 +603,22 @@ def hot_path_forward(pk: PackedHotPath, gwc_l, gwc_r, cat_l, cat_r, g, keep=None
     r = conv(c, pk.dres1_0, K3S1, ACT_RELU)
     cost0 = conv(r, pk.dres1_2, K3S1, ACT_NONE, res_post=c)
     Options.use_tc = tc0 and "cva" not in Options.fp32_stages
-    k1 = {} if keep is not None else None
-    k2 = {} if keep is not None else None
-    k3 = {} if keep is not None else None
-    _, out1 = cva_forward(pk.cva[0], cost0, res_post=cost0, keep=k1)
-    logits2, out2 = cva_forward(pk.cva[1], out1, keep=k2)
-    _, out3 = cva_forward(pk.cva[2], out2, keep=k3)
+    kept = [{} if keep is not None else None for _ in pk.cva]
+    cur, out1, logits2 = cost0, None, None
+    for i, stage in enumerate(pk.cva):      # cva1 adds cost0 back (gwcnet_dca_g.py:229), the others chain
+        lg, cur = cva_forward(stage, cur, res_post=cost0 if i == 0 else None, keep=kept[i])
+        if i == 0:
+            out1 = cur
+        if i + 1 == pk.pv_stage:
+            logits2 = lg
     Options.use_tc = tc0 and "cls3" not in Options.fp32_stages
-    h = conv(out3, pk.cls3_0, K3S1, ACT_RELU)
+    h = conv(cur, pk.cls3_0, K3S1, ACT_RELU)
     logits = conv_cout1_any(h, pk.cls3_2)
     pred_q = softmax_regress(logits)
     Options.use_tc = tc0
     mask = _prop_mask_wait(side_job)
     pred4 = convex_upsample(mask, pred_q)
     if keep is not None:
-        keep.update(volume=vol, dres0=c, cost0=cost0, out1=out1, cva1=k1, cva2=k2, cva3=k3,
-                    classif3_logits=logits, pred_quarter=pred_q, mask=mask)
-    return pred4, logits2
+        keep.update(volume=vol, dres0=c, cost0=cost0, out1=out1, classif3_logits=logits, pred_quarter=pred_q, mask=mask)
+        keep.update({f"cva{i + 1}": k for i, k in enumerate(kept)})
+    return pred4, (logits if not pk.cva else logits2)     # no cva stage (gwcnet_dca0_g.py:190): the head's own logits

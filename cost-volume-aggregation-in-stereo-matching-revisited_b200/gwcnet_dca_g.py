@@ -83,10 +83,17 @@ class hourglass(nn.Module):
 
 
 class GwcNet(nn.Module):
-    """precision: "parity" (hi+lo bf16 planes, meets |d disp| <= 0.05 px) or "fast" (single bf16)."""
+    """precision: "parity" (hi+lo 16-bit planes, meets |d disp| <= 0.05 px) or "fast" (single 16-bit plane).
+
+    The class constants describe the stage graph; the reference's stage-count variants (gwcnet_dca{0,1,2,4}_g.py)
+    subclass this with other values and run the same kernels."""
+    NUM_CVA = 3           # cva stages; the head is classif<NUM_CVA>, the heads below it are training-only
+    PV_STAGE = 2          # eval returns the class logits of this stage (`prob_volume2`, gwcnet_dca_g.py:282)
+    SQUEEZE_PRED = False  # eval returns pred4 [B,1,H,W]; the 0/1/2-stage variants return pred.squeeze(1)
 
     def __init__(self, maxdisp, use_concat_volume=True, precision="parity"):
         super().__init__()
+        self.num_cva, self.pv_stage = self.NUM_CVA, self.PV_STAGE
         assert maxdisp % 8 == 0, "maxdisp must be a multiple of 8 (1/4 volume, 1/8 DCA stage)"
         self.maxdisp = maxdisp
         self.use_concat_volume = use_concat_volume
@@ -101,10 +108,9 @@ class GwcNet(nn.Module):
         self.dres0 = nn.Sequential(convbn_3d(self.num_groups + self.concat_channels * 2, 32, 3, 1, 1),
                                    nn.ReLU(inplace=True), convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True))
         self.dres1 = nn.Sequential(convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True), convbn_3d(32, 32, 3, 1, 1))
-        self.cva1 = cva(self.maxdisp, 32, downsample=True)
-        self.cva2 = cva(self.maxdisp, 32, downsample=True)
-        self.cva3 = cva(self.maxdisp, 32, downsample=True)
-        for i in range(4):   # classif0..2 are training-only heads; kept for the state_dict layout
+        for i in range(self.num_cva):
+            setattr(self, f"cva{i + 1}", cva(self.maxdisp, 32, downsample=True))
+        for i in range(self.num_cva + 1):   # the heads below classif<N> are training-only; kept for the state_dict layout
             setattr(self, f"classif{i}", nn.Sequential(
                 convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True),
                 nn.Conv3d(32, 1, kernel_size=3, padding=1, stride=1, bias=False)))
@@ -167,5 +173,6 @@ class GwcNet(nn.Module):
         fl = self.feature_extraction(left)
         fr = self.feature_extraction(right)
         g = self.guidance(left)["g"]
-        return self.hot_path(fl["gwc_feature"], fr["gwc_feature"], fl.get("concat_feature"),
-                             fr.get("concat_feature"), g)
+        pred, pv = self.hot_path(fl["gwc_feature"], fr["gwc_feature"], fl.get("concat_feature"),
+                                 fr.get("concat_feature"), g)
+        return (pred.squeeze(1) if self.SQUEEZE_PRED else pred), pv

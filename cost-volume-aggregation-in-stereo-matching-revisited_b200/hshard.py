@@ -5,7 +5,7 @@ layer that looks at neighbouring rows and one [B, D/8] sum all-reduce per cva st
 STATUS: host logic and exchange plan are covered on CPU (tests/test_hshard_plan.py: the drivers below run the same
 plan over the CPU checker's ATen ops, in-process with 2/3/4 virtual ranks and over gloo with world_size 2, against
 the un-sharded CPU result).  The kernel sequence `hot_path_steps` itself has NOT run on a GPU yet (the round's GPU budget was
-spent before it was written); tests/test_gpu_hshard.py holds its parity test, enabled with DCA_TEST_HSHARD=1.
+spent before it was written); tests/test_gpu_hshard.py holds its parity test, enabled with DCA_TEST_UNVALIDATED=1.
 
 Frame of one rank.  The rank owns the 1/4-res rows [r0, r1) (both even, so its 1/8-res rows [r0/2, r1/2) align).
 Every local tensor carries halo rows: 2 at 1/4 res (buffer = global rows [r0-2, r1+2)), 1 at 1/8 res (global rows
@@ -259,10 +259,12 @@ def hot_path_steps(pk: E.PackedHotPath, gwc_l, gwc_r, cat_l, cat_r, g):
     yield Rows(r.t, 3, H4_HALO)
     cost0 = E.conv(r, pk.dres1_2, E.K3S1, E.ACT_NONE, res_post=c)
     yield Rows(cost0.t, 3, H4_HALO)
-    _, out1 = yield from _cva_steps(pk.cva[0], cost0, res_post=cost0)
-    logits2, out2 = yield from _cva_steps(pk.cva[1], out1)
-    _, out3 = yield from _cva_steps(pk.cva[2], out2)
-    h = E.conv(out3, pk.cls3_0, E.K3S1, E.ACT_RELU)
+    cur, logits2 = cost0, None
+    for i, stage in enumerate(pk.cva):
+        lg, cur = yield from _cva_steps(stage, cur, res_post=cost0 if i == 0 else None)
+        if i + 1 == pk.pv_stage:
+            logits2 = lg
+    h = E.conv(cur, pk.cls3_0, E.K3S1, E.ACT_RELU)
     yield Rows(h.t, 3, H4_HALO)
     logits = E.conv_cout1_any(h, pk.cls3_2)               # valid on the owned rows and the halo row next to them
     pred_q = E.softmax_regress(logits)                    # [B,1,Hb4,W4]
@@ -271,7 +273,10 @@ def hot_path_steps(pk: E.PackedHotPath, gwc_l, gwc_r, cat_l, cat_r, g):
     pred4 = E.convex_upsample(mask, pred_q)
     Hb4 = pred_q.shape[2]
     pred4 = pred4[:, :, 4 * H4_HALO:4 * (Hb4 - H4_HALO)].contiguous()
-    pv2 = logits2[:, :, H8_HALO:logits2.shape[2] - H8_HALO].contiguous()
+    if logits2 is None:                                   # no cva stage: the head's own 1/4-res logits
+        pv2 = logits[:, :, H4_HALO:Hb4 - H4_HALO].contiguous()
+    else:
+        pv2 = logits2[:, :, H8_HALO:logits2.shape[2] - H8_HALO].contiguous()
     return pred4, pv2
 
 

@@ -260,9 +260,12 @@ def convex_upsample(ctx: _Ctx, prefix, g, disp):
 
 
 def hot_path(sd, gwc_l, gwc_r, cat_l, cat_r, g, maxdisp, num_groups=40, operand_bits=None,
-             calibrate=False, collect=None):
+             calibrate=False, collect=None, num_cva=3, pv_stage=2):
     """GwcNet.forward (eval) from feature maps to (pred4 [B,1,H,W], prob_volume2 [B,D8,H8,W8]).
-    gwcnet_dca_g.py:216-240,282.  `collect` (dict) receives every boundary tensor."""
+    gwcnet_dca_g.py:216-240,282.  `collect` (dict) receives every boundary tensor.
+    Stage-count variants (same graph, N cva stages, head classif<N>, class logits of stage `pv_stage` returned):
+    gwcnet_dca0_g.py:154-190 (N=0: returns the 1/4-res head logits), gwcnet_dca1_g.py:160-210 (N=1, stage 1),
+    gwcnet_dca2_g.py:167-235 (N=2, stage 2), gwcnet_dca4_g.py:214-302 (N=4, stage 4)."""
     ctx = _Ctx(sd, operand_bits, calibrate)
     D4 = maxdisp // 4
     vol = torch.cat([build_gwc_volume(gwc_l, gwc_r, D4, num_groups),
@@ -271,26 +274,31 @@ def hot_path(sd, gwc_l, gwc_r, cat_l, cat_r, g, maxdisp, num_groups=40, operand_
     c = ctx.convbn3d(c, "dres0.2", 1, 1, "relu")
     r = ctx.convbn3d(c, "dres1.0", 1, 1, "relu")
     cost0 = ctx.convbn3d(r, "dres1.2", 1, 1, None) + c
-    pv1, aug1 = cva_forward(ctx, "cva1", cost0, collect)
-    out1 = cost0 + aug1
-    pv2, out2 = cva_forward(ctx, "cva2", out1, collect)
-    pv3, out3 = cva_forward(ctx, "cva3", out2, collect)
-    h = ctx.convbn3d(out3, "classif3.0", 1, 1, "relu")
-    logits = ctx.conv3d(h, "classif3.2.weight", 1, 1).squeeze(1)
+    cur, out1, pvs = cost0, None, []
+    for i in range(num_cva):
+        pv, out = cva_forward(ctx, f"cva{i + 1}", cur, collect)
+        cur = cost0 + out if i == 0 else out
+        if i == 0:
+            out1 = cur
+        pvs.append(pv)
+    h = ctx.convbn3d(cur, f"classif{num_cva}.0", 1, 1, "relu")
+    logits = ctx.conv3d(h, f"classif{num_cva}.2.weight", 1, 1).squeeze(1)
     pred_q = disparity_regression(F.softmax(logits, dim=1), D4)
     pred4 = convex_upsample(ctx, "prop", g, pred_q)
+    pv_out = logits if num_cva == 0 else pvs[pv_stage - 1].squeeze(1)
     if collect is not None:
         collect.update(volume=vol, dres0=c, cost0=cost0, out1=out1, classif3_logits=logits,
-                       pred_quarter=pred_q, pred4=pred4, prob_volume2=pv2.squeeze(1))
-    return pred4, pv2.squeeze(1)
+                       pred_quarter=pred_q, pred4=pred4, prob_volume2=pv_out)
+    return pred4, pv_out
 
 
 # --------------------------------------------------------------------------------------------
 # synthetic, calibrated hot-path checkpoint -- reference-independent
 # --------------------------------------------------------------------------------------------
-def hot_path_param_shapes(num_groups=40, concat_channels=12):
+def hot_path_param_shapes(num_groups=40, concat_channels=12, num_cva=3):
     """Reference-layout state_dict entries of the hot path (dres*, cva*, classif*, prop).
-    gwcnet_dca_g.py:141-171, cva.py:14-56, SelfAttention_bn.py:20-52."""
+    gwcnet_dca_g.py:141-171, cva.py:14-56, SelfAttention_bn.py:20-52.  Stages beyond the third (gwcnet_dca4_g.py:173,191)
+    are appended AFTER prop so that the seeded values of everything else do not move."""
     shapes = {}
 
     def conv3(key, co, ci, k=3):
@@ -310,7 +318,8 @@ def hot_path_param_shapes(num_groups=40, concat_channels=12):
     cb("dres1.0", 32, 32); cb("dres1.2", 32, 32)
     for i in range(4):
         cb(f"classif{i}.0", 32, 32); conv3(f"classif{i}.2.weight", 1, 32)
-    for s in (1, 2, 3):
+
+    def cva_stage(s):
         p = f"cva{s}"
         cb(p + ".downsample.1", 32, 32)
         a = p + ".slc_net.cross_attention"
@@ -323,13 +332,19 @@ def hot_path_param_shapes(num_groups=40, concat_channels=12):
         shapes[p + ".cost_agg.conv3.0.weight"] = (64, 32, 3, 3, 3)   # ConvTranspose3d: [Cin,Cout,...]
         bn(p + ".cost_agg.conv3.1", 32)
         cb(p + ".cost_agg.redir", 32, 32, 1)
+
+    for s in (1, 2, 3):
+        cva_stage(s)
     shapes["prop.conv.0.0.weight"] = (128, 64, 3, 3)
     bn("prop.conv.0.1", 128)
     shapes["prop.conv.2.weight"] = (144, 128, 3, 3)
+    for s in range(4, num_cva + 1):
+        cb(f"classif{s}.0", 32, 32); conv3(f"classif{s}.2.weight", 1, 32)
+        cva_stage(s)
     return shapes
 
 
-def synth_state_dict(seed=0, num_groups=40, concat_channels=12):
+def synth_state_dict(seed=0, num_groups=40, concat_channels=12, num_cva=3):
     """Random hot-path weights with the reference's init law (normal(0, sqrt(2/(k^3*Cout))),
     gwcnet_dca_g.py:173-178) and BN gamma~U(.75,1.25), beta~N(0,.1^2); running stats are
     placeholders until `calibrate_state_dict` runs.  numpy PCG64 so the values are identical on
@@ -337,7 +352,7 @@ def synth_state_dict(seed=0, num_groups=40, concat_channels=12):
     import numpy as np
     rng = np.random.default_rng(seed)
     sd = {}
-    for key, shp in hot_path_param_shapes(num_groups, concat_channels).items():
+    for key, shp in hot_path_param_shapes(num_groups, concat_channels, num_cva).items():
         leaf = key.rsplit(".", 1)[1]
         if leaf == "num_batches_tracked":
             sd[key] = torch.tensor(1, dtype=torch.int64)
@@ -375,9 +390,9 @@ def synth_features(seed, B, H4, W4, shift=3, C=320, Cc=12, Cg=64):
     return gl.contiguous(), gr.contiguous(), cl.contiguous(), cr.contiguous(), gd.contiguous()
 
 
-def calibrate_state_dict(sd, feats, maxdisp, num_groups=40):
+def calibrate_state_dict(sd, feats, maxdisp, num_groups=40, num_cva=3):
     """One train-mode-BN pass so running stats equal batch stats (unit-scale activations).
     Mutates and returns sd."""
     with torch.no_grad():
-        hot_path(sd, *feats, maxdisp=maxdisp, num_groups=num_groups, calibrate=True)
+        hot_path(sd, *feats, maxdisp=maxdisp, num_groups=num_groups, calibrate=True, num_cva=num_cva)
     return sd
