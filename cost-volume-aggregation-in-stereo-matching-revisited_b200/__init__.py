@@ -1,5 +1,5 @@
 """B200-native DCANet cost-volume hot path (feature maps -> disparity) behind the reference's module API."""
-from . import _lib, engine, hshard
+from . import _lib, engine, hshard, kitti_io
 from . import gwcnet_dca0_g, gwcnet_dca1_g, gwcnet_dca2_g, gwcnet_dca4_g
 from .cva import Multi_Aggregation, cva
 from .gwcnet_dca_g import GwcNet, feature_extraction, hourglass
@@ -11,4 +11,4 @@ from .submodule import (PropgationNet_4x, build_concat_volume, build_cost_planes
 
 __all__ = ["GwcNet", "feature_extraction", "hourglass", "cva", "Multi_Aggregation", "SemanticLevelContext",
            "SelfAttentionBlock", "PropgationNet_4x", "build_gwc_volume", "build_concat_volume", "build_cost_planes",
-           "disparity_regression", "softmax_disparity_regression", "convbn", "convbn_3d", "engine", "hshard", "HotPathPipeline"]
+           "disparity_regression", "softmax_disparity_regression", "convbn", "convbn_3d", "engine", "hshard", "kitti_io", "HotPathPipeline"]
