@@ -8,6 +8,10 @@ import ctypes
 import torch
 
 
+class _List(list):
+    pass
+
+
 class _NoStream:
     cuda_stream = 0
 
@@ -19,7 +23,8 @@ class _NoStream:
 def recording():
     import dcanet_b200 as d
     E, L = d.engine, d._lib
-    trace = []
+    trace = _List()
+    full = trace.full = _List()      # same calls with the pointer arguments kept (see dataflow_trace)
 
     def fake_call(name, *args):
         if name == "dca_fold_bn":         # the one packed value the host logic branches on (zero BN scale): make it 1.0
@@ -27,6 +32,7 @@ def recording():
             ctypes.memmove(args[5], ones, 4 * args[8])
             ctypes.memset(args[6], 0, 4 * args[8])
         trace.append((name,) + tuple(a for a in args if isinstance(a, int) and not isinstance(a, bool) and 0 <= a < (1 << 20)))
+        full.append((name,) + tuple(args))
 
     saved = (L.call, E._require_cuda, E._stream, torch.cuda.current_stream, E.Options.prop_side_stream)
     L.call = fake_call
@@ -49,3 +55,31 @@ def forward_trace(net, H4, W4, B=1):
         with torch.no_grad():
             out = net.hot_path(*feats)
         return trace[n0:], out
+
+
+def dataflow_trace(net, H4, W4, B=1):
+    """Like forward_trace, but every pointer argument is replaced by 'P<k>', k = order of first appearance in the
+    forward: the buffer-level data flow between the launches.  All buffers are kept alive during the forward so that an
+    address is never reused for two tensors."""
+    feats = [torch.zeros(B, c, H4, W4) for c in (320, 320, 12, 12, 64)]
+    alive, real_empty = [], torch.empty
+
+    def hold(*a, **k):
+        t = real_empty(*a, **k)
+        alive.append(t)
+        return t
+
+    with recording() as trace:
+        net.packed()
+        n0 = len(trace.full)
+        torch.empty = hold
+        try:
+            with torch.no_grad():
+                net.hot_path(*feats)
+        finally:
+            torch.empty = real_empty
+        ids, out = {}, []
+        for row in trace.full[n0:]:
+            out.append(tuple(("P%d" % ids.setdefault(a, len(ids))) if isinstance(a, int) and a >= (1 << 20) else a
+                             for a in row))
+        return out

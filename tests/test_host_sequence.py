@@ -49,3 +49,11 @@ def test_hsharded_forward_host_flow():
     want.update({("dca_class_stats", 1, 6, 4, W4 // 2, 0): 3})          # S[b,k] over the 4 owned 1/8-res rows, per cva
     got = collections.Counter(sharded)
     assert got == collections.Counter({k: v * world for k, v in want.items()})
+
+
+def test_default_forward_buffer_dataflow():
+    """Same launches AND the same buffer wiring between them (pointer arguments normalised to first-appearance ids) as
+    recorded from the engine that passed the GPU parity suite: guards host refactors that cannot be run on a GPU."""
+    import dcanet_b200 as d
+    got = _dryrun.dataflow_trace(d.GwcNet(48).eval(), 16, 32)
+    assert got == _gold("kernel_dataflow_tiny.json")
