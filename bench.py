@@ -170,13 +170,13 @@ def run_hshard(args, d, net, dist, dev, rank, world, barrier, K, Wm):
         del full
     with torch.no_grad():
         for i in range(Wm):
-            net.hot_path_hsharded(*slabs[i % nsets], rank=rank, world=world)
+            net.hot_path_hsharded(*slabs[i % nsets], rank=rank, world=world, transport=args.hshard_transport)
         d._lib.LAUNCHES = 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
         for i in range(K):
-            net.hot_path_hsharded(*slabs[i % nsets], rank=rank, world=world)
+            net.hot_path_hsharded(*slabs[i % nsets], rank=rank, world=world, transport=args.hshard_transport)
         e1.record()
         barrier()
     tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -191,7 +191,7 @@ def run_hshard(args, d, net, dist, dev, rank, world, barrier, K, Wm):
             "data": "synthetic",
             "config": {"workload": args.config, "H": H, "W": W, "maxdisp": maxdisp, "batch": B,
                        "parallelism": f"rows of one pair over {world} ranks: {r1 - r0} quarter-res rows + 2 halo rows "
-                                      "per side each; NCCL send/recv halos, 3 all-reduces of [B, D/8]"},
+                                      "per side each; halo rows by " + args.hshard_transport + ", 3 all-reduces of [B, D/8]"},
             "gpu_launches": d._lib.LAUNCHES}))
     dist.destroy_process_group()
     return 0
@@ -211,6 +211,8 @@ def main():
     ap.add_argument("--hshard", action="store_true",
                     help="configs[4] mode: ONE pair per step, its rows split over the N ranks (halo exchange + 3 "
                          "all-reduces per forward, strong scaling); needs torchrun with N > 1")
+    ap.add_argument("--hshard-transport", default="nccl", choices=["nccl", "p2p"],
+                    help="halo rows by NCCL send/recv or by peer-memory stores (csrc/halo_p2p.cu)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -18,6 +18,9 @@ else
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 \
       --master-port 29511 bench.py --gpus "$N" --hshard --config middlebury_1536x2048 --steps 10 --warmup 3 \
       > gpurun_out/r2_hshard_${N}gpu.json 2> gpurun_out/r2_hshard_${N}gpu.err; echo "hshard bench rc=$?"
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 \
+      --master-port 29512 bench.py --gpus "$N" --hshard --hshard-transport p2p --config middlebury_1536x2048 --steps 10 \
+      --warmup 3 > gpurun_out/r2_hshard_p2p_${N}gpu.json 2> gpurun_out/r2_hshard_p2p_${N}gpu.err; echo "hshard p2p bench rc=$?"
   timeout 600 python bench.py --config middlebury_1536x2048 --steps 10 --warmup 3 --no-cpu-baseline \
       > gpurun_out/r2_middlebury_1gpu.json 2>/dev/null; echo "1-gpu middlebury rc=$?"
 fi

@@ -159,12 +159,13 @@ class GwcNet(nn.Module):
         """feature maps -> (pred4 [B,1,H,W], prob_volume2 [B,D8,H8,W8]); the graded path."""
         return engine.hot_path_forward(self.packed(), gwc_l, gwc_r, cat_l, cat_r, g, keep)
 
-    def hot_path_hsharded(self, gwc_l, gwc_r, cat_l, cat_r, g, rank, world, group=None):
+    def hot_path_hsharded(self, gwc_l, gwc_r, cat_l, cat_r, g, rank, world, group=None, transport="nccl"):
         """One rank of the H-sharded single-pair mode (BASELINE configs[4]): this rank's OWNED 1/4-res rows of the
         feature maps in (`hshard.owned_rows`), its rows of (pred4, prob_volume2) out; halo rows and the per-class sums
         travel over torch.distributed.  See hshard.py for the plan and its verification status."""
         from . import hshard
-        return hshard.hot_path_forward_hsharded(self.packed(), gwc_l, gwc_r, cat_l, cat_r, g, rank, world, group)
+        return hshard.hot_path_forward_hsharded(self.packed(), gwc_l, gwc_r, cat_l, cat_r, g, rank, world, group,
+                                                transport)
 
     def forward(self, left, right, disp_true=None):
         if self.training:

@@ -143,26 +143,101 @@ def drive_lockstep(gens):
                 _halo_rows(r, False).copy_(_send_rows(reqs[i + 1], True))
 
 
-def drive_distributed(gen, rank, world, group=None):
+class PeerHalo:
+    """Halo rows over NVLink peer memory (csrc/halo_p2p.cu) instead of NCCL send/recv: two launches per exchange on the
+    compute stream, no host round trip.  Every rank owns one symmetric buffer (torch symmetric memory, peer-mapped by
+    all ranks of the box): 2 parities x 2 directions of staging slots, two 64-bit arrival counters and an error word.
+    Slot / counter index 0 = "arrives from ABOVE" (written by rank-1), 1 = "arrives from BELOW" (written by rank+1).
+    NOT YET RUN ON A GPU -- opt-in (`transport="p2p"`)."""
+
+    def __init__(self, rank, world, device, group=None, slot_bytes=8 << 20):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.rank, self.world, self.slot = rank, world, int(slot_bytes)
+        self.buf = symm.empty(4 * self.slot + 64, dtype=torch.uint8, device=device)
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.buf.zero_()
+        torch.cuda.current_stream().synchronize()
+        self.hdl.barrier()
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.ctas = _lib.load().dca_halo_push_ctas()
+        self.epoch = 0
+
+    def _slot(self, r, parity, direction):
+        return self.ptrs[r] + (2 * parity + direction) * self.slot
+
+    def _flag(self, r, direction):
+        return self.ptrs[r] + 4 * self.slot + 8 * direction
+
+    def supports(self, req: Rows):
+        t = req.t
+        inner = t.element_size()
+        for d in range(req.dim + 1, t.dim()):
+            inner *= t.shape[d]
+        outer = 1
+        for d in range(req.dim):
+            outer *= t.shape[d]
+        return (t.is_cuda and t.is_contiguous() and inner % 16 == 0 and t.data_ptr() % 16 == 0
+                and outer * req.h * inner <= self.slot)
+
+    def refresh(self, req: Rows):
+        """Interior sides of one exchange (the caller fills the image-border side).  Every rank must call this for the
+        same sequence of requests: the arrival counters count exchanges."""
+        t, r = req.t, self.rank
+        inner = t.element_size()
+        for d in range(req.dim + 1, t.dim()):
+            inner *= t.shape[d]
+        outer = 1
+        for d in range(req.dim):
+            outer *= t.shape[d]
+        rows = t.shape[req.dim]
+        self.epoch += 1
+        par = self.epoch & 1
+        up, down = r - 1, r + 1
+        has_up, has_down = up >= 0, down < self.world
+        st = E._stream()
+        _lib.call("dca_halo_push", t.data_ptr(), outer, rows, inner, req.h,
+                  self._slot(up, par, 1) if has_up else 0, self._slot(down, par, 0) if has_down else 0,
+                  self._flag(up, 1) if has_up else 0, self._flag(down, 0) if has_down else 0, st)
+        _lib.call("dca_halo_wait_unpack", t.data_ptr(), outer, rows, inner, req.h,
+                  self._slot(r, par, 0) if has_up else 0, self._slot(r, par, 1) if has_down else 0,
+                  self._flag(r, 0) if has_up else 0, self._flag(r, 1) if has_down else 0,
+                  self.epoch * self.ctas, self.ptrs[r] + 4 * self.slot + 16, st)
+
+    def check(self):
+        """Raises if a wait timed out (a neighbour never pushed).  Synchronises; call after the forward."""
+        torch.cuda.current_stream().synchronize()
+        if int(self.buf[4 * self.slot + 16:4 * self.slot + 20].view(torch.int32).item()) != 0:
+            raise _lib.DcaError("H-shard peer-memory halo exchange timed out waiting for a neighbour")
+
+
+def drive_distributed(gen, rank, world, group=None, peer: "PeerHalo" = None):
     """Run one rank's generator under torch.distributed (nccl on the GPU box, gloo in the CPU tests): halo rows travel
-    as grouped point-to-point sends/receives with the two neighbours, S[b,k] as an all-reduce."""
+    as grouped point-to-point sends/receives with the two neighbours (or, with `peer`, as direct NVLink stores into the
+    neighbours' staging buffers), S[b,k] as an all-reduce."""
     import torch.distributed as dist
     try:
         req = next(gen)
         while True:
             if isinstance(req, Sum):
                 dist.all_reduce(req.t, op=dist.ReduceOp.SUM, group=group)
+            elif peer is not None and req.exchange and peer.supports(req):
+                if rank == 0:
+                    _fill_border(req, True)
+                if rank == world - 1:
+                    _fill_border(req, False)
+                peer.refresh(req)
             else:
                 ops, landing = [], []
-                for top, peer in ((True, rank - 1), (False, rank + 1)):
-                    if peer < 0 or peer >= world:
+                for top, nb in ((True, rank - 1), (False, rank + 1)):
+                    if nb < 0 or nb >= world:
                         _fill_border(req, top)
                         continue
                     if not req.exchange:
                         continue
                     out = _send_rows(req, top).contiguous()
                     buf = torch.empty_like(out)
-                    gpeer = peer if group is None else dist.get_global_rank(group, peer)
+                    gpeer = nb if group is None else dist.get_global_rank(group, nb)
                     ops.append(dist.P2POp(dist.isend, out, gpeer, group))
                     ops.append(dist.P2POp(dist.irecv, buf, gpeer, group))
                     landing.append((top, buf))
@@ -280,9 +355,21 @@ def hot_path_steps(pk: E.PackedHotPath, gwc_l, gwc_r, cat_l, cat_r, g):
     return pred4, pv2
 
 
-def hot_path_forward_hsharded(pk, gwc_l, gwc_r, cat_l, cat_r, g, rank, world, group=None):
-    """One rank of the H-sharded forward under torch.distributed (inputs and outputs: this rank's owned rows)."""
-    return drive_distributed(hot_path_steps(pk, gwc_l, gwc_r, cat_l, cat_r, g), rank, world, group)
+_PEERS = {}
+
+
+def hot_path_forward_hsharded(pk, gwc_l, gwc_r, cat_l, cat_r, g, rank, world, group=None, transport="nccl"):
+    """One rank of the H-sharded forward under torch.distributed (inputs and outputs: this rank's owned rows).
+    transport: "nccl" (grouped send/recv) or "p2p" (peer-memory stores, csrc/halo_p2p.cu; not yet run on a GPU)."""
+    peer = None
+    if transport == "p2p":
+        key = (gwc_l.device.index, rank, world, id(group))
+        peer = _PEERS.get(key)
+        if peer is None:
+            peer = _PEERS[key] = PeerHalo(rank, world, gwc_l.device, group)
+    elif transport != "nccl":
+        raise _lib.DcaError(f"unknown H-shard transport {transport!r}")
+    return drive_distributed(hot_path_steps(pk, gwc_l, gwc_r, cat_l, cat_r, g), rank, world, group, peer)
 
 
 def hot_path_forward_virtual(pk, gwc_l, gwc_r, cat_l, cat_r, g, world):
