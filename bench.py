@@ -179,6 +179,8 @@ def run_hshard(args, d, net, dist, dev, rank, world, barrier, K, Wm):
             net.hot_path_hsharded(*slabs[i % nsets], rank=rank, world=world, transport=args.hshard_transport)
         e1.record()
         barrier()
+    for peer in hs._PEERS.values():      # p2p transport: a timed-out wait (neighbour never pushed) invalidates the run
+        peer.check()
     tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     if rank == 0:
