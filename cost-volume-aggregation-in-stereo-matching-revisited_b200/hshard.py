@@ -13,7 +13,7 @@ Every local tensor carries halo rows: 2 at 1/4 res (buffer = global rows [r0-2, 
 the transposed conv (`cva.py:21`) and the trilinear x2 (`cva.py:64`) keep their row alignment in the local frame, so
 the single-GPU kernels run unchanged on the slab.  A k3 kernel computes garbage in the outermost halo row (it sees the
 buffer's zero padding instead of the neighbour's rows); after each such layer the halo rows are refreshed:
-  * interior side: the neighbour's owned rows (P2P send/recv, NCCL on NVLink; <= 3.1 MB per exchange at Middlebury),
+  * interior side: the neighbour's owned rows (<= 12.6 MB per side and exchange at Middlebury: 2 rows x 2 planes x 96 x 512 x 32 ch x 2 B),
   * image border: zeros -- exactly the zero padding of the reference's convs / AvgPool3d(count_include_pad) /
     F.unfold(padding=1) -- or, for the trilinear input only, a copy of the border row (align_corners=False clamps).
 Per-pixel ops (1x1x1 convs, attention over the disparity axis, softmax + regression) keep valid halos valid.
@@ -150,7 +150,7 @@ class PeerHalo:
     Slot / counter index 0 = "arrives from ABOVE" (written by rank-1), 1 = "arrives from BELOW" (written by rank+1).
     NOT YET RUN ON A GPU -- opt-in (`transport="p2p"`)."""
 
-    def __init__(self, rank, world, device, group=None, slot_bytes=8 << 20):
+    def __init__(self, rank, world, device, group=None, slot_bytes=16 << 20):
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
         self.rank, self.world, self.slot = rank, world, int(slot_bytes)
