@@ -1,9 +1,10 @@
 // Halo-row exchange of the H-sharded single-pair mode over NVLink peer memory (no NCCL, no host round trip).
 //
-// A tensor is seen as [outer][rows][inner bytes]; a rank owns rows [h, rows-h) and keeps h halo rows at both ends.
+// A tensor is seen as [outer][rows][inner bytes]; a rank owns rows [h, rows-h) and keeps h halo rows at both ends, of
+// which only the `live` rows next to the owned ones are ever read for an owned result (hshard.py) and travel.
 // One exchange = two launches on the rank's compute stream:
 //
-//   halo_push_kernel         reads the first / last h OWNED rows and stores them, packed, straight into the UPPER /
+//   halo_push_kernel         reads the first / last `live` OWNED rows and stores them, packed, straight into the UPPER /
 //                            LOWER neighbour's staging slot (peer pointers into the neighbours' symmetric buffers: the
 //                            stores travel over NVLink), then releases them: __threadfence_system + one system-scope
 //                            atomic increment per CTA of the neighbour's arrival counter.
@@ -29,7 +30,7 @@ struct HaloMsg {
   char* dst;
   long long outer;                    // slices
   long long src_pitch, dst_pitch;     // bytes between consecutive slices at the source / destination
-  long long chunk;                    // bytes per slice = h * inner (multiple of 16)
+  long long chunk;                    // bytes per slice = live * inner (multiple of 16)
 };
 
 __device__ __forceinline__ void halo_copy(const HaloMsg& m) {
@@ -88,13 +89,14 @@ using namespace dca;
 
 extern "C" int dca_halo_push_ctas() { return PUSH_CTAS; }
 
-// Rows [h, 2h) of `t` go to the upper neighbour's staging slot, rows [rows-2h, rows-h) to the lower neighbour's.
-// peer_*_stage / peer_*_flag: peer-mapped device addresses (0 = no neighbour on that side).
-extern "C" int dca_halo_push(const void* t, long long outer, long long rows, long long inner_bytes, int h,
+// The `live` owned rows next to each cut travel: rows [h, h+live) of `t` go to the upper neighbour's staging slot, rows
+// [rows-h-live, rows-h) to the lower neighbour's.  peer_*_stage / peer_*_flag: peer-mapped device addresses
+// (0 = no neighbour on that side).
+extern "C" int dca_halo_push(const void* t, long long outer, long long rows, long long inner_bytes, int h, int live,
                              void* peer_up_stage, void* peer_down_stage, void* peer_up_flag, void* peer_down_flag,
                              void* stream) {
-  if (!t || outer <= 0 || h <= 0 || rows < 4LL * h || inner_bytes <= 0) return DCA_ERR_ARG;
-  const long long chunk = (long long)h * inner_bytes;
+  if (!t || outer <= 0 || h <= 0 || live <= 0 || live > h || rows < 2LL * h + live || inner_bytes <= 0) return DCA_ERR_ARG;
+  const long long chunk = (long long)live * inner_bytes;
   if ((chunk & 15) || ((rows * inner_bytes) & 15) || (inner_bytes & 15) || ((uintptr_t)t & 15) ||
       ((uintptr_t)peer_up_stage & 15) || ((uintptr_t)peer_down_stage & 15))
     return DCA_ERR_UNSUPPORTED;
@@ -103,7 +105,7 @@ extern "C" int dca_halo_push(const void* t, long long outer, long long rows, lon
   const char* base = (const char*)t;
   HaloMsg up{peer_up_stage ? base + (long long)h * inner_bytes : nullptr, (char*)peer_up_stage, outer,
              rows * inner_bytes, chunk, chunk};
-  HaloMsg down{peer_down_stage ? base + (rows - 2LL * h) * inner_bytes : nullptr, (char*)peer_down_stage, outer,
+  HaloMsg down{peer_down_stage ? base + (rows - h - (long long)live) * inner_bytes : nullptr, (char*)peer_down_stage, outer,
                rows * inner_bytes, chunk, chunk};
   halo_push_kernel<<<dim3(PUSH_CTAS, 2), HALO_THREADS, 0, (cudaStream_t)stream>>>(
       up, down, (unsigned long long*)peer_up_flag, (unsigned long long*)peer_down_flag);
@@ -111,20 +113,22 @@ extern "C" int dca_halo_push(const void* t, long long outer, long long rows, lon
   return DCA_OK;
 }
 
-// Waits until the own arrival counters reach `target`, then fills rows [0, h) of `t` from `stage_top` and rows
-// [rows-h, rows) from `stage_bottom` (0 = image border on that side: nothing is waited for or written).
-extern "C" int dca_halo_wait_unpack(void* t, long long outer, long long rows, long long inner_bytes, int h,
+// Waits until the own arrival counters reach `target`, then fills the `live` halo rows next to the owned ones: rows
+// [h-live, h) of `t` from `stage_top`, rows [rows-h, rows-h+live) from `stage_bottom` (0 = image border on that side:
+// nothing is waited for or written).
+extern "C" int dca_halo_wait_unpack(void* t, long long outer, long long rows, long long inner_bytes, int h, int live,
                                     const void* stage_top, const void* stage_bottom, const void* flag_top,
                                     const void* flag_bottom, unsigned long long target, void* err, void* stream) {
-  if (!t || !err || outer <= 0 || h <= 0 || rows < 4LL * h || inner_bytes <= 0) return DCA_ERR_ARG;
-  const long long chunk = (long long)h * inner_bytes;
+  if (!t || !err || outer <= 0 || h <= 0 || live <= 0 || live > h || rows < 2LL * h + live || inner_bytes <= 0)
+    return DCA_ERR_ARG;
+  const long long chunk = (long long)live * inner_bytes;
   if ((chunk & 15) || ((rows * inner_bytes) & 15) || (inner_bytes & 15) || ((uintptr_t)t & 15) ||
       ((uintptr_t)stage_top & 15) || ((uintptr_t)stage_bottom & 15))
     return DCA_ERR_UNSUPPORTED;
   if ((stage_top && !flag_top) || (stage_bottom && !flag_bottom)) return DCA_ERR_ARG;
   if (!stage_top && !stage_bottom) return DCA_OK;
   char* base = (char*)t;
-  HaloMsg top{(const char*)stage_top, base, outer, chunk, rows * inner_bytes, chunk};
+  HaloMsg top{(const char*)stage_top, base + (long long)(h - live) * inner_bytes, outer, chunk, rows * inner_bytes, chunk};
   HaloMsg bottom{(const char*)stage_bottom, base + (rows - (long long)h) * inner_bytes, outer, chunk,
                  rows * inner_bytes, chunk};
   halo_wait_unpack_kernel<<<dim3(PUSH_CTAS, 2), HALO_THREADS, 0, (cudaStream_t)stream>>>(

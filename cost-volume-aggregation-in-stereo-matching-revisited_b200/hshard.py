@@ -13,7 +13,7 @@ Every local tensor carries halo rows: 2 at 1/4 res (buffer = global rows [r0-2, 
 the transposed conv (`cva.py:21`) and the trilinear x2 (`cva.py:64`) keep their row alignment in the local frame, so
 the single-GPU kernels run unchanged on the slab.  A k3 kernel computes garbage in the outermost halo row (it sees the
 buffer's zero padding instead of the neighbour's rows); after each such layer the halo rows are refreshed:
-  * interior side: the neighbour's owned rows (<= 12.6 MB per side and exchange at Middlebury: 2 rows x 2 planes x 96 x 512 x 32 ch x 2 B),
+  * interior side: the neighbour's owned rows (only the ONE row next to the cut travels, `live`: <= 6.3 MB per side and exchange at Middlebury = 2 planes x 96 x 512 x 32 ch x 2 B),
   * image border: zeros -- exactly the zero padding of the reference's convs / AvgPool3d(count_include_pad) /
     F.unfold(padding=1) -- or, for the trilinear input only, a copy of the border row (align_corners=False clamps).
 Per-pixel ops (1x1x1 convs, attention over the disparity axis, softmax + regression) keep valid halos valid.
@@ -35,6 +35,7 @@ from . import engine as E
 
 H4_HALO = 2      # halo rows at 1/4 resolution (even: keeps the stride-2 alignment)
 H8_HALO = 1      # halo rows at 1/8 resolution
+H4_LIVE = 1      # 1/4-res halo rows that are ever read for an owned output (the outer one only keeps the alignment)
 
 
 # --------------------------------------------------------------------------------------------
@@ -71,12 +72,19 @@ def owned_rows(t, world, rank, dim=2, scale=1):
 @dataclass
 class Rows:
     """Refresh the `h` halo rows at both ends of `dim` of `t` (owned rows = [h, n-h)).  Interior side: the neighbour's
-    owned rows next to the cut (only if `exchange`).  Image border: `fill` = "zero" | "replicate" | "keep"."""
+    owned rows next to the cut (only if `exchange`).  Image border: `fill` = "zero" | "replicate" | "keep" (all h rows).
+    `live`: only that many halo rows, the ones next to the owned rows, are read by any op that produces OWNED output
+    (the outer 1/4-res halo row exists for the stride-2 alignment only), so only they travel."""
     t: torch.Tensor
     dim: int
     h: int
     fill: str = "zero"
     exchange: bool = True
+    live: int = 0         # rows (next to the owned ones) that actually travel; 0 = all h
+
+    @property
+    def nlive(self):
+        return self.live or self.h
 
 
 @dataclass
@@ -98,14 +106,15 @@ def _fill_border(req: Rows, top: bool):
 
 
 def _send_rows(req: Rows, to_upper: bool):
-    """The owned rows a neighbour needs: the first h owned rows go up, the last h owned rows go down."""
-    n = req.t.shape[req.dim]
-    return req.t.narrow(req.dim, req.h if to_upper else n - 2 * req.h, req.h)
+    """The owned rows a neighbour needs: the first `live` owned rows go up, the last `live` owned rows go down."""
+    n, k = req.t.shape[req.dim], req.nlive
+    return req.t.narrow(req.dim, req.h if to_upper else n - req.h - k, k)
 
 
 def _halo_rows(req: Rows, top: bool):
-    n = req.t.shape[req.dim]
-    return req.t.narrow(req.dim, 0 if top else n - req.h, req.h)
+    """The `live` halo rows next to the owned ones."""
+    n, k = req.t.shape[req.dim], req.nlive
+    return req.t.narrow(req.dim, req.h - k if top else n - req.h, k)
 
 
 def drive_lockstep(gens):
@@ -178,7 +187,7 @@ class PeerHalo:
         for d in range(req.dim):
             outer *= t.shape[d]
         return (t.is_cuda and t.is_contiguous() and inner % 16 == 0 and t.data_ptr() % 16 == 0
-                and outer * req.h * inner <= self.slot)
+                and outer * req.nlive * inner <= self.slot)
 
     def refresh(self, req: Rows):
         """Interior sides of one exchange (the caller fills the image-border side).  Every rank must call this for the
@@ -196,10 +205,10 @@ class PeerHalo:
         up, down = r - 1, r + 1
         has_up, has_down = up >= 0, down < self.world
         st = E._stream()
-        _lib.call("dca_halo_push", t.data_ptr(), outer, rows, inner, req.h,
+        _lib.call("dca_halo_push", t.data_ptr(), outer, rows, inner, req.h, req.nlive,
                   self._slot(up, par, 1) if has_up else 0, self._slot(down, par, 0) if has_down else 0,
                   self._flag(up, 1) if has_up else 0, self._flag(down, 0) if has_down else 0, st)
-        _lib.call("dca_halo_wait_unpack", t.data_ptr(), outer, rows, inner, req.h,
+        _lib.call("dca_halo_wait_unpack", t.data_ptr(), outer, rows, inner, req.h, req.nlive,
                   self._slot(r, par, 0) if has_up else 0, self._slot(r, par, 1) if has_down else 0,
                   self._flag(r, 0) if has_up else 0, self._flag(r, 1) if has_down else 0,
                   self.epoch * self.ctas, self.ptrs[r] + 4 * self.slot + 16, st)
@@ -292,14 +301,14 @@ def _cva_steps(pk, cost, res_post=None):
     yield Rows(t.t, 3, H8_HALO + 1, fill="replicate", exchange=False)
     fused = E.up2(2, t, cost, pk.fuse_up2b_w, pk.fuse_scale, pk.fuse_shift, E.ACT_NONE, 32, cost.D, cost_down.H,
                   cost_down.W)
-    yield Rows(fused.t, 3, H4_HALO)
+    yield Rows(fused.t, 3, H4_HALO, live=H4_LIVE)
     c1 = E.conv(fused, pk.conv1, E.K3S2, E.ACT_RELU)
     yield Rows(c1.t, 3, H8_HALO)
     c2 = E.conv(c1, pk.conv2, E.K3S1, E.ACT_RELU)
     yield Rows(c2.t, 3, H8_HALO)
     fd = pk.conv3_fused
     out = E.up2(0, c2, fused, fd.w_tc, fd.scale, fd.shift, E.ACT_RELU, 64, c2.D, c2.H, c2.W, res_post=res_post)
-    yield Rows(out.t, 3, H4_HALO)
+    yield Rows(out.t, 3, H4_HALO, live=H4_LIVE)
     return logits, out
 
 
@@ -317,34 +326,35 @@ def hot_path_steps(pk: E.PackedHotPath, gwc_l, gwc_r, cat_l, cat_r, g):
             feats.append(None)
             continue
         fp = _pad_rows(E._f32c(f), H4_HALO)
-        yield Rows(fp, 2, H4_HALO)
+        yield Rows(fp, 2, H4_HALO, live=H4_LIVE)
         feats.append(fp)
     gl, gr, cl, cr, gd = feats
     # guidance/mask branch of PropgationNet_4x (`gwcnet_dca_g.py:112-115,119`); main stream in this mode
     gp = E.Planes.from_ncdhw(gd, planes=P)
     m1 = E.conv2d_tc(gp, pk.prop0_tc, E.ACT_RELU)
-    yield Rows(m1.t, 3, H4_HALO)
+    yield Rows(m1.t, 3, H4_HALO, live=H4_LIVE)
     mask = E.conv2d_tc(m1, pk.prop2_tc, E.ACT_NONE, out_fp32=True)          # per-pixel use from here on
     vol = E.fused_volume(gl, gr, cl, cr, D4, pk.num_groups, P)               # row-local; zero rows give a zero volume
     c = E.conv(vol, pk.dres0_0, E.K3S1, E.ACT_RELU)
-    yield Rows(c.t, 3, H4_HALO)
+    yield Rows(c.t, 3, H4_HALO, live=H4_LIVE)
     c = E.conv(c, pk.dres0_2, E.K3S1, E.ACT_RELU)
-    yield Rows(c.t, 3, H4_HALO)
+    yield Rows(c.t, 3, H4_HALO, live=H4_LIVE)
     r = E.conv(c, pk.dres1_0, E.K3S1, E.ACT_RELU)
-    yield Rows(r.t, 3, H4_HALO)
+    yield Rows(r.t, 3, H4_HALO, live=H4_LIVE)
     cost0 = E.conv(r, pk.dres1_2, E.K3S1, E.ACT_NONE, res_post=c)
-    yield Rows(cost0.t, 3, H4_HALO)
+    yield Rows(cost0.t, 3, H4_HALO, live=H4_LIVE)
     cur, logits2 = cost0, None
     for i, stage in enumerate(pk.cva):
         lg, cur = yield from _cva_steps(stage, cur, res_post=cost0 if i == 0 else None)
         if i + 1 == pk.pv_stage:
             logits2 = lg
     h = E.conv(cur, pk.cls3_0, E.K3S1, E.ACT_RELU)
-    yield Rows(h.t, 3, H4_HALO)
-    logits = E.conv_cout1_any(h, pk.cls3_2)               # valid on the owned rows and the halo row next to them
+    yield Rows(h.t, 3, H4_HALO, live=H4_LIVE)
+    logits = E.conv_cout1_any(h, pk.cls3_2)               # valid on the owned rows (only one halo row of h is live)
     pred_q = E.softmax_regress(logits)                    # [B,1,Hb4,W4]
-    # F.unfold(padding=1) of the reference: zero DISPARITY outside the image; interior halo row is already valid
-    yield Rows(pred_q, 2, H4_HALO, fill="zero", exchange=False)
+    # the convex upsampling reads the 3x3 neighbourhood of the regressed disparity: one row from each neighbour, and
+    # zero DISPARITY outside the image (F.unfold(padding=1) of the reference)
+    yield Rows(pred_q, 2, H4_HALO, fill="zero", live=H4_LIVE)
     pred4 = E.convex_upsample(mask, pred_q)
     Hb4 = pred_q.shape[2]
     pred4 = pred4[:, :, 4 * H4_HALO:4 * (Hb4 - H4_HALO)].contiguous()

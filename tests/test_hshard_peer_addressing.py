@@ -4,6 +4,7 @@ arrival counters, targets).  The two C-ABI calls are replaced by a ctypes emulat
 which is what the GPU does in time (a wait spins until the neighbours' pushes have landed)."""
 import ctypes
 
+import pytest
 import torch
 
 import dcanet_b200 as d
@@ -18,12 +19,12 @@ class _Emu:
 
     def call(self, name, *a):
         if name == "dca_halo_push":
-            t, outer, rows, inner, h, up_stage, down_stage, up_flag, down_flag, _ = a
-            for stage, flag, first in ((up_stage, up_flag, h), (down_stage, down_flag, rows - 2 * h)):
+            t, outer, rows, inner, h, live, up_stage, down_stage, up_flag, down_flag, _ = a
+            for stage, flag, first in ((up_stage, up_flag, h), (down_stage, down_flag, rows - h - live)):
                 if not stage:
                     continue
                 for o in range(outer):
-                    ctypes.memmove(stage + o * h * inner, t + (o * rows + first) * inner, h * inner)
+                    ctypes.memmove(stage + o * live * inner, t + (o * rows + first) * inner, live * inner)
                 c = ctypes.c_ulonglong.from_address(flag)
                 c.value += CTAS
         elif name == "dca_halo_wait_unpack":
@@ -32,13 +33,13 @@ class _Emu:
             raise AssertionError(name)
 
     def flush(self):
-        for t, outer, rows, inner, h, st_top, st_bot, f_top, f_bot, target, err, _ in self.waits:
-            for stage, flag, first in ((st_top, f_top, 0), (st_bot, f_bot, rows - h)):
+        for t, outer, rows, inner, h, live, st_top, st_bot, f_top, f_bot, target, err, _ in self.waits:
+            for stage, flag, first in ((st_top, f_top, h - live), (st_bot, f_bot, rows - h)):
                 if not stage:
                     continue
                 assert ctypes.c_ulonglong.from_address(flag).value >= target, "wait would spin forever"
                 for o in range(outer):
-                    ctypes.memmove(t + (o * rows + first) * inner, stage + o * h * inner, h * inner)
+                    ctypes.memmove(t + (o * rows + first) * inner, stage + o * live * inner, live * inner)
         self.waits = []
 
 
@@ -54,7 +55,8 @@ def _peers(world, slot):
     return peers, bufs
 
 
-def test_peer_halo_slots_counters_and_parity(monkeypatch):
+@pytest.mark.parametrize("live", [0, 1])
+def test_peer_halo_slots_counters_and_parity(monkeypatch, live):
     world, h = 3, 2
     emu = _Emu()
     monkeypatch.setattr(hs._lib, "call", emu.call)
@@ -66,12 +68,12 @@ def test_peer_halo_slots_counters_and_parity(monkeypatch):
         want = [t.clone() for t in ts]
 
         def one(t):
-            yield hs.Rows(t, 1, h, fill="keep")
+            yield hs.Rows(t, 1, h, fill="keep", live=live)
             return t
 
         want = hs.drive_lockstep([one(t) for t in want])   # the reference semantics of an exchange
         for r in range(world):
-            req = hs.Rows(ts[r], 1, h, fill="keep")
+            req = hs.Rows(ts[r], 1, h, fill="keep", live=live)
             assert ts[r].data_ptr() % 16 == 0
             peers[r].refresh(req)
         emu.flush()

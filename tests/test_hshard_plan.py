@@ -42,7 +42,7 @@ def _cva_oracle_steps(ctx, p, cost, res=None):
     yield Rows(aug_down, 3, 1, fill="replicate", exchange=False)
     aug = F.interpolate(aug_down, scale_factor=(2, 2, 2), mode="trilinear")
     fused = ctx.convbn3d(torch.cat([aug, cost], dim=1), p + ".fuse.0", 1, 0, None)
-    yield Rows(fused, 3, 2)
+    yield Rows(fused, 3, 2, live=1)
     c1 = ctx.convbn3d(fused, p + ".cost_agg.conv1.0", 2, 1, "relu")
     yield Rows(c1, 3, 1)
     c2 = ctx.convbn3d(c1, p + ".cost_agg.conv2.0", 1, 1, "relu")
@@ -52,7 +52,7 @@ def _cva_oracle_steps(ctx, p, cost, res=None):
     if res is not None:
         out = out + res
     out = out.contiguous()
-    yield Rows(out, 3, 2)
+    yield Rows(out, 3, 2, live=1)
     return logits, out
 
 
@@ -62,29 +62,29 @@ def _oracle_steps(sd, gl, gr, cl, cr, g):
     feats = []
     for f in (gl, gr, cl, cr, g):
         fp = F.pad(f, (0, 0, 2, 2)).contiguous()
-        yield Rows(fp, 2, 2)
+        yield Rows(fp, 2, 2, live=1)
         feats.append(fp)
     gl, gr, cl, cr, g = feats
     m1 = F.relu(ctx.bn(ctx.conv2d(g, "prop.conv.0.0.weight"), "prop.conv.0.1")).contiguous()
-    yield Rows(m1, 2, 2)
+    yield Rows(m1, 2, 2, live=1)
     mlog = ctx.conv2d(m1, "prop.conv.2.weight")
     vol = torch.cat([O.build_gwc_volume(gl, gr, D4, 40), O.build_concat_volume(cl, cr, D4)], dim=1)
     c = ctx.convbn3d(vol, "dres0.0", 1, 1, "relu")
-    yield Rows(c, 3, 2)
+    yield Rows(c, 3, 2, live=1)
     c = ctx.convbn3d(c, "dres0.2", 1, 1, "relu")
-    yield Rows(c, 3, 2)
+    yield Rows(c, 3, 2, live=1)
     r = ctx.convbn3d(c, "dres1.0", 1, 1, "relu")
-    yield Rows(r, 3, 2)
+    yield Rows(r, 3, 2, live=1)
     cost0 = (ctx.convbn3d(r, "dres1.2", 1, 1, None) + c).contiguous()
-    yield Rows(cost0, 3, 2)
+    yield Rows(cost0, 3, 2, live=1)
     _, out1 = yield from _cva_oracle_steps(ctx, "cva1", cost0, res=cost0)
     logits2, out2 = yield from _cva_oracle_steps(ctx, "cva2", out1)
     _, out3 = yield from _cva_oracle_steps(ctx, "cva3", out2)
     h = ctx.convbn3d(out3, "classif3.0", 1, 1, "relu")
-    yield Rows(h, 3, 2)
+    yield Rows(h, 3, 2, live=1)
     logits = ctx.conv3d(h, "classif3.2.weight", 1, 1).squeeze(1)
     pred_q = O.disparity_regression(F.softmax(logits, dim=1), D4).contiguous()
-    yield Rows(pred_q, 2, 2, fill="zero", exchange=False)
+    yield Rows(pred_q, 2, 2, fill="zero", live=1)
     B, _, H, W = pred_q.shape
     m = F.softmax(mlog.view(B, 9, 4, 4, H, W), dim=1)
     dp = F.pad(4.0 * pred_q[:, 0], (1, 1, 1, 1))
@@ -148,11 +148,28 @@ def test_rows_request_semantics_in_lockstep():
     assert out[0][0, :, 0].tolist() == [0, 0, 2, 3, 4, 5, 6, 7]
 
 
+def _poison_dead_rows(gen):
+    """Before every exchange, NaN the halo rows that do NOT travel (h - live outer rows): the result may not depend on
+    them.  (The image-border fill then zeroes them again on the outside; at interior cuts they stay NaN.)"""
+    try:
+        req = next(gen)
+        while True:
+            if isinstance(req, Rows) and req.nlive < req.h:
+                n, dead = req.t.shape[req.dim], req.h - req.nlive
+                req.t.narrow(req.dim, 0, dead).fill_(float("nan"))
+                req.t.narrow(req.dim, n - dead, dead).fill_(float("nan"))
+            x = yield req
+            req = gen.send(x)
+    except StopIteration as stop:
+        return stop.value
+
+
 @pytest.mark.parametrize("H4,world", [(16, 2), (20, 3), (16, 4)])
 def test_hsharded_plan_matches_unsharded_oracle_virtual_ranks(H4, world):
     feats, sd, ref4, refpv = _case(H4, 24)
     with torch.no_grad():
-        gens = [_oracle_steps(sd, *[hs.owned_rows(f, world, r) for f in feats]) for r in range(world)]
+        gens = [_poison_dead_rows(_oracle_steps(sd, *[hs.owned_rows(f, world, r) for f in feats]))
+                for r in range(world)]
         res = hs.drive_lockstep(gens)
     _check(torch.cat([r[0] for r in res], 2), torch.cat([r[1] for r in res], 2), ref4, refpv)
 
