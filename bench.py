@@ -256,10 +256,6 @@ def main():
     K, Wm = max(1, args.steps), max(3, args.warmup)
     net = workloads.init_bench_weights_(d.GwcNet(maxdisp, precision=args.precision), 0).to(dev).eval()
     H4, W4 = H // 4, W // 4
-    nsets = 4   # rotate input sets: 4 x 80 MB > L2, and every step streams a 368 MB volume (>> 126 MB L2)
-    host_sets = [workloads.feature_maps(100 * rank + s, B, H4, W4, pin=True) for s in range(nsets)]
-    dev_sets = [[t.to(dev, non_blocking=True) for t in hs] for hs in host_sets]
-    torch.cuda.synchronize()
 
     def barrier():
         torch.cuda.synchronize()
@@ -269,6 +265,11 @@ def main():
 
     if args.hshard:
         return run_hshard(args, d, net, dist, dev, rank, world, barrier, K, Wm)
+
+    nsets = 4   # rotate input sets: 4 x 80 MB > L2, and every step streams a 368 MB volume (>> 126 MB L2)
+    host_sets = [workloads.feature_maps(100 * rank + s, B, H4, W4, pin=True) for s in range(nsets)]
+    dev_sets = [[t.to(dev, non_blocking=True) for t in hs] for hs in host_sets]
+    torch.cuda.synchronize()
 
     if args.breakdown:
         with torch.no_grad():
