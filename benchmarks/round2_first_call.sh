@@ -15,6 +15,8 @@ if [ "$N" = "1" ]; then
   timeout 600 python bench.py > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err; echo "bench rc=$?"
   tail -c 600 gpurun_out/r2_unvalidated_tests.log
 else
+  DCA_TEST_UNVALIDATED=1 timeout 900 python -m pytest tests/test_gpu_hshard.py -q -k two_gpus \
+      > gpurun_out/r2_hshard_2gpu_tests.log 2>&1; echo "2-gpu hshard tests rc=$?"; tail -c 400 gpurun_out/r2_hshard_2gpu_tests.log
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 \
       --master-port 29511 bench.py --gpus "$N" --hshard --config middlebury_1536x2048 --steps 10 --warmup 3 \
       > gpurun_out/r2_hshard_${N}gpu.json 2> gpurun_out/r2_hshard_${N}gpu.err; echo "hshard bench rc=$?"
