@@ -9,7 +9,7 @@ if [ "$N" = "1" ]; then
   # 1. the regular parity suite must still be green (host graph was generalised to N cva stages)
   timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r2_gpu_tests.log 2>&1; echo "gpu tests rc=$?"
   # 2. opt-in tests: H-sharded kernel sequence (virtual ranks on one device) and the stage-count variants
-  DCA_TEST_UNVALIDATED=1 timeout 900 python -m pytest tests/test_gpu_hshard.py tests/test_gpu_variants.py -q \
+  DCA_TEST_UNVALIDATED=1 timeout 900 python -m pytest tests/test_gpu_hshard.py tests/test_gpu_variants.py tests/test_gpu_composites.py -q \
       > gpurun_out/r2_unvalidated_tests.log 2>&1; echo "unvalidated tests rc=$?"
   # 3. bench line of the unchanged default route
   timeout 600 python bench.py > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err; echo "bench rc=$?"

@@ -51,6 +51,10 @@ SIGNATURES = {
     "dca_planes_from_ncdhw": [_vp, _vp] + [_c_int] * 7 + [_vp],
     "dca_planes_to_ncdhw": [_vp, _c_int, _vp] + [_c_int] * 6 + [_vp],
     "dca_pack_weights": [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp],
+    "dca_conv3d_igemm": [_c_int, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _c_int, _vp, _c_int, _vp, _c_int,
+                         _c_int] + [_c_int] * 9 + [_vp],
+    "dca_pool_conv": [_vp, _vp, _vp, _vp, _vp, _vp] + [_c_int] * 7 + [_vp],
+    "dca_softmax_regress_upsample": [_vp, _vp, _vp, _vp] + [_c_int] * 4 + [_vp],
     "dca_halo_push_ctas": [],
     "dca_halo_push": [_vp, _ll, _ll, _ll, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "dca_halo_wait_unpack": [_vp, _ll, _ll, _ll, _c_int, _c_int, _vp, _vp, _vp, _vp, ctypes.c_ulonglong, _vp, _vp],

@@ -159,6 +159,22 @@ int dca_halo_wait_unpack(void* t, long long outer, long long rows, long long inn
                          const void* stage_bottom, const void* flag_top, const void* flag_bottom,
                          unsigned long long target, void* err, void* stream);
 
+/* (6) compositions under the family names of SURVEY.md section 8(b) -------------------------------- */
+/* dca_conv3d_igemm: the implicit-GEMM family (convbn_3d / Conv3d s2 / ConvTranspose3d / 1x1x1, submodule.py:121-124,
+ * cva.py:16-24): same contract as dca_conv3d_tc. */
+int dca_conv3d_igemm(int mode, const void* x, int planes_in, const void* w_tc, const float* scale, const float* shift,
+                     const void* res_pre, const void* res_post, int planes_res, const void* up, int planes_up,
+                     const void* side, int side_c, void* y, int planes_out, int act, int B, int Cin, int Cout, int Di,
+                     int Hi, int Wi, int Do, int Ho, int Wo, void* stream);
+/* dca_pool_conv: cva.downsample (cva.py:39-41) = dca_avgpool3d into the caller's `pooled` scratch, then the 3x3x3 conv +
+ * folded BN + act on it; y and pooled are [planes][B][(Di+1)/2][(Hi+1)/2][(Wi+1)/2][C]. */
+int dca_pool_conv(const void* x, void* pooled, const void* w_tc, const float* scale, const float* shift, void* y,
+                  int planes, int act, int B, int C, int Di, int Hi, int Wi, void* stream);
+/* dca_softmax_regress_upsample: gwcnet_dca_g.py:238-239 + :120-124 = dca_softmax_regress into pred_q [B,1,H,W] (kept as
+ * the 1/4-res result), then dca_convex_upsample to out [B,1,4H,4W]. */
+int dca_softmax_regress_upsample(const float* logits, const float* mask, float* pred_q, float* out, int B, int D, int H,
+                                 int W, void* stream);
+
 /* layout + parameter preparation ---------------------------------------------------------------- */
 int dca_planes_from_ncdhw(const float* x, void* y, int planes, int B, int C, int Cp, int D, int H, int W,
                           void* stream);
