@@ -196,13 +196,13 @@ def test_dropping_the_halo_refresh_is_detected():
     assert not err < 0.05, err          # (a NaN from an emptied class also counts as detected)
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, H4=16):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     import torch.distributed as dist
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(2)
-    feats, sd, ref4, refpv = _case(16, 24)
+    feats, sd, ref4, refpv = _case(H4, 24)
     with torch.no_grad():
         gen = _oracle_steps(sd, *[hs.owned_rows(f, world, rank) for f in feats])
         pred4, pv = hs.drive_distributed(gen, rank, world)
@@ -211,7 +211,9 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_hsharded_plan_over_gloo_world_size_2():
+@pytest.mark.parametrize("world,H4", [(2, 16), (3, 20)])
+def test_hsharded_plan_over_gloo(world, H4):
+    """world 3: the middle rank exchanges with both neighbours in one grouped send/recv."""
     import torch.multiprocessing as mp
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -219,13 +221,13 @@ def test_hsharded_plan_over_gloo_world_size_2():
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, H4)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted((q.get(timeout=300) for _ in procs), key=lambda r: r[0])
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    _, _, ref4, refpv = _case(16, 24)
+    _, _, ref4, refpv = _case(H4, 24)
     _check(torch.cat([torch.from_numpy(r[1]) for r in res], 2), torch.cat([torch.from_numpy(r[2]) for r in res], 2),
            ref4, refpv)
