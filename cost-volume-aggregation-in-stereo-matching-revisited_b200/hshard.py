@@ -4,8 +4,8 @@ layer that looks at neighbouring rows and one [B, D/8] sum all-reduce per cva st
 
 STATUS: host logic and exchange plan are covered on CPU (tests/test_hshard_plan.py: the drivers below run the same
 plan over the CPU checker's ATen ops, in-process with 2/3/4 virtual ranks and over gloo with world_size 2, against
-the un-sharded CPU result).  The kernel sequence `hot_path_steps` itself has NOT run on a GPU yet (the round's GPU budget was
-spent before it was written); tests/test_gpu_hshard.py holds its parity test, enabled with DCA_TEST_UNVALIDATED=1.
+the un-sharded CPU result).  The kernel sequence `hot_path_steps` is covered on the GPU by tests/test_gpu_hshard.py
+(virtual ranks on one device, and one process per GPU over both transports when >= 2 GPUs are visible).
 
 Frame of one rank.  The rank owns the 1/4-res rows [r0, r1) (both even, so its 1/8-res rows [r0/2, r1/2) align).
 Every local tensor carries halo rows: 2 at 1/4 res (buffer = global rows [r0-2, r1+2)), 1 at 1/8 res (global rows
@@ -157,7 +157,7 @@ class PeerHalo:
     compute stream, no host round trip.  Every rank owns one symmetric buffer (torch symmetric memory, peer-mapped by
     all ranks of the box): 2 parities x 2 directions of staging slots, two 64-bit arrival counters and an error word.
     Slot / counter index 0 = "arrives from ABOVE" (written by rank-1), 1 = "arrives from BELOW" (written by rank+1).
-    NOT YET RUN ON A GPU -- opt-in (`transport="p2p"`)."""
+    Opt-in (`transport="p2p"`)."""
 
     def __init__(self, rank, world, device, group=None, slot_bytes=16 << 20):
         import torch.distributed as dist
@@ -370,7 +370,7 @@ _PEERS = {}
 
 def hot_path_forward_hsharded(pk, gwc_l, gwc_r, cat_l, cat_r, g, rank, world, group=None, transport="nccl"):
     """One rank of the H-sharded forward under torch.distributed (inputs and outputs: this rank's owned rows).
-    transport: "nccl" (grouped send/recv) or "p2p" (peer-memory stores, csrc/halo_p2p.cu; not yet run on a GPU)."""
+    transport: "nccl" (grouped send/recv) or "p2p" (peer-memory stores, csrc/halo_p2p.cu)."""
     peer = None
     if transport == "p2p":
         key = (gwc_l.device.index, rank, world, id(group))

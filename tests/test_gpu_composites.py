@@ -1,13 +1,9 @@
 """The entry points named after SURVEY 8(b)'s kernel families (csrc/abi_composites.cu) against the calls they compose:
-bit-identical.  Written after the round's GPU budget ended: opt-in (DCA_TEST_UNVALIDATED=1) until seen green once."""
-import os
-
+bit-identical."""
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DCA_TEST_UNVALIDATED") != "1",
-                                 reason="composite entry points not yet run on a GPU (set DCA_TEST_UNVALIDATED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 def test_pool_conv_igemm_and_regress_upsample_equal_their_parts():

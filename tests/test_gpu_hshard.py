@@ -1,16 +1,12 @@
 """H-sharded single-pair mode on the GPU (hshard.hot_path_steps): N virtual ranks on one device against the un-sharded
-forward of the same network and against the oracle.
-
-NOT YET RUN ON A GPU: the kernel sequence was written after the round's GPU budget was spent, so this test is opt-in
-(DCA_TEST_UNVALIDATED=1) until it has been seen green once; the plan itself is verified on CPU in test_hshard_plan.py."""
+forward of the same network and against the oracle; with >= 2 GPUs also one process per GPU over both transports
+(first green on B200: round 2, 1 and 2 GPUs).  The plan itself is verified on CPU in test_hshard_plan.py."""
 import os
 
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DCA_TEST_UNVALIDATED") != "1",
-                                 reason="H-sharded kernel sequence not yet validated on a GPU (set DCA_TEST_UNVALIDATED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("world", [2, 3])

@@ -1,9 +1,7 @@
 """Stage-count variants on the GPU against fixtures made by the reference's own variant modules
-(tests/golden/make_golden_variants.py).  Same kernels as the 3-stage model; the host graph was generalised after the
-round's GPU budget was spent, so these are opt-in (DCA_TEST_UNVALIDATED=1) until seen green once.  The unchanged
+(tests/golden/make_golden_variants.py).  Same kernels as the 3-stage model, N-stage host graph.  The unchanged
 launch sequence of the default model is checked on CPU (tests/test_host_sequence.py)."""
 import importlib
-import os
 
 import pytest
 import torch
@@ -11,9 +9,7 @@ import torch
 from test_variants import VARIANTS, load_variant
 from _util import _t
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DCA_TEST_UNVALIDATED") != "1",
-                                 reason="variant graphs not yet run on a GPU (set DCA_TEST_UNVALIDATED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("n", VARIANTS)
