@@ -118,13 +118,38 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
+def common_config(cfg, n_gpus):
+    """The workload description shared, key for key, by both arms (the driver compares the dicts)."""
+    H, W, maxdisp, B = workloads.CONFIGS[cfg]
+    return {"workload": cfg, "H": H, "W": W, "maxdisp": maxdisp, "batch_per_gpu": B, "groups": 40,
+            "precision": "parity (|d disp| <= 0.05 px of the fp32 torch forward)",
+            "parallelism": f"pairs sharded over {n_gpus} GPU(s), no collective",
+            "l2": "inputs rotate over 4 feature sets (320 MB) and every step streams >3 GB of activations, both > 126 MB L2",
+            "path": "feature maps -> disparity (volume, dres0/1, 3x cva, classif3, regression, convex upsample)",
+            "algorithmic_gflop_per_pair": workloads.hot_path_flops(H, W, maxdisp) / 1e9}
+
+
+def cpu_arm(cfg, steps, warmup, budget_s):
+    """CPU arm: the reference's own torch forward from baseline/_ref when it is staged (kind "reference"), else the
+    oracle port (kind "port").  Returns (pairs/s, ms/pair, cores, kind, sample)."""
+    from baseline import reference_arm
+    if reference_arm.available() and os.environ.get("DCA_BENCH_CPU_ARM", "reference") != "port":
+        import dcanet_b200 as d
+        H, W, maxdisp, B = workloads.CONFIGS[cfg]
+        net = workloads.init_bench_weights_(d.GwcNet(maxdisp), 0)       # state_dict layout == the reference's
+        v, ms, cores, sample, _ = reference_arm.run(H, W, maxdisp, B, steps, warmup, net.state_dict(), budget_s)
+        return v, ms, cores, "reference", sample
+    v, ms, cores, sample = cpu_reference_run(cfg, steps, warmup, budget_s)
+    return v, ms, cores, "port", sample
+
+
 def cpu_reference_run(cfg, steps, warmup, budget_s=150.0):
     """The reference's CPU implementation of the path = the oracle port (torch fp32 on all host cores),
     timed on a bounded sample of the workload: an H-crop of the KITTI pair, scaled by the row fraction."""
     from oracle import dcanet_oracle as O      # checker used as the timed CPU arm ONLY here
     import dcanet_b200 as d
     H, W, maxdisp, B = workloads.CONFIGS[cfg]
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     torch.set_num_threads(cores)
     net = workloads.init_bench_weights_(d.GwcNet(maxdisp), 0)
     sd = {k: v for k, v in net.state_dict().items() if not k.startswith(("feature_extraction.", "guidance."))}
@@ -155,12 +180,25 @@ def cpu_reference_run(cfg, steps, warmup, budget_s=150.0):
     return 1.0 / t_pair, t_pair * 1e3, cores, sample
 
 
-def run_hshard(args, d, net, dist, dev, rank, world, barrier, K, Wm):
+def halo_plan_bytes(H, W, maxdisp, B, planes=2):
+    """Bytes ONE rank sends to ONE neighbour per forward in the H-sharded mode (the plan of hshard.hot_path_steps: only
+    the one live row next to a cut travels).  1/4-res 32-ch plane rows: dres0.0/2, dres1.0/2, 3 x (fused, out), classif3.0
+    = 11; 1/8-res rows: 3 x (pooled, cost_down, h: 32 ch; c1, c2: 64 ch; logits fp32); feature maps (fp32, 332 + 332 +
+    ... channels), prop m1 (128 ch) and the regressed disparity."""
+    D4, W4, D8, W8 = maxdisp // 4, W // 4, maxdisp // 8, W // 8
+    row4 = planes * B * D4 * W4 * 32 * 2
+    row8 = planes * B * D8 * W8 * 32 * 2
+    total = 11 * row4 + 3 * (3 * row8 + 2 * 2 * row8 + B * D8 * W8 * 4)
+    total += B * W4 * 4 * (320 + 320 + 12 + 12 + 64)          # fp32 feature-map rows
+    total += planes * B * W4 * 128 * 2 + B * W4 * 4          # prop m1 row, regressed disparity row
+    return total
+
+
+def measure_hshard(cfg, transport, d, net, dist, dev, rank, world, barrier, K, Wm):
     """Single-pair H-sharded mode (BASELINE configs[4]): every step is ONE pair whose 1/4-res rows are split
     over the ranks; the data path has a real exchange (halo rows with both neighbours after every k3 layer, one
-    [B, D/8] all-reduce per cva), so this is strong scaling.  Not part of the default run."""
-    assert dist is not None and world > 1, "--hshard needs torchrun with more than one rank"
-    H, W, maxdisp, B = workloads.CONFIGS[args.config]
+    [B, D/8] all-reduce per cva), so this is strong scaling.  Returns the record (valid on every rank)."""
+    H, W, maxdisp, B = workloads.CONFIGS[cfg]
     hs = d.hshard
     nsets = 2
     slabs = []
@@ -170,31 +208,54 @@ def run_hshard(args, d, net, dist, dev, rank, world, barrier, K, Wm):
         del full
     with torch.no_grad():
         for i in range(Wm):
-            net.hot_path_hsharded(*slabs[i % nsets], rank=rank, world=world, transport=args.hshard_transport)
+            net.hot_path_hsharded(*slabs[i % nsets], rank=rank, world=world, transport=transport)
         d._lib.LAUNCHES = 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        t_host0 = time.perf_counter()
         e0.record()
         for i in range(K):
-            net.hot_path_hsharded(*slabs[i % nsets], rank=rank, world=world, transport=args.hshard_transport)
+            net.hot_path_hsharded(*slabs[i % nsets], rank=rank, world=world, transport=transport)
         e1.record()
+        t_issue = time.perf_counter() - t_host0          # host time to ISSUE the K forwards (no sync inside)
         barrier()
     for peer in hs._PEERS.values():      # p2p transport: a timed-out wait (neighbour never pushed) invalidates the run
         peer.check()
-    tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    launches = d._lib.LAUNCHES
+    tt = torch.tensor([e0.elapsed_time(e1), t_issue * 1e3], dtype=torch.float64, device=dev)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt[0])
+    r0, r1 = hs.row_partition(H // 4, world)[0]
+    halo = halo_plan_bytes(H, W, maxdisp, B)
+    del slabs
+    torch.cuda.empty_cache()
+    return {"workload": cfg, "H": H, "W": W, "maxdisp": maxdisp, "batch": B, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_pair": ms / K / B, "pairs_per_s": K * B / (ms * 1e-3), "transport": transport,
+            "host_issue_ms_per_pair": float(tt[1]) / K / B,
+            "rows_per_rank": r1 - r0, "halo_rows_per_side": 2,
+            "halo_bytes_per_neighbour_per_step": halo,
+            "exchanges_per_step": 36, "allreduces_per_step": 3,
+            "nvlink_roofline_ms": halo / 770e9 * 1e3,
+            "gpu_launches": launches,
+            "algorithmic_gflop_per_pair": workloads.hot_path_flops(H, W, maxdisp) / 1e9}
+
+
+def run_hshard(args, d, net, dist, dev, rank, world, barrier, K, Wm):
+    """`--hshard`: the H-sharded mode as the whole run (strong scaling).  Not part of the default run; the default run at
+    N > 1 appends the same measurement as the `hshard` sub-record."""
+    assert dist is not None and world > 1, "--hshard needs torchrun with more than one rank"
+    rec = measure_hshard(args.config, args.hshard_transport, d, net, dist, dev, rank, world, barrier, K, Wm)
     if rank == 0:
-        ms = float(tt[0])
-        r0, r1 = hs.row_partition(H // 4, world)[0]
         print(json.dumps({
-            "metric": f"{args.config} pairs/s (one pair H-sharded over {world} GPUs)", "value": K * B / (ms * 1e-3),
-            "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True,
+            "metric": f"{args.config} pairs/s (one pair H-sharded over {world} GPUs)", "value": rec["pairs_per_s"],
+            "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": rec["ms_per_pair"],
+            "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f16x2 split operands, fp32 accumulate",
             "data": "synthetic",
-            "config": {"workload": args.config, "H": H, "W": W, "maxdisp": maxdisp, "batch": B,
-                       "parallelism": f"rows of one pair over {world} ranks: {r1 - r0} quarter-res rows + 2 halo rows "
+            "config": {"workload": args.config, "H": rec["H"], "W": rec["W"], "maxdisp": rec["maxdisp"], "batch": rec["batch"],
+                       "parallelism": f"rows of one pair over {world} ranks: {rec['rows_per_rank']} quarter-res rows + 2 halo rows "
                                       "per side each; halo rows by " + args.hshard_transport + ", 3 all-reduces of [B, D/8]"},
-            "gpu_launches": d._lib.LAUNCHES}))
+            "hshard": rec, "gpu_launches": rec["gpu_launches"]}))
     dist.destroy_process_group()
     return 0
 
@@ -213,7 +274,11 @@ def main():
     ap.add_argument("--hshard", action="store_true",
                     help="configs[4] mode: ONE pair per step, its rows split over the N ranks (halo exchange + 3 "
                          "all-reduces per forward, strong scaling); needs torchrun with N > 1")
-    ap.add_argument("--hshard-transport", default="nccl", choices=["nccl", "p2p"],
+    ap.add_argument("--latency-steps", type=int, default=200,
+                    help="extra latency loop after the K timed steps (p50/p90 in the `latency` key; 0 = skip)")
+    ap.add_argument("--no-hshard-record", action="store_true",
+                    help="N > 1: skip the H-sharded Middlebury sub-record (configs[4]) appended to the line")
+    ap.add_argument("--hshard-transport", default="p2p", choices=["nccl", "p2p"],
                     help="halo rows by NCCL send/recv or by peer-memory stores (csrc/halo_p2p.cu)")
     args = ap.parse_args()
 
@@ -229,13 +294,12 @@ def main():
         if rank != 0:
             return 0
         steps, warmup = max(1, args.steps), max(0, args.warmup)
-        v, ms, cores, sample = cpu_reference_run(args.config, steps, warmup)
+        v, ms, cores, kind, sample = cpu_arm(args.config, steps, warmup, 150.0)
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
                 "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": args.config, "H": H, "W": W, "maxdisp": maxdisp, "batch": B,
-                           "path": "feature maps -> disparity (oracle port of the reference torch forward, CPU)"},
-                "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                "config": common_config(args.config, args.gpus),
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -244,13 +308,15 @@ def main():
     assert torch.cuda.is_available(), "bench.py --impl ours needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    import dcanet_b200 as d
+    affinity0 = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    numa = d.pipeline.bind_host_to_gpu_numa(local_rank)      # before any pinned allocation (first touch)
     dist = None
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=dev)
 
-    import dcanet_b200 as d
     if args.no_tc:
         d.engine.Options.use_tc = False
     K, Wm = max(1, args.steps), max(3, args.warmup)
@@ -330,9 +396,27 @@ def main():
         e1.record(pipe.compute_stream)
         barrier()
         e2e_ms = e0.elapsed_time(e1)
-        gc.enable()
         if rank == 0:
             sampler.stop()
+
+        # ---------------- latency distribution (20 warm-up + 200 timed), extra key only ----------
+        n_lat = max(0, args.latency_steps)
+        lat = None
+        if n_lat:
+            evl = [torch.cuda.Event(enable_timing=True) for _ in range(n_lat + 1)]
+            for i in range(20):
+                net.hot_path(*dev_sets[i % nsets])
+            barrier()
+            evl[0].record()
+            for i in range(n_lat):
+                net.hot_path(*dev_sets[i % nsets])
+                evl[i + 1].record()
+            barrier()
+            ls = sorted(evl[i].elapsed_time(evl[i + 1]) / B for i in range(n_lat))
+            lat = {"steps": n_lat, "warmup": 20, "p50_ms_per_pair": ls[n_lat // 2], "p90_ms_per_pair": ls[int(0.9 * n_lat)],
+                   "p99_ms_per_pair": ls[min(n_lat - 1, int(0.99 * n_lat))], "mean_ms_per_pair": sum(ls) / n_lat,
+                   "pairs_per_s": n_lat * B / (evl[0].elapsed_time(evl[n_lat]) * 1e-3)}
+        gc.enable()
 
         # ---------------- roofline of the dominant kernel: conv3d k3 s1 32->32 at 1/4 res ----------------
         roof = None
@@ -390,6 +474,33 @@ def main():
                                         "ms_per_launch": vol_ms, "algorithmic_bytes_per_launch": vb,
                                         "peak_source": src}
 
+    # ---------------- configs[4] sub-record: one Middlebury pair H-sharded over the N ranks ----------------
+    hrec = None
+    if dist is not None and not args.no_hshard_record:
+        del dev_sets, host_sets, pipe
+        torch.cuda.empty_cache()
+        mcfg = "middlebury_1536x2048"
+        mnet = workloads.init_bench_weights_(d.GwcNet(workloads.CONFIGS[mcfg][2], precision=args.precision), 0).to(dev).eval()
+        hrec = measure_hshard(mcfg, args.hshard_transport, d, mnet, dist, dev, rank, world, barrier, 10, 3)
+        # the un-sharded time of the same pair on ONE GPU (rank 0's device; the other ranks idle), for the speed-up
+        if rank == 0:
+            fm = [t.to(dev) for t in workloads.feature_maps(0, 1, 1536 // 4, 2048 // 4)]
+            with torch.no_grad():
+                for _ in range(2):
+                    mnet.hot_path(*fm)
+                a1, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                a1.record()
+                for _ in range(5):
+                    mnet.hot_path(*fm)
+                b1.record()
+                torch.cuda.synchronize()
+            hrec["unsharded_ms_per_pair_1gpu"] = a1.elapsed_time(b1) / 5
+            hrec["speedup_vs_1gpu"] = hrec["unsharded_ms_per_pair_1gpu"] / hrec["ms_per_pair"]
+            del fm
+        del mnet
+        barrier()
+
     # max over ranks
     tt = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -404,12 +515,8 @@ def main():
                 "dtype": "f16x2 split operands (hi+lo fp16 planes, 22-bit significand), fp32 accumulate" if args.precision == "parity"
                 else "f16 operands, fp32 accumulate",
                 "data": "synthetic",
-                "config": {"workload": args.config, "H": H, "W": W, "maxdisp": maxdisp, "batch_per_gpu": B,
-                           "groups": 40, "precision": args.precision, "parallelism": f"pairs sharded over {world} GPU(s), no collective",
-                           "l2": "inputs rotate over 4 feature sets (320 MB) and every step streams >3 GB of "
-                                 "activations, both > 126 MB L2",
-                           "path": "feature maps -> disparity (volume, dres0/1, 3x cva, classif3, regression, convex upsample)",
-                           "algorithmic_gflop_per_pair": workloads.hot_path_flops(H, W, maxdisp) / 1e9},
+                "config": common_config(args.config, world),
+                "precision_mode": args.precision,
                 "clocks": sampler.summary(),
                 "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K,
@@ -417,9 +524,16 @@ def main():
                 "gpu_launches": launches,
                 "roofline": roof}
         line.update(extra)
+        if lat is not None:
+            line["latency"] = lat
+        if hrec is not None:
+            line["hshard"] = hrec
+        line["host"] = {"numa_node_bound": numa, "cpus": len(os.sched_getaffinity(0)) if affinity0 is not None else None}
+        if affinity0 is not None:
+            os.sched_setaffinity(0, affinity0)          # the CPU arm below uses every host core again
         if world == 1 and not args.no_cpu_baseline:
-            v, ms, cores, sample = cpu_reference_run(args.config, 2, 1, budget_s=25.0)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+            v, ms, cores, kind, sample = cpu_arm(args.config, 2, 1, 25.0)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
                                     "ms_per_pair": ms}
         print(json.dumps(line))
     if dist is not None:

@@ -14,10 +14,11 @@
 // Both neighbours push before they wait (stream order), so there is no cycle.  The staging slots are double buffered
 // by exchange parity on the host side: a neighbour can only overwrite slot p after it has seen this rank's NEXT push,
 // which this rank issues after its unpack of slot p (same stream).  The arrival counters only ever grow
-// (exchange number x PUSH_CTAS), so they need no reset.  A wait that exceeds ~2 s sets *err and falls through instead
-// of hanging the device.
+// (exchange number x PUSH_CTAS), so they need no reset.  A wait that exceeds the time-out (default 10 s,
+// dca_halo_set_timeout_ms) sets *err and falls through instead of hanging the device; the host checks the error word
+// after every forward (hshard.PeerHalo) and raises.
 //
-// STATUS: compiled for sm_100a, not yet run on a GPU (written after round 1's GPU budget ended).
+// STATUS: green on 2 B200 (tests/test_gpu_hshard.py, round 2); bench lines under profiles/r2_hshard_*.
 #include "dca_common.cuh"
 
 namespace dca {
@@ -68,7 +69,8 @@ __device__ __forceinline__ unsigned long long global_ns() {
 
 __global__ void __launch_bounds__(HALO_THREADS)
 halo_wait_unpack_kernel(const HaloMsg top, const HaloMsg bottom, const unsigned long long* flag_top,
-                        const unsigned long long* flag_bottom, unsigned long long target, int* err) {
+                        const unsigned long long* flag_bottom, unsigned long long target, int* err,
+                        unsigned long long timeout_ns) {
   const HaloMsg& m = blockIdx.y ? bottom : top;
   const unsigned long long* flag = blockIdx.y ? flag_bottom : flag_top;
   if (m.src == nullptr) return;
@@ -76,7 +78,7 @@ halo_wait_unpack_kernel(const HaloMsg top, const HaloMsg bottom, const unsigned 
     const unsigned long long t0 = global_ns();
     while (ld_acquire_sys(flag) < target) {
       __nanosleep(100);
-      if (global_ns() - t0 > 2000000000ULL) { atomicExch(err, 1); break; }
+      if (global_ns() - t0 > timeout_ns) { atomicExch(err, 1); break; }
     }
   }
   __syncthreads();
@@ -87,7 +89,17 @@ halo_wait_unpack_kernel(const HaloMsg top, const HaloMsg bottom, const unsigned 
 
 using namespace dca;
 
+static unsigned long long g_halo_timeout_ns = 10000000000ULL;
+
 extern "C" int dca_halo_push_ctas() { return PUSH_CTAS; }
+
+// time-out of the arrival wait (default 10 s): first-call skew between ranks (lazy module loads, weight packing) can
+// reach seconds; after it the error word is set and the forward is invalid
+extern "C" int dca_halo_set_timeout_ms(int ms) {
+  if (ms <= 0) return DCA_ERR_ARG;
+  g_halo_timeout_ns = (unsigned long long)ms * 1000000ULL;
+  return DCA_OK;
+}
 
 // The `live` owned rows next to each cut travel: rows [h, h+live) of `t` go to the upper neighbour's staging slot, rows
 // [rows-h-live, rows-h) to the lower neighbour's.  peer_*_stage / peer_*_flag: peer-mapped device addresses
@@ -132,7 +144,8 @@ extern "C" int dca_halo_wait_unpack(void* t, long long outer, long long rows, lo
   HaloMsg bottom{(const char*)stage_bottom, base + (rows - (long long)h) * inner_bytes, outer, chunk,
                  rows * inner_bytes, chunk};
   halo_wait_unpack_kernel<<<dim3(PUSH_CTAS, 2), HALO_THREADS, 0, (cudaStream_t)stream>>>(
-      top, bottom, (const unsigned long long*)flag_top, (const unsigned long long*)flag_bottom, target, (int*)err);
+      top, bottom, (const unsigned long long*)flag_top, (const unsigned long long*)flag_bottom, target, (int*)err,
+      g_halo_timeout_ns);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }

@@ -325,6 +325,12 @@ def up2(kind, x: Planes, side: Planes, w_tc, scale, shift, act, cin, dl, hl, wl,
     """dca_up2_tc: kind 0 transposed conv (+side 1x1x1), kind 1 trilinear x2 of a padded tensor + side 1x1x1,
     kind 2 bilinear x2 in (h, w) of a depth-interpolated padded tensor + side 1x1x1 (dl = OUTPUT depth)."""
     y = Planes(x.B, dl if kind == 2 else 2 * dl, 2 * hl, 2 * wl, 32, x.planes, x.t.device)
+    for name, o in (("side", side), ("res_post", res_post)):
+        # both are read at the OUTPUT resolution through tensor maps built from (dl, hl, wl): a mismatch (odd H/4 or W/4)
+        # would be silent out-of-bounds reads, where the reference raises at its torch.cat (cva.py:55)
+        if o is not None and (o.B, o.D, o.H, o.W) != (y.B, y.D, y.H, y.W):
+            raise _lib.DcaError(f"up2: {name} is {(o.B, o.D, o.H, o.W)}, the output is {(y.B, y.D, y.H, y.W)} "
+                                "(D/4, H/4 and W/4 must be even)")
     _lib.call("dca_up2_tc", kind, x.ptr, x.planes, side.ptr if side is not None else 0,
               side.C if side is not None else 0, w_tc.data_ptr(), _ptr(scale), _ptr(shift),
               res_post.ptr if res_post is not None else 0, res_post.planes if res_post is not None else 1, y.ptr, act,
@@ -436,6 +442,9 @@ class PackedCva:
         torch.cuda.current_stream().synchronize()
 
 
+FUSED_REDIR_MAX = 1.0e3     # largest |Wr * sr / s3| accepted by the fused deconv + redir pack
+
+
 class _FusedDeconv:
     """conv3 (ConvTranspose3d 64->32 + BN) and redir (1x1x1 32->32 + BN) of Multi_Aggregation as ONE GEMM:
     s3*deconv + b3 + sr*(Wr x) + br = s3*(deconv + (diag(sr/s3) Wr) x) + (b3 + br): 27 deconv taps + a 28th
@@ -450,6 +459,12 @@ def _pack_deconv_with_redir(agg, pc3, pcr, planes):
     s3, sr = pc3.scale[:32], pcr.scale[:32]
     if pc3.w_tc is None or bool((s3.abs() < 1e-12).any()):
         return None                                   # a zero BN scale cannot be divided out: keep the two kernels
+    # the rescaled redir weights go into fp16 hi/lo planes (saturating at 65504, and hi*lo products in fp32): decline when
+    # a decayed / dead BN gamma of conv3 would blow them up (real checkpoints have gammas down to 1e-8); the two-kernel
+    # route (redir as its own 1x1x1 conv, added as res_pre) has no such division
+    wr_scaled = agg.redir[0].weight.detach().float().view(32, 32) * (sr / s3).view(32, 1)
+    if not bool(torch.isfinite(wr_scaled).all()) or float(wr_scaled.abs().max()) > FUSED_REDIR_MAX:
+        return None
     lib = _lib.load()
     per_tap = lib.dca_pack_weights_tc_bytes(32, 64, 1, planes)
     buf = torch.empty(28 * per_tap, dtype=torch.uint8, device=pc3.w.device)
@@ -587,16 +602,42 @@ def _prop_mask_wait(job):
     return mask
 
 
+def check_feature_shapes(pk, gwc_l, gwc_r, cat_l, cat_r, g):
+    """The five feature maps must agree in (B, H/4, W/4); with cva stages D/4, H/4 and W/4 must be even (the reference
+    raises at `torch.cat` in cva.py:55 otherwise; here the up2 tensor maps would be built with the wrong pitches)."""
+    if gwc_l.dim() != 4 or gwc_l.shape != gwc_r.shape:
+        raise _lib.DcaError(f"gwc features must be two equal [B,C,H/4,W/4] tensors, got {tuple(gwc_l.shape)} / {tuple(gwc_r.shape)}")
+    B, _, H4, W4 = gwc_l.shape
+    if (cat_l is None) != (cat_r is None):
+        raise _lib.DcaError("concat features: both or none")
+    for name, t in (("cat_l", cat_l), ("cat_r", cat_r), ("guidance", g)):
+        if t is not None and (t.dim() != 4 or (t.shape[0], t.shape[2], t.shape[3]) != (B, H4, W4)):
+            raise _lib.DcaError(f"{name} is {tuple(t.shape)}, expected [{B}, C, {H4}, {W4}]")
+    if cat_l is not None and cat_l.shape != cat_r.shape:
+        raise _lib.DcaError("concat features differ in shape")
+    if pk.cva and (H4 % 2 or W4 % 2 or (pk.maxdisp // 4) % 2):
+        raise _lib.DcaError(f"cva needs even D/4, H/4, W/4 (got {pk.maxdisp // 4}, {H4}, {W4}): pad the images to a "
+                            "multiple of 8 (the reference's callers pad to 16, main_dca.py:153-166)")
+
+
 def hot_path_forward(pk: PackedHotPath, gwc_l, gwc_r, cat_l, cat_r, g, keep=None):
     """Feature maps -> (pred4 [B,1,H,W], prob_volume2 logits [B,D8,H8,W8]).
     Mirrors GwcNet.forward (eval) of the reference, models/gwcnet_dca_g.py:216-240,282."""
     _require_cuda(gwc_l, gwc_r, cat_l, cat_r, g)
+    check_feature_shapes(pk, gwc_l, gwc_r, cat_l, cat_r, g)
     P = pk.planes
     D4 = pk.maxdisp // 4
     side_job = _prop_mask_start(pk, _f32c(g), P)
     vol = fused_volume(_f32c(gwc_l), _f32c(gwc_r), _f32c(cat_l) if cat_l is not None else None,
                        _f32c(cat_r) if cat_r is not None else None, D4, pk.num_groups, P)
     tc0 = Options.use_tc
+    try:
+        return _hot_path_stages(pk, vol, side_job, tc0, keep)
+    finally:
+        Options.use_tc = tc0          # fp32_stages (diagnostics) toggles it per stage; never leak that into later calls
+
+
+def _hot_path_stages(pk, vol, side_job, tc0, keep):
     Options.use_tc = tc0 and "dres" not in Options.fp32_stages
     c = conv(vol, pk.dres0_0, K3S1, ACT_RELU)
     c = conv(c, pk.dres0_2, K3S1, ACT_RELU)

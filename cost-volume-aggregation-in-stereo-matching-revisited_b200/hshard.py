@@ -26,6 +26,7 @@ for single-device verification).
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import torch
@@ -171,6 +172,12 @@ class PeerHalo:
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         self.ctas = _lib.load().dca_halo_push_ctas()
         self.epoch = 0
+        ms = int(os.environ.get("DCA_HALO_TIMEOUT_MS", "10000"))
+        _lib.call("dca_halo_set_timeout_ms", ms)
+        # the error word of the arrival waits is copied to pinned host memory at the end of every forward and looked at
+        # at the start of the next one (and by check()): a timed-out wait raises instead of yielding stale halo rows
+        self._err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._err_event = None
 
     def _slot(self, r, parity, direction):
         return self.ptrs[r] + (2 * parity + direction) * self.slot
@@ -213,10 +220,29 @@ class PeerHalo:
                   self._flag(r, 0) if has_up else 0, self._flag(r, 1) if has_down else 0,
                   self.epoch * self.ctas, self.ptrs[r] + 4 * self.slot + 16, st)
 
+    def _err_word(self):
+        return self.buf[4 * self.slot + 16:4 * self.slot + 20].view(torch.int32)
+
+    def end_forward(self):
+        """Queue the copy of the error word (no synchronisation); `begin_forward` / `check` look at it."""
+        self._err_host.copy_(self._err_word(), non_blocking=True)
+        self._err_event = torch.cuda.Event()
+        self._err_event.record()
+
+    def begin_forward(self):
+        """Raises if a wait of the PREVIOUS forward timed out (its results were invalid)."""
+        if self._err_event is not None:
+            self._err_event.synchronize()        # long complete: the caller consumed that forward's results
+            self._err_event = None
+            if int(self._err_host[0]) != 0:
+                raise _lib.DcaError("H-shard peer-memory halo exchange timed out waiting for a neighbour: the previous "
+                                    "forward's results were invalid")
+
     def check(self):
         """Raises if a wait timed out (a neighbour never pushed).  Synchronises; call after the forward."""
         torch.cuda.current_stream().synchronize()
-        if int(self.buf[4 * self.slot + 16:4 * self.slot + 20].view(torch.int32).item()) != 0:
+        self._err_event = None
+        if int(self._err_word().item()) != 0:
             raise _lib.DcaError("H-shard peer-memory halo exchange timed out waiting for a neighbour")
 
 
@@ -276,8 +302,8 @@ def _require_default_route(pk):
     if not (o.use_tc and o.use_up2 and o.up2_bilinear and o.prop_on_tc and not o.fp32_stages):
         raise _lib.DcaError("the H-sharded mode runs the default tcgen05 route only (engine.Options at defaults)")
     for c in pk.cva:
-        if not c.attn.has_wa or c.conv3_fused is None or c.conv3_fused.tc_planes != pk.planes:
-            raise _lib.DcaError("the H-sharded mode needs the fused deconv+redir pack (non-zero BN scales)")
+        if not c.attn.has_wa:
+            raise _lib.DcaError("the H-sharded mode needs the fuse conv folded into the attention pack")
 
 
 def _cva_steps(pk, cost, res_post=None):
@@ -307,7 +333,13 @@ def _cva_steps(pk, cost, res_post=None):
     c2 = E.conv(c1, pk.conv2, E.K3S1, E.ACT_RELU)
     yield Rows(c2.t, 3, H8_HALO)
     fd = pk.conv3_fused
-    out = E.up2(0, c2, fused, fd.w_tc, fd.scale, fd.shift, E.ACT_RELU, 64, c2.D, c2.H, c2.W, res_post=res_post)
+    if fd is not None and fd.tc_planes == c2.planes:
+        out = E.up2(0, c2, fused, fd.w_tc, fd.scale, fd.shift, E.ACT_RELU, 64, c2.D, c2.H, c2.W, res_post=res_post)
+    else:
+        # the fused deconv + redir pack was declined (a tiny BN gamma of conv3, engine._pack_deconv_with_redir): redir as
+        # its own 1x1x1 conv (per voxel: valid halos stay valid), added before the ReLU of the transposed conv
+        redir = E.conv(fused, pk.redir, E.K1, E.ACT_NONE)
+        out = E.conv(c2, pk.conv3, E.T3S2, E.ACT_RELU, res_pre=redir, res_post=res_post)
     yield Rows(out.t, 3, H4_HALO, live=H4_LIVE)
     return logits, out
 
@@ -317,6 +349,7 @@ def hot_path_steps(pk: E.PackedHotPath, gwc_l, gwc_r, cat_l, cat_r, g):
     of the fp32 feature maps [B,C,Hl,W4].  Result: (pred4 [B,1,4*Hl,4*W4], prob_volume2 [B,D8,Hl/2,W8])."""
     E._require_cuda(gwc_l, gwc_r, cat_l, cat_r, g)
     _require_default_route(pk)
+    E.check_feature_shapes(pk, gwc_l, gwc_r, cat_l, cat_r, g)
     if gwc_l.shape[2] % 2 or gwc_l.shape[2] < 4:
         raise _lib.DcaError("a rank must own an even number (>= 4) of 1/4-resolution rows")
     P, D4 = pk.planes, pk.maxdisp // 4
@@ -376,10 +409,16 @@ def hot_path_forward_hsharded(pk, gwc_l, gwc_r, cat_l, cat_r, g, rank, world, gr
         key = (gwc_l.device.index, rank, world, id(group))
         peer = _PEERS.get(key)
         if peer is None:
+            # created AFTER the weights are packed (pk exists); its rendezvous ends with a barrier over the ranks, so the
+            # first exchange starts with every rank ready
             peer = _PEERS[key] = PeerHalo(rank, world, gwc_l.device, group)
+        peer.begin_forward()
     elif transport != "nccl":
         raise _lib.DcaError(f"unknown H-shard transport {transport!r}")
-    return drive_distributed(hot_path_steps(pk, gwc_l, gwc_r, cat_l, cat_r, g), rank, world, group, peer)
+    res = drive_distributed(hot_path_steps(pk, gwc_l, gwc_r, cat_l, cat_r, g), rank, world, group, peer)
+    if peer is not None:
+        peer.end_forward()
+    return res
 
 
 def hot_path_forward_virtual(pk, gwc_l, gwc_r, cat_l, cat_r, g, world):

@@ -148,10 +148,11 @@ int dca_convex_upsample(const float* mask, const float* disp, float* out, int B,
  * multi-GPU port of the reference would do with NCCL send/recv after every 3x3x3 layer.  `t` is viewed as
  * [outer][rows][inner_bytes]; the rank owns rows [h, rows-h) and only the `live` <= h halo rows next to them are ever read.
  * dca_halo_push stores the owned rows [h,h+live) / [rows-h-live,rows-h) into the upper / lower neighbour's staging slot (peer-mapped addresses, 0 = no neighbour) and bumps the neighbour's
- * 64-bit arrival counter by dca_halo_push_ctas(); dca_halo_wait_unpack spins (bounded, ~2 s, then *err = 1) until the
+ * 64-bit arrival counter by dca_halo_push_ctas(); dca_halo_wait_unpack spins (bounded: dca_halo_set_timeout_ms, default 10 s, then *err = 1) until the
  * own counters reach `target` and copies the staged rows into the halo rows [h-live,h) / [rows-h,rows-h+live).  Needs 16-byte aligned rows
- * (DCA_ERR_UNSUPPORTED otherwise: use the NCCL transport for that tensor).  Not yet run on a GPU. */
+ * (DCA_ERR_UNSUPPORTED otherwise: use the NCCL transport for that tensor). */
 int dca_halo_push_ctas(void);
+int dca_halo_set_timeout_ms(int ms);
 int dca_halo_push(const void* t, long long outer, long long rows, long long inner_bytes, int h, int live, void* peer_up_stage,
                   void* peer_down_stage, void* peer_up_flag, void* peer_down_flag, void* stream);
 int dca_halo_wait_unpack(void* t, long long outer, long long rows, long long inner_bytes, int h, int live,
