@@ -44,6 +44,8 @@ SIGNATURES = {
     "dca_avgpool3d": [_vp, _vp] + [_c_int] * 6 + [_vp],
     "dca_class_stats": [_vp, _vp, _vp, _vp] + [_c_int] * 4 + [_vp],
     "dca_disp_attention": [_vp, _vp, _vp, _vp, _vp, _c_int, _vp] + [_c_int] * 7 + [_vp],
+    "dca_self_attention": [_vp, _vp, _vp, _vp] + [_c_int] * 6 + [_vp],
+    "dca_regress_f32": [_vp, _vp] + [_c_int] * 4 + [_vp],
     "dca_up2_tc": [_c_int, _vp, _c_int, _vp, _c_int, _vp, _vp, _vp, _vp, _c_int, _vp, _c_int] + [_c_int] * 5 + [_vp],
     "dca_upsample_fuse": [_vp] * 6 + [_c_int] * 6 + [_vp],
     "dca_softmax_regress": [_vp, _vp] + [_c_int] * 4 + [_vp],

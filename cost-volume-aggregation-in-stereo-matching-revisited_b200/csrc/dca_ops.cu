@@ -235,7 +235,10 @@ template <int PLANES, int MT, int DT, int WPP, int CORE>
 __global__ void __launch_bounds__(CORE ? 576 : 256 * WPP)
 disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ cls, const float* __restrict__ e,
                       const float* __restrict__ S, const float* __restrict__ wts, int has_wa,
-                      __nv_bfloat16* __restrict__ y, int B, int D, int H, int Wd, int pad) {
+                      __nv_bfloat16* __restrict__ y, int B, int D, int H, int Wd, int pad,
+                      const __nv_bfloat16* __restrict__ key_feats) {
+  // key_feats != nullptr: the generic two-input form SelfAttentionBlock.forward(query_feats, key_feats)
+  // (SelfAttention_bn.py:62-98): the key rows are read from their own tensor instead of being built from (cls, e, S)
   constexpr int ROWS = 16 * MT;
   constexpr int PAIR = 2 * ROWS * AT_PITCH;                    // bf16 elements of one (hi, lo) activation pair
   constexpr int FBUF = ROWS * AT_C;                            // floats of one fp32 buffer
@@ -298,14 +301,16 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
         pf_l[r] = (PLANES == 2) ? *reinterpret_cast<const uint4*>(x + plane + off) : make_uint4(0, 0, 0, 0);
       }
     }
-    pf_kp = cls[pixn];
-    pf_e = e[pixn];
+    if (key_feats == nullptr) {
+      pf_kp = cls[pixn];
+      pf_e = e[pixn];
+    }
   };
   if (CORE) prefetch(blockIdx.x * warps + warp);
   for (int pix = blockIdx.x * warps + warp; pix < B * HW; pix += gridDim.x * warps) {
     const int b = pix / HW, p = pix % HW;
-    const int kp = CORE ? pf_kp : cls[pix];
-    const float wp = (CORE ? pf_e : e[pix]) / S[(size_t)b * D + kp];
+    const int kp = key_feats ? -1 : (CORE ? pf_kp : cls[pix]);
+    const float wp = key_feats ? 0.f : (CORE ? pf_e : e[pix]) / S[(size_t)b * D + kp];
     // ---- x (already hi/lo in HBM) -> P0 verbatim ----
     if (CORE) {
 #pragma unroll
@@ -348,6 +353,18 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
       for (int j = 0; j < 4; ++j) at_split2((f[2 * j] + g2[2 * j]) * ks, (f[2 * j + 1] + g2[2 * j + 1]) * ks, hw[j], lw[j]);
       *reinterpret_cast<uint4*>(rh) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
       *reinterpret_cast<uint4*>(rl) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+    if (key_feats != nullptr) {
+      // explicit key tensor: this warp replaces ITS rows [row0, row0 + 16*MTW) of P0 (the only rows it reads below)
+      for (int r0 = 0; r0 < 16 * MTW; r0 += 8) {
+        const int d = row0 + r0 + (lane >> 2), q = lane & 3;
+        if (d < D) {
+          const size_t off = (((size_t)b * D + d) * HW + p) * AT_C + q * 8;
+          *reinterpret_cast<uint4*>(P0 + d * AT_PITCH + q * 8) = *reinterpret_cast<const uint4*>(key_feats + off);
+          *reinterpret_cast<uint4*>(P0 + ROWS * AT_PITCH + d * AT_PITCH + q * 8) =
+              (PLANES == 2) ? *reinterpret_cast<const uint4*>(key_feats + plane + off) : make_uint4(0, 0, 0, 0);
+        }
+      }
     }
     __syncwarp();
     warp_project_mma<MTW, ROWS>(P0, Wk0, ss + 2 * 64, true, P2, nullptr, lane, row0);
@@ -784,6 +801,19 @@ softmax_regress_kernel(const float* __restrict__ logits, float* __restrict__ pre
   pred[(size_t)b * HW + p] = acc / s;
 }
 
+// disparity_regression of the reference (submodule.py:127-131) on its own: pred = sum_d d * x[d], x = whatever the
+// caller passes (probabilities in the reference's use; NOT renormalised here).  thread = pixel, fp32.
+__global__ void __launch_bounds__(256)
+regress_f32_kernel(const float* __restrict__ x, float* __restrict__ pred, int D, int HW) {
+  const int b = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const float* xp = x + (size_t)b * D * HW + p;
+  float acc = 0.f;
+  for (int d = 0; d < D; ++d) acc = fmaf(xp[(size_t)d * HW], (float)d, acc);
+  pred[(size_t)b * HW + p] = acc;
+}
+
 // ------------------------------------------------------------------------------------------------
 // convex 4x upsampling.  mask fp32 channels-last [B,H,W,144] (c = n*16 + i*4 + j), disp [B,H,W],
 // out [B,1,4H,4W].  thread = (pixel, sub-row i): softmax over the 9 neighbours for its 4 columns.
@@ -968,11 +998,11 @@ static int g_attention_team = 1;
 // D/8 == 24: 1 (default) = two warps per pixel + mma.sync attention core, 2 = two warps + fp32 FMA core, 0 = one warp
 extern "C" int dca_attention_set_team(int on) { g_attention_team = on; return DCA_OK; }
 
-extern "C" int dca_disp_attention(const void* x, const int* cls, const float* e, const float* S, const float* weights,
-                                  int has_wa, void* y, int pad, int planes, int B, int C, int D, int H, int W,
-                                  void* stream) {
+static int attention_launch(const void* x, const int* cls, const float* e, const float* S, const float* weights,
+                            int has_wa, void* y, int pad, int planes, int B, int C, int D, int H, int W,
+                            const void* key, void* stream) {
   if (pad < 0 || pad > 2) return DCA_ERR_ARG;
-  if (!x || !cls || !e || !S || !weights || !y || planes < 1 || planes > 2 || B <= 0 || D <= 0) return DCA_ERR_ARG;
+  if (!x || (!key && (!cls || !e || !S)) || !weights || !y || planes < 1 || planes > 2 || B <= 0 || D <= 0) return DCA_ERR_ARG;
   if (C != AT_C) return DCA_ERR_UNSUPPORTED;
   const int MT = (D + 15) / 16;
   if (MT > 4) return DCA_ERR_UNSUPPORTED;
@@ -992,7 +1022,7 @@ extern "C" int dca_disp_attention(const void* x, const int* cls, const float* e,
     auto kern = disp_attention_kernel<P_, MT_, DT_, WPP_, CORE_>;                                                          \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
     kern<<<grid, warps * 32 * WPP_, smem, st>>>((const __nv_bfloat16*)x, cls, e, S, weights, has_wa,              \
-                                                (__nv_bfloat16*)y, B, D, H, W, pad);                             \
+                                                (__nv_bfloat16*)y, B, D, H, W, pad, (const __nv_bfloat16*)key);   \
   } while (0)
 #define DCA_AT_LAUNCH(P_, MT_) DCA_AT_LAUNCH2(P_, MT_, 0, 1, 0)
   if (D == 24 && g_attention_team == 1) {          // two warps per pixel, tensor-core attention core
@@ -1010,6 +1040,21 @@ extern "C" int dca_disp_attention(const void* x, const int* cls, const float* e,
 #undef DCA_AT_LAUNCH2
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
+}
+
+extern "C" int dca_disp_attention(const void* x, const int* cls, const float* e, const float* S, const float* weights,
+                                  int has_wa, void* y, int pad, int planes, int B, int C, int D, int H, int W,
+                                  void* stream) {
+  return attention_launch(x, cls, e, S, weights, has_wa, y, pad, planes, B, C, D, H, W, nullptr, stream);
+}
+
+// SelfAttentionBlock.forward(query_feats, key_feats) (SelfAttention_bn.py:62-98), the generic two-input form:
+// q = Pq1(Pq0(query)), k = Pk1(Pk0(key)), v = Pv(key), out = Po(softmax(q k^T / sqrt(8)) v) per pixel over the D axis.
+// query, key, y: cost planes [P][B][D][H][W][32]; weights as for dca_disp_attention (the 7th matrix is unused).
+extern "C" int dca_self_attention(const void* query, const void* key, const float* weights, void* y, int planes, int B,
+                                  int C, int D, int H, int W, void* stream) {
+  if (!key) return DCA_ERR_ARG;
+  return attention_launch(query, nullptr, nullptr, nullptr, weights, 0, y, 0, planes, B, C, D, H, W, key, stream);
 }
 
 extern "C" int dca_upsample_fuse(const void* t, const void* cost, const float* WcT, const float* scale,
@@ -1034,6 +1079,14 @@ extern "C" int dca_softmax_regress(const float* logits, float* pred, int B, int 
   if (!logits || !pred || B <= 0 || D <= 0 || H <= 0 || W <= 0) return DCA_ERR_ARG;
   const int HW = H * W;
   softmax_regress_kernel<<<dim3((HW + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(logits, pred, D, HW);
+  DCA_RETURN_IF_LAUNCH_FAILED();
+  return DCA_OK;
+}
+
+extern "C" int dca_regress_f32(const float* x, float* pred, int B, int D, int H, int W, void* stream) {
+  if (!x || !pred || B <= 0 || D <= 0 || H <= 0 || W <= 0) return DCA_ERR_ARG;
+  const int HW = H * W;
+  regress_f32_kernel<<<dim3((HW + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(x, pred, D, HW);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }

@@ -18,13 +18,11 @@ class Multi_Aggregation(nn.Module):
         self.precision_planes = 2
 
     def forward(self, x):
+        """x fp32 [B,C,D,H,W] (even D, H, W) -> ReLU(BN(deconv(conv2(conv1 x))) + BN(redir x)) (cva.py:26-31)."""
         engine._require_cuda(x)
-        xp = engine.Planes.from_ncdhw(x, self.precision_planes)
-        c1 = engine.conv(xp, engine.pack_convbn(self.conv1[0]), engine.K3S2, engine.ACT_RELU)
-        c2 = engine.conv(c1, engine.pack_convbn(self.conv2[0]), engine.K3S1, engine.ACT_RELU)
-        redir = engine.conv(xp, engine.pack_convbn(self.redir), engine.K1, engine.ACT_NONE)
-        pc3 = engine.PackedConv(self.conv3[0].weight, self.conv3[1], transposed=True)
-        return engine.conv(c2, pc3, engine.T3S2, engine.ACT_RELU, res_pre=redir).to_ncdhw()
+        P = self.precision_planes
+        pk = engine.cached_pack(self, ("agg", P), lambda: engine.PackedAgg(self, P))
+        return engine.agg_forward(pk, engine.Planes.from_ncdhw(x, P)).to_ncdhw()
 
 
 class cva(nn.Module):
@@ -51,7 +49,8 @@ class cva(nn.Module):
         if not downsample:
             raise NotImplementedError("DCANet always calls cva with downsample=True (gwcnet_dca_g.py:228-232)")
         engine._require_cuda(cost_volume)
-        pk = engine.PackedCva(self, self.precision_planes)
+        pk = engine.cached_pack(self, ("cva", self.precision_planes),
+                                lambda: engine.PackedCva(self, self.precision_planes))
         keep = {}
         logits, out = engine.cva_forward(pk, engine.Planes.from_ncdhw(cost_volume, self.precision_planes), keep=keep)
         self.last = keep

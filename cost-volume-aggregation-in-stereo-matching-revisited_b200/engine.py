@@ -353,6 +353,36 @@ def softmax_regress(logits):
     return pred
 
 
+def regress(x):
+    """sum_d d * x[:, d] (the reference's disparity_regression on its own, submodule.py:127-131)."""
+    B, D, H, W = x.shape
+    pred = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+    _lib.call("dca_regress_f32", x.data_ptr(), pred.data_ptr(), B, D, H, W, _stream())
+    return pred
+
+
+def self_attention(q: Planes, k: Planes, weights):
+    """SelfAttentionBlock.forward(query_feats, key_feats) (SelfAttention_bn.py:62-98) on cost planes."""
+    assert (q.B, q.D, q.H, q.W, q.C, q.planes) == (k.B, k.D, k.H, k.W, k.C, k.planes)
+    y = Planes(q.B, q.D, q.H, q.W, q.C, q.planes, q.t.device)
+    _lib.call("dca_self_attention", q.ptr, k.ptr, weights.data_ptr(), y.ptr, q.planes, q.B, q.C, q.D, q.H, q.W, _stream())
+    return y
+
+
+def cached_pack(module, key, build):
+    """Pack a module's parameters for the kernels ONCE and reuse the pack until a parameter or buffer of the module is
+    replaced, moved or modified in place (data_ptr / _version signature).  The function-level API (cva, Multi_Aggregation,
+    hourglass, SemanticLevelContext, PropgationNet_4x, run_convbn_3d) goes through this, so drop-in callers do not
+    re-pack every weight on every call."""
+    sig = tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+    cache = module.__dict__.setdefault("_dca_packs", {})
+    hit = cache.get(key)
+    if hit is None or hit[0] != sig:
+        hit = cache[key] = (sig, build())
+        torch.cuda.current_stream().synchronize()      # temporaries of the packers die here
+    return hit[1]
+
+
 def convex_upsample(mask, disp):
     B, _, H, W = disp.shape
     out = torch.empty((B, 1, 4 * H, 4 * W), dtype=torch.float32, device=disp.device)
@@ -412,15 +442,11 @@ class PackedCva:
         self.fuse_c = pc_c                                # cost half of the fuse conv (+ the fuse BN)
         self.fuse_wcT = pc_c.w.view(32, 32).contiguous()  # [ci][co]
         self.fuse_scale, self.fuse_shift = pc_c.scale, pc_c.shift
-        agg = m.cost_agg
-        self.conv1 = pack_convbn(agg.conv1[0])
-        self.conv2 = pack_convbn(agg.conv2[0])
-        self.conv3 = PackedConv(agg.conv3[0].weight, agg.conv3[1], transposed=True)
-        self.redir = pack_convbn(agg.redir)
-        for pc in (self.down, self.cls0, self.conv1, self.conv2, self.redir):
+        self.agg = PackedAgg(m.cost_agg, planes)
+        self.conv1, self.conv2, self.conv3, self.redir = self.agg.conv1, self.agg.conv2, self.agg.conv3, self.agg.redir
+        self.conv3_fused = self.agg.conv3_fused
+        for pc in (self.down, self.cls0):
             pc.pack_tc(planes)
-        self.conv3.pack_tc(planes, transposed=True)
-        self.conv3_fused = _pack_deconv_with_redir(agg, self.conv3, self.redir, planes)
         # trilinear x2 + cat + fuse as a GEMM: 4 diagonal interpolation taps {27,9,3,1}/64 * I and the cost half Wc
         w5 = torch.zeros((32, 32, 5), dtype=torch.float32, device=fuse_w.device)       # [co][ci][tap]
         eye = torch.eye(32, device=fuse_w.device)
@@ -443,6 +469,44 @@ class PackedCva:
 
 
 FUSED_REDIR_MAX = 1.0e3     # largest |Wr * sr / s3| accepted by the fused deconv + redir pack
+
+
+class PackedAgg:
+    """Multi_Aggregation (cva.py:13-31): conv1 (k3 s2) -> conv2 (k3 s1) -> conv3 (transposed k3 s2) + redir (1x1x1)."""
+
+    def __init__(self, agg, planes):
+        self.conv1 = pack_convbn(agg.conv1[0])
+        self.conv2 = pack_convbn(agg.conv2[0])
+        self.conv3 = PackedConv(agg.conv3[0].weight, agg.conv3[1], transposed=True)
+        self.redir = pack_convbn(agg.redir)
+        for pc in (self.conv1, self.conv2, self.redir):
+            pc.pack_tc(planes)
+        self.conv3.pack_tc(planes, transposed=True)
+        c = agg.redir[0].weight.shape[0]
+        self.conv3_fused = _pack_deconv_with_redir(agg, self.conv3, self.redir, planes) if c == 32 else None
+
+
+def agg_forward(pk: PackedAgg, x: Planes, res_post: Planes = None, keep=None):
+    """Multi_Aggregation.forward (cva.py:26-31): ReLU(BN(conv3(conv2(conv1 x))) + BN(redir x)) (+ res_post)."""
+    c1 = conv(x, pk.conv1, K3S2, ACT_RELU)
+    c2 = conv(c1, pk.conv2, K3S1, ACT_RELU)
+    fd = pk.conv3_fused
+    if Options.use_tc and Options.use_up2 and fd is not None and fd.tc_planes == c2.planes:
+        out = up2(0, c2, x, fd.w_tc, fd.scale, fd.shift, ACT_RELU, 64, c2.D, c2.H, c2.W, res_post=res_post)
+    elif Options.use_tc and Options.fuse_redir_in_deconv and fd is not None and fd.tc_planes == c2.planes \
+            and tc_supported(T3S2, 64, 32):
+        # ReLU(BN(deconv(c2)) + BN(redir(x))) (+ res_post) as one tcgen05 GEMM with a 28th, 1x1x1 tap
+        out = Planes(c2.B, 2 * c2.D, 2 * c2.H, 2 * c2.W, 32, c2.planes, c2.t.device)
+        _lib.call("dca_conv3d_tc", T3S2, c2.ptr, c2.planes, fd.w_tc.data_ptr(), fd.scale.data_ptr(),
+                  fd.shift.data_ptr(), 0, res_post.ptr if res_post is not None else 0,
+                  res_post.planes if res_post is not None else 1, 0, 1, x.ptr, x.C, out.ptr, c2.planes,
+                  ACT_RELU, c2.B, 64, 32, c2.D, c2.H, c2.W, out.D, out.H, out.W, _stream())
+    else:
+        redir = conv(x, pk.redir, K1, ACT_NONE)
+        out = conv(c2, pk.conv3, T3S2, ACT_RELU, res_pre=redir, res_post=res_post)
+    if keep is not None:
+        keep.update(c1=c1, c2=c2)
+    return out
 
 
 class _FusedDeconv:
@@ -500,22 +564,7 @@ def cva_forward(pk: PackedCva, cost: Planes, res_post: Planes = None, keep=None)
         fused = conv(cost, pk.fuse_c, K1, ACT_NONE, up=t)
     else:
         fused = upsample_fuse(t, cost, pk.fuse_wcT, pk.fuse_scale, pk.fuse_shift)
-    c1 = conv(fused, pk.conv1, K3S2, ACT_RELU)
-    c2 = conv(c1, pk.conv2, K3S1, ACT_RELU)
-    fd = pk.conv3_fused
-    if Options.use_tc and Options.use_up2 and fd is not None and fd.tc_planes == c2.planes:
-        out = up2(0, c2, fused, fd.w_tc, fd.scale, fd.shift, ACT_RELU, 64, c2.D, c2.H, c2.W, res_post=res_post)
-    elif Options.use_tc and Options.fuse_redir_in_deconv and fd is not None and fd.tc_planes == c2.planes \
-            and tc_supported(T3S2, 64, 32):
-        # ReLU(BN(deconv(c2)) + BN(redir(fused))) (+ res_post) as one tcgen05 GEMM with a 28th, 1x1x1 tap
-        out = Planes(c2.B, 2 * c2.D, 2 * c2.H, 2 * c2.W, 32, c2.planes, c2.t.device)
-        _lib.call("dca_conv3d_tc", T3S2, c2.ptr, c2.planes, fd.w_tc.data_ptr(), fd.scale.data_ptr(),
-                  fd.shift.data_ptr(), 0, res_post.ptr if res_post is not None else 0,
-                  res_post.planes if res_post is not None else 1, 0, 1, fused.ptr, fused.C, out.ptr, c2.planes,
-                  ACT_RELU, c2.B, 64, 32, c2.D, c2.H, c2.W, out.D, out.H, out.W, _stream())
-    else:
-        redir = conv(fused, pk.redir, K1, ACT_NONE)
-        out = conv(c2, pk.conv3, T3S2, ACT_RELU, res_pre=redir, res_post=res_post)
+    out = agg_forward(pk.agg, fused, res_post=res_post)
     if keep is not None:
         keep.update(cost_down=cost_down, logits=logits, class_map=cls, e=e, S=S, t=t, fused=fused, out=out)
     return logits, out

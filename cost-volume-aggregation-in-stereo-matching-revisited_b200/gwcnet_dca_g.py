@@ -68,17 +68,31 @@ class hourglass(nn.Module):
         self.redir2 = convbn_3d(c * 2, c * 2, kernel_size=1, stride=1, pad=0)
         self.precision_planes = 2
 
-    def forward(self, x):
+    def _pack(self, planes):
         E = engine
-        xp = E.Planes.from_ncdhw(x, self.precision_planes)
-        c1 = E.conv(xp, E.pack_convbn(self.conv1[0]), E.K3S2, E.ACT_RELU)
-        c2 = E.conv(c1, E.pack_convbn(self.conv2[0]), E.K3S1, E.ACT_RELU)
-        c3 = E.conv(c2, E.pack_convbn(self.conv3[0]), E.K3S2, E.ACT_RELU)
-        c4 = E.conv(c3, E.pack_convbn(self.conv4[0]), E.K3S1, E.ACT_RELU)
-        r2 = E.conv(c2, E.pack_convbn(self.redir2), E.K1, E.ACT_NONE)
-        c5 = E.conv(c4, E.PackedConv(self.conv5[0].weight, self.conv5[1], True), E.T3S2, E.ACT_RELU, res_pre=r2)
-        r1 = E.conv(xp, E.pack_convbn(self.redir1), E.K1, E.ACT_NONE)
-        c6 = E.conv(c5, E.PackedConv(self.conv6[0].weight, self.conv6[1], True), E.T3S2, E.ACT_RELU, res_pre=r1)
+        pk = {n: E.pack_convbn(getattr(self, n)[0]) for n in ("conv1", "conv2", "conv3", "conv4")}
+        pk["redir1"], pk["redir2"] = E.pack_convbn(self.redir1), E.pack_convbn(self.redir2)
+        pk["conv5"] = E.PackedConv(self.conv5[0].weight, self.conv5[1], True)
+        pk["conv6"] = E.PackedConv(self.conv6[0].weight, self.conv6[1], True)
+        for n, pc in pk.items():      # tcgen05 operand packs where the kernels take the channel counts (32/64)
+            pc.pack_tc(planes, transposed=n in ("conv5", "conv6"))
+        return pk
+
+    def forward(self, x):
+        """x fp32 [B,C,D,H,W] (D, H, W multiples of 4) -> [B,C,D,H,W]; reference gwcnet_dca_g.py:94-106."""
+        E = engine
+        E._require_cuda(x)
+        P = self.precision_planes
+        pk = E.cached_pack(self, ("hourglass", P), lambda: self._pack(P))
+        xp = E.Planes.from_ncdhw(x, P)
+        c1 = E.conv(xp, pk["conv1"], E.K3S2, E.ACT_RELU)
+        c2 = E.conv(c1, pk["conv2"], E.K3S1, E.ACT_RELU)
+        c3 = E.conv(c2, pk["conv3"], E.K3S2, E.ACT_RELU)
+        c4 = E.conv(c3, pk["conv4"], E.K3S1, E.ACT_RELU)
+        r2 = E.conv(c2, pk["redir2"], E.K1, E.ACT_NONE)
+        c5 = E.conv(c4, pk["conv5"], E.T3S2, E.ACT_RELU, res_pre=r2)
+        r1 = E.conv(xp, pk["redir1"], E.K1, E.ACT_NONE)
+        c6 = E.conv(c5, pk["conv6"], E.T3S2, E.ACT_RELU, res_pre=r1)
         return c6.to_ncdhw()
 
 

@@ -23,6 +23,7 @@ class SelfAttentionBlock(nn.Module):
         self.out_project = self.buildproject(transform_channels, out_channels, value_out_num_convs, value_out_norm)
         self.query_downsample, self.key_downsample = query_downsample, key_downsample
         self.matmul_norm, self.transform_channels = matmul_norm, transform_channels
+        self.precision_planes = 2
 
     def buildproject(self, in_channels, out_channels, num_convs, use_norm):
         def unit(ci):
@@ -32,6 +33,15 @@ class SelfAttentionBlock(nn.Module):
         return nn.Sequential(*convs) if len(convs) > 1 else convs[0]
 
     def forward(self, query_feats, key_feats):
-        """Generic two-input form is not what DCANet calls; SemanticLevelContext drives the fused kernel
-        (key = query * class-wise scale).  Kept for API parity: key_feats must be that scaled query."""
-        raise NotImplementedError("use SemanticLevelContext.forward (fused key construction + attention)")
+        """query_feats, key_feats fp32 [B,32,D,H,W] -> context [B,32,D,H,W] (SelfAttention_bn.py:62-98): two-layer
+        query/key projections, one-layer value/out projections (1x1x1 conv + BN + LeakyReLU 0.1), 4 heads x 8 channels,
+        softmax(q k^T / sqrt(8)) v over the D axis per pixel.  DCANet itself goes through SemanticLevelContext, whose
+        kernel call builds the key from the class statistics in place; this is the generic two-input form."""
+        engine._require_cuda(query_feats, key_feats)
+        if query_feats.shape != key_feats.shape or query_feats.dim() != 5 or query_feats.shape[1] != 32:
+            raise engine._lib.DcaError("SelfAttentionBlock.forward: query and key must both be [B,32,D,H,W]")
+        P = getattr(self, "precision_planes", 2)
+        pk = engine.cached_pack(self, ("attn", P), lambda: engine.PackedAttention(self))
+        q = engine.Planes.from_ncdhw(query_feats, P)
+        k = engine.Planes.from_ncdhw(key_feats, P)
+        return engine.self_attention(q, k, pk.buf).to_ncdhw()

@@ -22,5 +22,6 @@ class SemanticLevelContext(nn.Module):
         xp = engine.Planes.from_ncdhw(x, self.precision_planes)
         cls, e, S = engine.class_stats(preds.contiguous().float())
         self.last_class_map = cls
-        pk = engine.PackedAttention(self.cross_attention)
+        pk = engine.cached_pack(self.cross_attention, ("attn", self.precision_planes),
+                                lambda: engine.PackedAttention(self.cross_attention))
         return engine.disp_attention(xp, cls, e, S, pk.buf, False).to_ncdhw()

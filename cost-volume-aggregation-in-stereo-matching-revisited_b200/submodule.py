@@ -42,12 +42,13 @@ def build_cost_planes(gwc_l, gwc_r, cat_l, cat_r, maxdisp, num_groups, planes=2)
 
 
 def disparity_regression(x, maxdisp):
-    """x = probabilities [B,D,H,W] -> [B,1,H,W]; reference models/submodule.py:127-131.
-    The kernel is softmax+regression fused; a probability input p is fed as log(p) (softmax(log p)
-    == p for a normalised p), so callers holding LOGITS should use softmax_disparity_regression."""
+    """x [B,D,H,W] -> sum_d d * x[:, d] as [B,1,H,W]; reference models/submodule.py:127-131 (x is NOT renormalised:
+    un-normalised input gives the same un-normalised result as the reference).  Callers holding LOGITS should use
+    softmax_disparity_regression (softmax fused, the probability volume never exists)."""
     assert len(x.shape) == 4
     assert x.shape[1] == maxdisp
-    return engine.softmax_regress(torch.log(x.contiguous().float().clamp_min(1e-38)))
+    engine._require_cuda(x)
+    return engine.regress(x.contiguous().float())
 
 
 def softmax_disparity_regression(logits, maxdisp):
@@ -76,7 +77,12 @@ def run_convbn_3d(seq, x, act=engine.ACT_NONE, planes=2):
     conv = seq[0]
     k, s = conv.kernel_size[0], conv.stride[0]
     mode = {(3, 1): engine.K3S1, (3, 2): engine.K3S2, (1, 1): engine.K1}[(k, s)]
-    y = engine.conv(engine.Planes.from_ncdhw(x, planes), engine.pack_convbn(seq), mode, act)
+
+    def build():
+        pc = engine.pack_convbn(seq)
+        pc.pack_tc(planes)
+        return pc
+    y = engine.conv(engine.Planes.from_ncdhw(x, planes), engine.cached_pack(seq, ("convbn", planes), build), mode, act)
     return y.to_ncdhw()
 
 
@@ -199,9 +205,17 @@ class PropgationNet_4x(nn.Module):
     def forward(self, guidance, disp):
         engine._require_cuda(guidance, disp)
         P = self.precision_planes
-        p0 = engine.pack_convbn(self.conv[0])
-        p2 = engine.PackedConv(self.conv[2].weight)
         gp = engine.Planes.from_ncdhw(guidance.contiguous().float(), planes=P)
-        m1 = engine.conv(gp, p0, engine.C2D3, engine.ACT_RELU)
-        mask = engine.conv(m1, p2, engine.C2D3, engine.ACT_NONE, out_fp32=True)
+        if engine.Options.use_tc and engine.Options.prop_on_tc and self.base_channels in (64, 128):
+            # the two 3x3 Conv2d on the halo-slab tcgen05 kernel (the route GwcNet.forward takes)
+            p0, p2 = engine.cached_pack(self, ("prop_tc", P), lambda: (
+                engine.PackedConv2dTc(self.conv[0][0].weight, self.conv[0][1], P),
+                engine.PackedConv2dTc(self.conv[2].weight, None, P)))
+            m1 = engine.conv2d_tc(gp, p0, engine.ACT_RELU)
+            mask = engine.conv2d_tc(m1, p2, engine.ACT_NONE, out_fp32=True)
+        else:
+            p0, p2 = engine.cached_pack(self, ("prop_direct", P), lambda: (
+                engine.pack_convbn(self.conv[0]), engine.PackedConv(self.conv[2].weight)))
+            m1 = engine.conv(gp, p0, engine.C2D3, engine.ACT_RELU)
+            mask = engine.conv(m1, p2, engine.C2D3, engine.ACT_NONE, out_fp32=True)
         return engine.convex_upsample(mask, disp.contiguous().float())

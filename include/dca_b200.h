@@ -135,12 +135,18 @@ int dca_class_stats(const float* logits, int* cls, float* e, float* S, int B, in
  *          replicated (input of dca_up2_tc kind 2). */
 int dca_disp_attention(const void* x, const int* cls, const float* e, const float* S, const float* weights,
                        int has_wa, void* y, int pad, int planes, int B, int C, int D, int H, int W, void* stream);
+/* SelfAttentionBlock.forward(query_feats, key_feats) (models/augment/SelfAttention_bn.py:62-98), the generic two-input
+ * form: query, key, y = cost planes [planes][B][D][H][W][32]; weights as above (the 7th matrix is not used). */
+int dca_self_attention(const void* query, const void* key, const float* weights, void* y, int planes, int B, int C,
+                       int D, int H, int W, void* stream);
 /* y = scale * (trilinear_x2(t) + WcT^T cost) + shift ; t at (Dl,Hl,Wl), cost / y at twice that. */
 int dca_upsample_fuse(const void* t, const void* cost, const float* WcT, const float* scale, const float* shift,
                       void* y, int planes, int B, int C, int Dl, int Hl, int Wl, void* stream);
 
 /* (4) regression + convex upsampling ------------------------------------------------------------ */
 int dca_softmax_regress(const float* logits, float* pred, int B, int D, int H, int W, void* stream);
+/* disparity_regression on its own (models/submodule.py:127-131): pred[b,h,w] = sum_d d * x[b,d,h,w], x not renormalised. */
+int dca_regress_f32(const float* x, float* pred, int B, int D, int H, int W, void* stream);
 int dca_convex_upsample(const float* mask, const float* disp, float* out, int B, int H, int W, void* stream);
 
 /* (5) H-sharded single-pair mode: halo rows over NVLink peer memory ------------------------------ */

@@ -70,16 +70,59 @@ def test_hot_path_kitti_full_size_matches_oracle(seed):
     planes / single-accumulator version of the kernels exceeded the per-pixel tolerance)"""
     import dcanet_b200 as d
     O, feats, sd = _config1(H4=96, W4=312, maxdisp=192, seed=seed)
+    col = {}
     with torch.no_grad():
-        ref4, refpv = O.hot_path(sd, *feats, maxdisp=192)
+        ref4, refpv = O.hot_path(sd, *feats, maxdisp=192, collect=col)
     net = _load_into(d.GwcNet(192), sd).cuda().eval()
+    keep = {}
     with torch.no_grad():
         pred4, pv2 = net.hot_path(*[f.cuda() for f in feats])
+        pred4k, _ = net.hot_path(*[f.cuda() for f in feats], keep=keep)
+    assert torch.equal(pred4, pred4k)
+    for s in (1, 2, 3):      # north_star: the argmax disparity-class masks must match EXACTLY, at full size too
+        assert torch.equal(keep[f"cva{s}"]["class_map"].cpu().long(), col[f"cva{s}.class_map"]), f"cva{s} mask"
     dd = (pred4.cpu() - ref4).abs()
     print("KITTI full-size parity: max %.4f mean %.5f px" % (float(dd.max()), float(dd.mean())))
     assert pred4.shape == (1, 1, 384, 1248) and pv2.shape == (1, 24, 48, 156)
     assert float(dd.max()) <= TOL_MAX and float(dd.mean()) <= TOL_MEAN
     assert float((pv2.cpu() - refpv).abs().max()) < 1e-2 * float(refpv.abs().max())
+
+
+@pytest.mark.parametrize("H4,W4,maxdisp", [(32, 80, 240), (16, 112, 384)])
+def test_hot_path_other_disparity_ranges(H4, W4, maxdisp):
+    """maxdisp 240 (D/8 = 30) and the Middlebury disparity range 384 (D/8 = 48) on small crops: the attention kernel's
+    generic templates (its mma.sync core is specialised for D/8 == 24), the march kernel's ragged last depth chunk and
+    D/4 > W/4 - shift columns of the volume."""
+    import dcanet_b200 as d
+    O, feats, sd = _config1(H4=H4, W4=W4, maxdisp=maxdisp, seed=4)
+    col = {}
+    with torch.no_grad():
+        ref4, refpv = O.hot_path(sd, *feats, maxdisp=maxdisp, collect=col)
+    net = _load_into(d.GwcNet(maxdisp), sd).cuda().eval()
+    keep = {}
+    with torch.no_grad():
+        pred4, pv2 = net.hot_path(*[f.cuda() for f in feats], keep=keep)
+    for s in (1, 2, 3):
+        assert torch.equal(keep[f"cva{s}"]["class_map"].cpu().long(), col[f"cva{s}.class_map"]), f"cva{s} mask"
+    dd = (pred4.cpu() - ref4).abs()
+    print("maxdisp %d parity: max %.4f mean %.5f px" % (maxdisp, float(dd.max()), float(dd.mean())))
+    assert pv2.shape == (1, maxdisp // 8, H4 // 2, W4 // 2)
+    assert float(dd.max()) <= TOL_MAX and float(dd.mean()) <= TOL_MEAN
+    assert float((pv2.cpu() - refpv).abs().max()) < 1e-2 * float(refpv.abs().max())
+
+
+def test_odd_quarter_res_shapes_are_rejected():
+    """H/4 or W/4 odd: the reference raises at torch.cat (cva.py:55); here DcaError before any launch."""
+    import dcanet_b200 as d
+    import workloads
+    net = workloads.init_bench_weights_(d.GwcNet(48), 0).cuda().eval()
+    f = [t.cuda() for t in workloads.feature_maps(0, 1, 10, 13)]
+    with pytest.raises(d._lib.DcaError):
+        net.hot_path(*f)
+    f = [t.cuda() for t in workloads.feature_maps(0, 1, 10, 12)]
+    f[4] = f[4][:, :, :8].contiguous()
+    with pytest.raises(d._lib.DcaError):
+        net.hot_path(*f)
 
 
 def test_fast_mode_tracks_bf16_emulated_oracle():
