@@ -71,12 +71,19 @@ avgpool3d_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict_
 // logits fp32 [B,D,H,W].  thread = pixel (coalesced along w for every d).
 // ------------------------------------------------------------------------------------------------
 constexpr int CS_MAXD = 256;
+// S[b,k] is summed in 2^-40 FIXED POINT (64-bit integer atomics, shared then global): integer addition is associative, so
+// the result does not depend on the order in which pixels / CTAs arrive -- two runs of the same forward are bit-identical
+// (a float atomicAdd version differed in the last bit from run to run).  e_p = exp(P[k_p]) lies in (1, e], sums stay
+// below 2^58 for any image the path can hold.  The last CTA to finish (ticket) converts the sums to fp32.
+constexpr float CS_FIX = 1099511627776.0f;   // 2^40
 __global__ void __launch_bounds__(256)
 class_stats_kernel(const float* __restrict__ logits, int* __restrict__ cls, float* __restrict__ e_out,
-                   float* __restrict__ S, int D, int HW) {
-  __shared__ float s_sum[CS_MAXD];
+                   float* __restrict__ S, unsigned long long* __restrict__ acc /* [B*D] sums + [1] ticket, zeroed */,
+                   int D, int HW, int BD) {
+  __shared__ unsigned long long s_sum[CS_MAXD];
+  __shared__ int s_last;
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < D; i += blockDim.x) s_sum[i] = 0.f;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) s_sum[i] = 0ull;
   __syncthreads();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p < HW) {
@@ -93,11 +100,25 @@ class_stats_kernel(const float* __restrict__ logits, int* __restrict__ cls, floa
     float e = expf(best);
     cls[(size_t)b * HW + p] = k;
     e_out[(size_t)b * HW + p] = e;
-    atomicAdd(&s_sum[k], e);
+    atomicAdd(&s_sum[k], __float2ull_rn(e * CS_FIX));
   }
   __syncthreads();
   for (int i = threadIdx.x; i < D; i += blockDim.x)
-    if (s_sum[i] != 0.f) atomicAdd(&S[(size_t)b * D + i], s_sum[i]);
+    if (s_sum[i] != 0ull) atomicAdd(&acc[(size_t)b * D + i], s_sum[i]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long t = atomicAdd(&acc[BD], 1ull);
+    s_last = (t == (unsigned long long)gridDim.x * gridDim.y - 1ull);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int i = threadIdx.x; i < BD; i += blockDim.x) {
+      const unsigned long long v = *reinterpret_cast<volatile unsigned long long*>(&acc[i]);
+      S[i] = (float)((double)v * (1.0 / 1099511627776.0));
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -983,13 +1004,17 @@ extern "C" int dca_avgpool3d(const void* x, void* y, int planes, int B, int C, i
   return DCA_OK;
 }
 
-extern "C" int dca_class_stats(const float* logits, int* cls, float* e, float* S, int B, int D, int H, int W,
-                               void* stream) {
-  if (!logits || !cls || !e || !S || B <= 0 || D <= 0 || D > CS_MAXD || H <= 0 || W <= 0) return DCA_ERR_ARG;
+extern "C" int dca_class_stats(const float* logits, int* cls, float* e, float* S, void* scratch, int B, int D, int H,
+                               int W, void* stream) {
+  // scratch: (B*D + 1) x 8 bytes, 8-byte aligned (fixed-point sums + ticket); zeroed here
+  if (!logits || !cls || !e || !S || !scratch || ((uintptr_t)scratch & 7) || B <= 0 || D <= 0 || D > CS_MAXD || H <= 0 ||
+      W <= 0)
+    return DCA_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  if (cudaMemsetAsync(S, 0, (size_t)B * D * sizeof(float), st) != cudaSuccess) return DCA_ERR_LAUNCH;
+  if (cudaMemsetAsync(scratch, 0, ((size_t)B * D + 1) * sizeof(unsigned long long), st) != cudaSuccess) return DCA_ERR_LAUNCH;
   const int HW = H * W;
-  class_stats_kernel<<<dim3((HW + 255) / 256, B), 256, 0, st>>>(logits, cls, e, S, D, HW);
+  class_stats_kernel<<<dim3((HW + 255) / 256, B), 256, 0, st>>>(logits, cls, e, S, (unsigned long long*)scratch, D, HW,
+                                                                B * D);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }

@@ -303,7 +303,9 @@ def class_stats(logits):
     cls = torch.empty((B, H, W), dtype=torch.int32, device=dev)
     e = torch.empty((B, H, W), dtype=torch.float32, device=dev)
     S = torch.empty((B, D), dtype=torch.float32, device=dev)
-    _lib.call("dca_class_stats", logits.data_ptr(), cls.data_ptr(), e.data_ptr(), S.data_ptr(), B, D, H, W, _stream())
+    scratch = torch.empty(B * D + 1, dtype=torch.int64, device=dev)     # fixed-point sums + ticket (order-independent)
+    _lib.call("dca_class_stats", logits.data_ptr(), cls.data_ptr(), e.data_ptr(), S.data_ptr(), scratch.data_ptr(), B, D,
+              H, W, _stream())
     return cls, e, S
 
 

@@ -127,8 +127,10 @@ int dca_tc_set_trunc_comp(float kappa);
 
 /* (2) DCA module ------------------------------------------------------------------------------- */
 int dca_avgpool3d(const void* x, void* y, int planes, int B, int C, int Di, int Hi, int Wi, void* stream);
-/* logits fp32 [B,D,H,W] -> class map int32 [B,H,W], e = exp(P[k_p]) [B,H,W], S [B,D] (zeroed here). */
-int dca_class_stats(const float* logits, int* cls, float* e, float* S, int B, int D, int H, int W, void* stream);
+/* logits fp32 [B,D,H,W] -> class map int32 [B,H,W], e = exp(P[k_p]) [B,H,W], S [B,D].  S is summed in 64-bit fixed
+ * point (order-independent: two runs are bit-identical); scratch = (B*D + 1) x 8 bytes, 8-byte aligned, zeroed here. */
+int dca_class_stats(const float* logits, int* cls, float* e, float* S, void* scratch, int B, int D, int H, int W,
+                    void* stream);
 /* weights: 7 x [32][32] transposed (q0,q1,k0,k1,v,o,Wa) then 6 x (scale[32],shift[32]). */
 /* pad = 1: y is [planes][B][D+2][H+2][W+2][C] with a replicated 1-voxel border (input of dca_up2_tc kind 1).
  * pad = 2: y is [planes][B][2D][H+2][W+2][C]: already interpolated x2 along depth (align_corners=False), h/w borders
