@@ -32,6 +32,8 @@ SIGNATURES = {
     "dca_pack_weights_tc_march": [_vp, _c_int, _vp, _c_int, _vp],
     "dca_pack_weights_tc_march_bytes": [_c_int] * 2,
     "dca_conv1_taps_tc": [_vp, _c_int, _vp, _vp] + [_c_int] * 5 + [_vp],
+    "dca_conv3d_tc_taps27": [_vp, _c_int, _vp, _c_int, _vp, _vp, _vp, _vp, _c_int] + [_c_int] * 5 + [_vp],
+    "dca_tap_gather_softmax_regress": [_vp, _vp, _vp] + [_c_int] * 4 + [_vp],
     "dca_tap_gather3d": [_vp, _vp] + [_c_int] * 4 + [_vp],
     "dca_conv2d_tc": [_vp, _c_int, _vp, _vp, _vp, _vp, _c_int, _c_int] + [_c_int] * 5 + [_vp],
     "dca_pack_weights_tc2d": [_vp, _c_int, _c_int, _vp, _c_int, _vp],

@@ -262,6 +262,21 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
   const int mn = p.march_n;
   const int my_march = mn ? ((total_tiles > (int)blockIdx.x) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0) : 0;
   const int n_items = mn ? my_march * mn : (p.cls_inner ? my_tiles * p.ncls : total_tiles);
+  if (mn) {
+    // march mode: clear this thread's slice of every accumulator plane once; afterwards a plane is cleared again right after
+    // it has been drained (below) and handed back through ITS OWN mbarrier tempty[j], so the MMA warp starts the next
+    // work item while the last planes of this one are still in the epilogue (no per-item drain bubble)
+    const uint32_t zaddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * 16;
+    for (int jj = 0; jj < mn; ++jj) {
+      tmem_st16_zero(zaddr + 32 * jj);
+      if (PLANES == 2) tmem_st16_zero(zaddr + MARCH_CORR + 32 * jj);     // correction block (hi.Wlo + lo.Whi)
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0)
+      for (int jj = 0; jj < mn; ++jj) mbar_arrive(&tempty[jj]);
+  }
   for (int item = (mn ? 0 : first); item < n_items; item += (mn ? 1 : step), ++it) {
     int r, cls, mj = 0, mwi = 0;
     if (mn) { cls = 0; mwi = fast_divmod(item, mn, p.inv_ncls, mj); r = (int)blockIdx.x + mwi * (int)gridDim.x; }
@@ -274,18 +289,6 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
     const int b = fast_divmod(r, p.Dt, p.inv_Dt, td);
     const uint32_t acc = it & 1;
     const int ty = th * TC_TH + hh, tx = tw * TC_TW + ww;
-    if (mn && mj == 0) {
-      // new work item: clear this thread's slice of the accumulator window, then tell the MMA warp (tempty[0])
-      const uint32_t zaddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * 16;
-      for (int jj = 0; jj < mn; ++jj) {
-        tmem_st16_zero(zaddr + 32 * jj);
-        if (PLANES == 2) tmem_st16_zero(zaddr + MARCH_CORR + 32 * jj);     // correction block (hi.Wlo + lo.Whi)
-      }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[0]);
-    }
     int oz = mn ? td * mn + mj : td * (p.out_stride_d ? p.out_stride_d : p.out_stride) + p.cls_off[cls][0],
         oy = ty * p.out_stride + p.cls_off[cls][1],
         ox = tx * p.out_stride + p.cls_off[cls][2];
@@ -360,6 +363,14 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
       }
+      if (mn) {                        // plane drained: clear this thread's slice of it and hand it back (tempty[mj])
+        tmem_st16_zero(taddr);
+        if (PLANES == 2) tmem_st16_zero(taddr + MARCH_CORR);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[mj]);
+      }
       if (valid && !(p.dbg & 1)) {
         const size_t off = off0 + c0;
         const int cb = c0 + half * 16;
@@ -418,6 +429,136 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
           if (PLANES == 2 && p.planes_out == 2) stg256(p.y + p.y_plane + off, lw);
         }
       }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ fused tail: conv(32ch, BN, ReLU) -> Conv3d(32 -> 1, k3)
+// classif3 (gwcnet_dca_g.py:166-168) and cva.classify (cva.py:51-53) are a 3x3x3 conv to 32 channels followed by a 3x3x3
+// conv to ONE channel.  The second conv is linear in its 27 taps: logit[v] = sum_tap P[tap][v + off(tap)] with
+// P[tap][v] = sum_c w27[tap][c] * h[v][c].  The first conv's epilogue holds h[v][0..32) of one voxel in the registers of
+// one thread (fp32, BEFORE any rounding to 16-bit planes), so it computes the 27 per-tap products right there on the
+// CUDA cores (864 FFMA per voxel, weights as constant-bank operands: they are launch parameters) and stores P (fp32,
+// tap-major [27][B*D*H*W]) INSTEAD of h: h is never written to or re-read from HBM, and the separate per-tap GEMM launch
+// (conv_tc_kernel<32,32>, 4.5 % tensor pipe) disappears.  dca_tap_gather_* (dca_ops.cu) then sums the shifted taps.
+// Thread = voxel with all 32 channels; the two sets of four epilogue warps (TMEM lane quarters 0..3 each) alternate over
+// output planes (march kernel) / tiles (halo kernel).
+struct TapW { float w[27 * 32]; };      // [tap = (kd*3+kh)*3+kw][ci]
+struct NoTapW { int unused; };
+template <int TAPS> struct TapArg { typedef NoTapW type; };
+template <> struct TapArg<1> { typedef TapW type; };
+
+template <int PLANES>
+__device__ __forceinline__ void taps_load_act(uint32_t t_main, uint32_t t_corr, float comp, const float* s_scale,
+                                              const float* s_shift, int act, float* v) {
+  uint32_t rh[32];
+  tmem_ld32(t_main, rh);
+  if (PLANES == 2) {
+    uint32_t rl[32];
+    tmem_ld32(t_corr, rl);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(rh[j]), comp, __uint_as_float(rl[j]));
+  } else {
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rh[j]) * comp;
+  }
+  const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
+  const float4* sh4 = reinterpret_cast<const float4*>(s_shift);
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 a = sc4[j4], c = sh4[j4];
+    v[4 * j4 + 0] = apply_act(fmaf(v[4 * j4 + 0], a.x, c.x), act); v[4 * j4 + 1] = apply_act(fmaf(v[4 * j4 + 1], a.y, c.y), act);
+    v[4 * j4 + 2] = apply_act(fmaf(v[4 * j4 + 2], a.z, c.z), act); v[4 * j4 + 3] = apply_act(fmaf(v[4 * j4 + 3], a.w, c.w), act);
+  }
+}
+
+__device__ __forceinline__ void taps_store(const float* v, const TapW& tw, float* __restrict__ P, size_t nvox, size_t vox) {
+#pragma unroll
+  for (int t = 0; t < 27; ++t) {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; c += 2) {
+      a0 = fmaf(v[c], tw.w[t * 32 + c], a0);
+      a1 = fmaf(v[c + 1], tw.w[t * 32 + c + 1], a1);
+    }
+    P[(size_t)t * nvox + vox] = a0 + a1;
+  }
+}
+
+template <int PLANES>
+__device__ __forceinline__ void tc_epilogue_taps(const TcParams& p, const TapW& tw, int total_tiles, uint32_t tmem_base,
+                                                 uint64_t* tfull, uint64_t* tempty, const float* s_scale,
+                                                 const float* s_shift, int warp, int lane) {
+  constexpr int COUT = 32;
+  const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) are reachable from this warp
+  const int set = (warp - 2) >> 2;              // which half of the planes / tiles this warp drains
+  const int row = quarter * 32 + lane;
+  const int hh = row / TC_TW, ww = row % TC_TW;
+  const int mn = p.march_n;
+  const size_t nvox = (size_t)p.B * p.Do * p.Ho * p.Wo;
+  float* __restrict__ Pout = reinterpret_cast<float*>(p.y);
+  const float comp = p.cls_comp[0];
+  const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+  const int my_items = (total_tiles > (int)blockIdx.x) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  if (mn) {
+    // clear the accumulator planes this thread drains (all 32 columns of its lanes) once; afterwards each plane is cleared
+    // right after it has been drained and handed back through its own mbarrier (rolling: no per-item drain bubble)
+    for (int jj = set; jj < mn; jj += 2) {
+      const uint32_t z = lane_base + (uint32_t)(32 * (mn - 1 - jj));
+      tmem_st16_zero(z); tmem_st16_zero(z + 16);
+      if (PLANES == 2) { tmem_st16_zero(z + MARCH_CORR); tmem_st16_zero(z + MARCH_CORR + 16); }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0)
+      for (int jj = set; jj < mn; jj += 2) mbar_arrive(&tempty[jj]);
+    for (int wi = 0; wi < my_items; ++wi) {
+      int r = (int)blockIdx.x + wi * (int)gridDim.x, tw_, th, td;
+      r = fast_divmod(r, p.tiles_w, p.inv_tiles_w, tw_);
+      r = fast_divmod(r, p.tiles_h, p.inv_tiles_h, th);
+      const int b = fast_divmod(r, p.Dt, p.inv_Dt, td);
+      const int ty = th * TC_TH + hh, tx = tw_ * TC_TW + ww;
+      for (int mj = set; mj < mn; mj += 2) {
+        const int oz = td * mn + mj;
+        const bool valid = (ty < p.Ho) && (tx < p.Wo) && (oz < p.Do);
+        const size_t vox = (((size_t)b * p.Do + oz) * p.Ho + ty) * p.Wo + tx;
+        mbar_wait(&tfull[mj], (uint32_t)(wi & 1));
+        tc_fence_after();
+        const uint32_t ta = lane_base + (uint32_t)(32 * (mn - 1 - mj));
+        float v[32];
+        taps_load_act<PLANES>(ta, ta + MARCH_CORR, comp, s_scale, s_shift, p.act, v);
+        // plane drained: clear it and hand it back to the MMA warp (its own mbarrier, 4 arrivals: this set of warps)
+        tmem_st16_zero(ta); tmem_st16_zero(ta + 16);
+        if (PLANES == 2) { tmem_st16_zero(ta + MARCH_CORR); tmem_st16_zero(ta + MARCH_CORR + 16); }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[mj]);
+        if (valid) taps_store(v, tw, Pout, nvox, vox);
+      }
+    }
+  } else {
+    for (int it = set; it < my_items; it += 2) {
+      int r = (int)blockIdx.x + it * (int)gridDim.x, tw_, th, td;
+      r = fast_divmod(r, p.tiles_w, p.inv_tiles_w, tw_);
+      r = fast_divmod(r, p.tiles_h, p.inv_tiles_h, th);
+      const int b = fast_divmod(r, p.Dt, p.inv_Dt, td);
+      const int ty = th * TC_TH + hh, tx = tw_ * TC_TW + ww;
+      const bool valid = (ty < p.Ho) && (tx < p.Wo) && (td < p.Do);
+      const size_t vox = (((size_t)b * p.Do + td) * p.Ho + ty) * p.Wo + tx;
+      const uint32_t acc = (uint32_t)(it & 1);
+      mbar_wait(&tfull[acc], (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const uint32_t ta = lane_base + acc * (uint32_t)(PLANES * COUT);
+      float v[32];
+      taps_load_act<PLANES>(ta, ta + COUT, comp, s_scale, s_shift, p.act, v);
+      tc_fence_before();                         // all TMEM reads of this tile are done: hand the buffer back
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);  // (barrier count 4: one set of warps drains a tile)
+      if (valid) taps_store(v, tw, Pout, nvox, vox);
     }
   }
 }
@@ -596,9 +737,10 @@ __device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, uint32_t sbo_b
          (layout << 61);
 }
 
-template <int CIN, int COUT, int PLANES>
+template <int CIN, int COUT, int PLANES, int TAPS = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
+                    const __grid_constant__ typename TapArg<TAPS>::type tw) {
   using Cfg = HaloCfg<CIN, COUT, PLANES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -625,7 +767,7 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
     for (int i = 0; i < Cfg::W_SLOTS; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TAPS ? 4 : 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tmap(&maps.a[0]);
     prefetch_tmap(&maps.w);
@@ -737,7 +879,8 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       }
     }
   } else {
-    tc_epilogue<COUT, PLANES>(p, total_tiles, tmem_base, tfull, tempty, s_scale, s_shift, warp, lane);
+    if constexpr (TAPS) tc_epilogue_taps<PLANES>(p, tw, total_tiles, tmem_base, tfull, tempty, s_scale, s_shift, warp, lane);
+    else tc_epilogue<COUT, PLANES>(p, total_tiles, tmem_base, tfull, tempty, s_scale, s_shift, warp, lane);
   }
 
   tc_fence_before();
@@ -1171,9 +1314,10 @@ struct MarchCfg {
   static constexpr int SMEM_BYTES = A_SLOTS * A_SLOT + W_BYTES_TOTAL + 1024 + 512 + 2 * COUT * 4;
 };
 
-template <int CIN, int PLANES>
+template <int CIN, int PLANES, int TAPS = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_march_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+conv_tc_march_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
+                     const __grid_constant__ typename TapArg<TAPS>::type tw) {
   using Cfg = MarchCfg<CIN, PLANES>;
   constexpr int COUT = Cfg::COUT;
   extern __shared__ uint8_t smem_raw[];
@@ -1186,8 +1330,8 @@ conv_tc_march_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   uint64_t* wfull = aempty + Cfg::A_SLOTS;       // [W_SLOTS]
   uint64_t* wempty = wfull + Cfg::W_SLOTS;       // [W_SLOTS]
   uint64_t* oready = wempty + Cfg::W_SLOTS;      // [MAXN] output plane j of the current item is complete
-  uint64_t* tzero = oready + Cfg::MAXN;          // [1]    accumulator window cleared for the next item
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tzero + 1);
+  uint64_t* pzero = oready + Cfg::MAXN;          // [MAXN] accumulator plane j drained and cleared for the next item
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pzero + Cfg::MAXN);
   float* s_scale = reinterpret_cast<float*>(w_base + Cfg::W_BYTES_TOTAL + 512);
   float* s_shift = s_scale + COUT;
 
@@ -1202,8 +1346,7 @@ conv_tc_march_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
     for (int i = 0; i < Cfg::W_SLOTS; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
-    for (int i = 0; i < Cfg::MAXN; ++i) mbar_init(&oready[i], 1);
-    mbar_init(tzero, 8);
+    for (int i = 0; i < Cfg::MAXN; ++i) { mbar_init(&oready[i], 1); mbar_init(&pzero[i], TAPS ? 4 : 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tmap(&maps.a[0]);
     prefetch_tmap(&maps.w);
@@ -1265,10 +1408,12 @@ conv_tc_march_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       uint32_t sa = 0, pa = 0, sw = 0, pw = 0, wi = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++wi) {
         const int ch = (item / (p.tiles_w * p.tiles_h)) % p.Dt;
-        mbar_wait(tzero, wi & 1);                  // accumulator window cleared by the epilogue warps
-        tc_fence_after();
 #pragma unroll 1
         for (int sidx = 0; sidx < n + 2; ++sidx) {
+          if (sidx < n) {                          // slab sidx is the first to write output plane sidx of this item:
+            mbar_wait(&pzero[sidx], wi & 1);       // drained (previous item) and cleared by the epilogue warps
+            tc_fence_after();
+          }
           const int dprime = ch * n - 1 + sidx;
           // output index inside the chunk fed through kd: j = sidx - kd, must lie in [0, n)
           const int kd_lo = max(0, sidx - n + 1), kd_hi = min(2, sidx);
@@ -1323,7 +1468,8 @@ conv_tc_march_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       }
     }
   } else {
-    tc_epilogue<COUT, PLANES>(p, total_items, tmem_base, oready, tzero, s_scale, s_shift, warp, lane);
+    if constexpr (TAPS) tc_epilogue_taps<PLANES>(p, tw, total_items, tmem_base, oready, pzero, s_scale, s_shift, warp, lane);
+    else tc_epilogue<COUT, PLANES>(p, total_items, tmem_base, oready, pzero, s_scale, s_shift, warp, lane);
   }
 
   tc_fence_before();
@@ -1352,8 +1498,9 @@ __global__ void pack_weight_tc_march_kernel(const float* __restrict__ w, int Ci,
   }
 }
 
-template <int CIN, int PLANES>
-static int launch_tc_march(const TcMaps& maps, const TcParams& p, cudaStream_t st) {
+template <int CIN, int PLANES, int TAPS = 0>
+static int launch_tc_march(const TcMaps& maps, const TcParams& p, cudaStream_t st,
+                           const typename TapArg<TAPS>::type* tw = nullptr) {
   using Cfg = MarchCfg<CIN, PLANES>;
   static_assert(Cfg::A_SLOTS >= 2 && Cfg::W_SLOTS >= 1, "smem plan");
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "smem plan");
@@ -1363,12 +1510,13 @@ static int launch_tc_march(const TcMaps& maps, const TcParams& p, cudaStream_t s
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
   }
-  cudaFuncSetAttribute(conv_tc_march_kernel<CIN, PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_march_kernel<CIN, PLANES, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   const int total = p.B * p.Dt * p.tiles_h * p.tiles_w;
   const int grid = total < g_num_sms ? total : g_num_sms;
   TcParams q = p; fill_recips(q);
   for (int c = 0; c < 8; ++c) fill_comp(q, c, 27 * (CIN / 16));
-  conv_tc_march_kernel<CIN, PLANES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, q);
+  typename TapArg<TAPS>::type none{};
+  conv_tc_march_kernel<CIN, PLANES, TAPS><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, q, tw ? *tw : none);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }
@@ -1479,8 +1627,9 @@ static int launch_tc_s2slab(const TcMaps& maps, const TcParams& p, cudaStream_t 
   return DCA_OK;
 }
 
-template <int CIN, int COUT, int PLANES>
-static int launch_tc_halo(const TcMaps& maps, const TcParams& p, cudaStream_t st) {
+template <int CIN, int COUT, int PLANES, int TAPS = 0>
+static int launch_tc_halo(const TcMaps& maps, const TcParams& p, cudaStream_t st,
+                          const typename TapArg<TAPS>::type* tw = nullptr) {
   using Cfg = HaloCfg<CIN, COUT, PLANES>;
   static_assert(Cfg::A_SLOTS >= 2 && Cfg::W_SLOTS >= 1, "smem plan");
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "smem plan");
@@ -1490,13 +1639,14 @@ static int launch_tc_halo(const TcMaps& maps, const TcParams& p, cudaStream_t st
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
   }
-  cudaFuncSetAttribute(conv_tc_halo_kernel<CIN, COUT, PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaFuncSetAttribute(conv_tc_halo_kernel<CIN, COUT, PLANES, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        Cfg::SMEM_BYTES);
   const int total = p.B * p.Dt * p.tiles_h * p.tiles_w;
   const int grid = total < g_num_sms ? total : g_num_sms;
   TcParams q = p; fill_recips(q);
   for (int c = 0; c < 8; ++c) fill_comp(q, c, q.nslab * 9 * (CIN / 16));
-  conv_tc_halo_kernel<CIN, COUT, PLANES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, q);
+  typename TapArg<TAPS>::type none{};
+  conv_tc_halo_kernel<CIN, COUT, PLANES, TAPS><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, q, tw ? *tw : none);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }
@@ -1991,4 +2141,47 @@ extern "C" int dca_conv3d_tc_march(const void* x, int planes, const void* w_marc
   if (!make_w_map(&maps.w, w_march, Cin, 9 * P * 3 * Cout, P * 3 * Cout)) return DCA_ERR_LAUNCH;
   if (Cin == 32) return P == 2 ? launch_tc_march<32, 2>(maps, p, st) : launch_tc_march<32, 1>(maps, p, st);
   return P == 2 ? launch_tc_march<64, 2>(maps, p, st) : launch_tc_march<64, 1>(maps, p, st);
+}
+
+// Conv3d k3 s1 p1 (Cin in {32,64} -> 32) + BN + activation, immediately followed by Conv3d(32 -> 1, k3, p1, no bias):
+//   P[tap][v] = sum_c w27[tap][c] * act(scale * conv(x, w)[v][c] + shift)      fp32, tap-major [27][B*D*H*W]
+// (classif3 gwcnet_dca_g.py:166-168, cva.classify cva.py:51-53).  The 32-channel intermediate is never stored.
+// use_march = 1: depth-marching kernel (w = dca_pack_weights_tc_march), else the halo-slab kernel (w = dca_pack_weights_tc).
+// w27_host: HOST pointer to [27][32] fp32 (becomes launch parameters).  dca_tap_gather_* turn P into logits / disparity.
+extern "C" int dca_conv3d_tc_taps27(const void* x, int planes, const void* w, int use_march, const float* scale,
+                                    const float* shift, const float* w27_host, float* P, int act, int B, int Cin, int D,
+                                    int H, int W, void* stream) {
+  if (!x || !w || !w27_host || !P || B <= 0 || planes < 1 || planes > 2 || D <= 0 || H <= 0 || W <= 0) return DCA_ERR_ARG;
+  if (Cin != 32 && Cin != 64) return DCA_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Pn = planes, Cout = 32;
+  TcMaps maps;
+  TcParams p;
+  TapW tw;
+  memcpy(tw.w, w27_host, sizeof(tw.w));
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.Do = D; p.Ho = H; p.Wo = W;
+  p.scale = scale; p.shift = shift;
+  p.y = (__nv_bfloat16*)P; p.planes_out = Pn; p.act = act; p.dbg = g_dbg;
+  p.ldc = Cout; p.cout_valid = Cout;
+  p.Ht = H; p.Wt = W; p.out_stride = 1; p.ncls = 1;
+  p.tiles_w = (W + TC_TW - 1) / TC_TW; p.tiles_h = (H + TC_TH - 1) / TC_TH;
+  if (!make_act_map(&maps.a[0], x, Cin, W, H, D, Pn * B, (size_t)Cin, (size_t)W * Cin, (size_t)H * W * Cin,
+                    (size_t)D * H * W * Cin, HB_W, HB_H))
+    return DCA_ERR_LAUNCH;
+  for (int i = 1; i < 9; ++i) maps.a[i] = maps.a[0];
+  if (use_march) {
+    const int nmax = Pn == 2 ? 8 : 16;
+    const int n = D < nmax ? D : nmax;
+    p.march_n = n;
+    p.Dt = (D + n - 1) / n;
+    if (!make_w_map(&maps.w, w, Cin, 9 * Pn * 3 * Cout, Pn * 3 * Cout)) return DCA_ERR_LAUNCH;
+    if (Cin == 32) return Pn == 2 ? launch_tc_march<32, 2, 1>(maps, p, st, &tw) : launch_tc_march<32, 1, 1>(maps, p, st, &tw);
+    return Pn == 2 ? launch_tc_march<64, 2, 1>(maps, p, st, &tw) : launch_tc_march<64, 1, 1>(maps, p, st, &tw);
+  }
+  p.nslab = 3; p.slab_dz[0] = -1; p.slab_dz[1] = 0; p.slab_dz[2] = 1;
+  p.Dt = D; p.ntaps = 27; p.cls_tap0[0] = 0; p.cls_tap0[1] = 27;
+  if (!make_w_map(&maps.w, w, Cin, 27 * Pn * Cout, Pn * Cout)) return DCA_ERR_LAUNCH;
+  if (Cin == 32) return Pn == 2 ? launch_tc_halo<32, 32, 2, 1>(maps, p, st, &tw) : launch_tc_halo<32, 32, 1, 1>(maps, p, st, &tw);
+  return Pn == 2 ? launch_tc_halo<64, 32, 2, 1>(maps, p, st, &tw) : launch_tc_halo<64, 32, 1, 1>(maps, p, st, &tw);
 }

@@ -951,30 +951,102 @@ __global__ void fold_bn_kernel(const float* __restrict__ gamma, const float* __r
 __global__ void __launch_bounds__(256)
 tap_gather3d_kernel(const float* __restrict__ P, float* __restrict__ out, int B, int D, int H, int W) {
   const size_t nvox = (size_t)B * D * H * W;
+  const int HW = H * W;
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
     const int w = (int)(v % W);
     size_t r = v / W;
     const int h = (int)(r % H); r /= H;
     const int d = (int)(r % D);
-    float acc = 0.f;
+    // unconditional, independent loads (an out-of-volume tap reads the centre voxel and is multiplied by 0)
+    float val[27];
 #pragma unroll
     for (int kd = 0; kd < 3; ++kd) {
-      const int dz = d + kd - 1;
-      if (dz < 0 || dz >= D) continue;
+      const bool okd = (d + kd - 1 >= 0) && (d + kd - 1 < D);
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
-        const int hy = h + kh - 1;
-        if (hy < 0 || hy >= H) continue;
+        const bool okh = okd && (h + kh - 1 >= 0) && (h + kh - 1 < H);
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-          const int wx = w + kw - 1;
-          if (wx < 0 || wx >= W) continue;
-          const long long nb = (long long)v + ((long long)(kd - 1) * H + (kh - 1)) * W + (kw - 1);
-          acc += __ldg(P + (size_t)((kd * 3 + kh) * 3 + kw) * nvox + nb);
+          const bool ok = okh && (w + kw - 1 >= 0) && (w + kw - 1 < W);
+          const long long nb = ok ? ((long long)(kd - 1) * HW + (kh - 1) * W + (kw - 1)) : 0ll;
+          val[(kd * 3 + kh) * 3 + kw] = __ldg(P + (size_t)((kd * 3 + kh) * 3 + kw) * nvox + v + nb) * (ok ? 1.f : 0.f);
         }
       }
     }
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 27; ++t) acc += val[t];
     out[v] = acc;
+  }
+}
+
+// Fused tail of classif3 (gwcnet_dca_g.py:235-239): logit[d] = 27-tap shifted sum of P (as tap_gather3d), then
+// softmax over d and disparity regression -- the logits and the probability volume never reach HBM.
+// Block = 32 w-columns x DG disparity groups of one image row; a thread walks its disparity chunk with an online
+// softmax (running max / sum / weighted sum), the DG partial states of a pixel are merged through shared memory.
+// Every load is coalesced along w.  logits_out (optional): the summed logits [B,D,H,W] (stage-count variants with no
+// cva stage return them).
+constexpr int TG_DG = 16;
+__global__ void __launch_bounds__(32 * TG_DG)
+tap_gather_softmax_regress_kernel(const float* __restrict__ P, float* __restrict__ pred, float* __restrict__ logits_out,
+                                  int B, int D, int H, int W) {
+  __shared__ float s_m[TG_DG][32], s_s[TG_DG][32], s_a[TG_DG][32];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int w = blockIdx.x * 32 + lane, h = blockIdx.y, b = blockIdx.z;
+  const size_t nvox = (size_t)B * D * H * W;
+  const int chunk = (D + TG_DG - 1) / TG_DG;
+  const int d0 = g * chunk, d1 = min(D, d0 + chunk);
+  float m = -INFINITY, sum = 0.f, acc = 0.f;
+  if (w < W) {
+    // in-plane validity of the 9 (kh, kw) neighbours and their clamped offsets (an invalid tap reads the centre voxel,
+    // its value is discarded): the 27 loads of a voxel are UNCONDITIONAL and independent, so they are all in flight
+    // together (a branch per tap serialised one DRAM latency per load)
+    float ok9[9];
+    int off9[9];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const bool ok = (h + kh - 1 >= 0) && (h + kh - 1 < H) && (w + kw - 1 >= 0) && (w + kw - 1 < W);
+        ok9[kh * 3 + kw] = ok ? 1.f : 0.f;
+        off9[kh * 3 + kw] = ok ? (kh - 1) * W + (kw - 1) : 0;
+      }
+    const int HW = H * W;
+    for (int d = d0; d < d1; ++d) {
+      const size_t v = (((size_t)b * D + d) * H + h) * W + w;
+      float val[27];
+#pragma unroll
+      for (int kd = 0; kd < 3; ++kd) {
+        const bool okd = (d + kd - 1 >= 0) && (d + kd - 1 < D);
+        const float* base = P + (size_t)(kd * 9) * nvox + v + (okd ? (long long)(kd - 1) * HW : 0ll);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) val[kd * 9 + t] = __ldg(base + (size_t)t * nvox + off9[t]) * (okd ? ok9[t] : 0.f);
+      }
+      float logit = 0.f;
+#pragma unroll
+      for (int t = 0; t < 27; ++t) logit += val[t];
+      if (logits_out) logits_out[v] = logit;
+      const float mn = fmaxf(m, logit);
+      const float corr = expf(m - mn), ev = expf(logit - mn);      // first step: exp(-inf) = 0
+      sum = sum * corr + ev;
+      acc = acc * corr + ev * (float)d;
+      m = mn;
+    }
+  }
+  s_m[g][lane] = m; s_s[g][lane] = sum; s_a[g][lane] = acc;
+  __syncthreads();
+  if (g == 0 && w < W) {
+    float M = s_m[0][lane];
+#pragma unroll
+    for (int i = 1; i < TG_DG; ++i) M = fmaxf(M, s_m[i][lane]);
+    float S = 0.f, A = 0.f;
+#pragma unroll
+    for (int i = 0; i < TG_DG; ++i) {
+      const float sc = (s_s[i][lane] > 0.f) ? expf(s_m[i][lane] - M) : 0.f;     // empty chunks carry m = -inf, s = 0
+      S = fmaf(s_s[i][lane], sc, S);
+      A = fmaf(s_a[i][lane], sc, A);
+    }
+    pred[((size_t)b * H + h) * W + w] = A / S;
   }
 }
 
@@ -1129,6 +1201,17 @@ extern "C" int dca_tap_gather3d(const float* P, float* out, int B, int D, int H,
   if (!P || !out || B <= 0 || D <= 0 || H <= 0 || W <= 0) return DCA_ERR_ARG;
   const size_t total = (size_t)B * D * H * W;
   tap_gather3d_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(P, out, B, D, H, W);
+  DCA_RETURN_IF_LAUNCH_FAILED();
+  return DCA_OK;
+}
+
+// P fp32 tap-major [27][B*D*H*W] (dca_conv3d_tc_taps27 / dca_conv1_taps_tc) -> pred [B,H,W] = sum_d d softmax_d(logits),
+// logits = 27-tap shifted sum of P; logits_out optional ([B,D,H,W]).  Replaces tap_gather3d + softmax_regress.
+extern "C" int dca_tap_gather_softmax_regress(const float* P, float* pred, float* logits_out, int B, int D, int H, int W,
+                                              void* stream) {
+  if (!P || !pred || B <= 0 || D <= 0 || H <= 0 || W <= 0 || H > 65535 || B > 65535) return DCA_ERR_ARG;
+  tap_gather_softmax_regress_kernel<<<dim3((W + 31) / 32, H, B), 32 * TG_DG, 0, (cudaStream_t)stream>>>(P, pred,
+                                                                                                    logits_out, B, D, H, W);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }

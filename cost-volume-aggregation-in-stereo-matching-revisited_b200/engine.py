@@ -146,6 +146,7 @@ class Options:
     prop_side_stream = os.environ.get("DCA_SIDE_STREAM", "1") != "0"
     fp32_stages = frozenset()     # diagnostics: stages whose convs run on the fp32 CUDA-core kernel: {'dres', 'cva', 'cls3'}
     use_up2 = True                # class-wise halo-slab kernel for the transposed conv and the trilinear fuse stage
+    fuse_tail = True              # conv(32ch)+BN+ReLU -> Conv3d(32->1): per-tap products from the first conv's epilogue
 
 
 def conv(x: Planes, pc: PackedConv, mode=K3S1, act=ACT_NONE, res_pre: Planes = None, res_post: Planes = None,
@@ -279,6 +280,41 @@ def conv_cout1_any(x: Planes, pc):
         _lib.call("dca_tap_gather3d", P.data_ptr(), y.data_ptr(), x.B, x.D, x.H, x.W, _stream())
         return y
     return conv_cout1(x, pc.host if isinstance(pc, PackedCout1) else pc)
+
+
+def conv_taps27(x: Planes, pc: PackedConv, pc1: "PackedCout1", act=ACT_RELU):
+    """act(BN(conv3x3x3(x)))  ->  per-tap products of the Conv3d(32 -> 1, k3) that follows, straight from the first conv's
+    epilogue: fp32 P [27, B, D, H, W] (tap-major), or None when the fused kernel does not apply (the caller then runs the
+    two convs separately)."""
+    if not (Options.use_tc and Options.fuse_tail and pc.cout == 32 and pc.cin in (32, 64) and pc.taps == 27
+            and pc.tc_planes == x.planes and pc1.host.shape == (27, 32)):
+        return None
+    march = (Options.use_march and pc.w_march is not None
+             and x.B * ((x.D + 15) // 16) * ((x.H + 15) // 16) * ((x.W + 7) // 8) >= Options.march_min_items)
+    w = pc.w_march if march else pc.w_tc
+    if w is None:
+        return None
+    P = torch.empty((27, x.B, x.D, x.H, x.W), dtype=torch.float32, device=x.t.device)
+    _lib.call("dca_conv3d_tc_taps27", x.ptr, x.planes, w.data_ptr(), int(march), _ptr(pc.scale), _ptr(pc.shift),
+              pc1.host.data_ptr(), P.data_ptr(), act, x.B, pc.cin, x.D, x.H, x.W, _stream())
+    return P
+
+
+def tap_gather(P):
+    """27-tap shifted sum: P [27,B,D,H,W] -> logits [B,D,H,W]."""
+    _, B, D, H, W = P.shape
+    y = torch.empty((B, D, H, W), dtype=torch.float32, device=P.device)
+    _lib.call("dca_tap_gather3d", P.data_ptr(), y.data_ptr(), B, D, H, W, _stream())
+    return y
+
+
+def tap_gather_softmax_regress(P, want_logits=False):
+    """P [27,B,D,H,W] -> (pred [B,1,H,W], logits [B,D,H,W] or None): shifted sum + softmax + regression in one kernel."""
+    _, B, D, H, W = P.shape
+    pred = torch.empty((B, 1, H, W), dtype=torch.float32, device=P.device)
+    logits = torch.empty((B, D, H, W), dtype=torch.float32, device=P.device) if want_logits else None
+    _lib.call("dca_tap_gather_softmax_regress", P.data_ptr(), pred.data_ptr(), _ptr(logits), B, D, H, W, _stream())
+    return pred, logits
 
 
 def pack_cout1(weight):
@@ -547,8 +583,12 @@ def cva_forward(pk: PackedCva, cost: Planes, res_post: Planes = None, keep=None)
     """cva.forward(downsample=True): returns (logits fp32 [B,D8,H8,W8], augmented cost Planes)."""
     pooled = avgpool(cost)
     cost_down = conv(pooled, pk.down, K3S1, ACT_RELU)
-    h = conv(cost_down, pk.cls0, K3S1, ACT_RELU)
-    logits = conv_cout1_any(h, pk.cls2)
+    P27 = conv_taps27(cost_down, pk.cls0, pk.cls2)
+    if P27 is not None:
+        logits = tap_gather(P27)
+    else:
+        h = conv(cost_down, pk.cls0, K3S1, ACT_RELU)
+        logits = conv_cout1_any(h, pk.cls2)
     cls, e, S = class_stats(logits)
     use_up2 = Options.use_tc and Options.use_up2 and pk.attn.has_wa
     bil = use_up2 and Options.up2_bilinear
@@ -704,9 +744,14 @@ def _hot_path_stages(pk, vol, side_job, tc0, keep):
         if i + 1 == pk.pv_stage:
             logits2 = lg
     Options.use_tc = tc0 and "cls3" not in Options.fp32_stages
-    h = conv(cur, pk.cls3_0, K3S1, ACT_RELU)
-    logits = conv_cout1_any(h, pk.cls3_2)
-    pred_q = softmax_regress(logits)
+    P27 = conv_taps27(cur, pk.cls3_0, pk.cls3_2)
+    if P27 is not None:
+        # the head's logits are only an OUTPUT when there is no cva stage (gwcnet_dca0_g.py:190) or when a caller keeps them
+        pred_q, logits = tap_gather_softmax_regress(P27, want_logits=(not pk.cva) or keep is not None)
+    else:
+        h = conv(cur, pk.cls3_0, K3S1, ACT_RELU)
+        logits = conv_cout1_any(h, pk.cls3_2)
+        pred_q = softmax_regress(logits)
     Options.use_tc = tc0
     mask = _prop_mask_wait(side_job)
     pred4 = convex_upsample(mask, pred_q)

@@ -313,9 +313,14 @@ def _cva_steps(pk, cost, res_post=None):
     yield Rows(pooled.t, 3, H8_HALO)
     cost_down = E.conv(pooled, pk.down, E.K3S1, E.ACT_RELU)
     yield Rows(cost_down.t, 3, H8_HALO)
-    h = E.conv(cost_down, pk.cls0, E.K3S1, E.ACT_RELU)
-    yield Rows(h.t, 3, H8_HALO)
-    logits = E.conv_cout1_any(h, pk.cls2)                      # fp32 [B, D8, Hb8, W8]
+    P27 = E.conv_taps27(cost_down, pk.cls0, pk.cls2)           # fused tail: per-tap products [27, B, D8, Hb8, W8]
+    if P27 is not None:
+        yield Rows(P27, 3, H8_HALO)                            # (they are a per-voxel function of the conv's output rows)
+        logits = E.tap_gather(P27)                             # fp32 [B, D8, Hb8, W8]
+    else:
+        h = E.conv(cost_down, pk.cls0, E.K3S1, E.ACT_RELU)
+        yield Rows(h.t, 3, H8_HALO)
+        logits = E.conv_cout1_any(h, pk.cls2)
     yield Rows(logits, 2, H8_HALO)
     cls, e, _ = E.class_stats(logits)                           # per pixel, halo rows included
     own = logits[:, :, H8_HALO:logits.shape[2] - H8_HALO].contiguous()
@@ -381,10 +386,15 @@ def hot_path_steps(pk: E.PackedHotPath, gwc_l, gwc_r, cat_l, cat_r, g):
         lg, cur = yield from _cva_steps(stage, cur, res_post=cost0 if i == 0 else None)
         if i + 1 == pk.pv_stage:
             logits2 = lg
-    h = E.conv(cur, pk.cls3_0, E.K3S1, E.ACT_RELU)
-    yield Rows(h.t, 3, H4_HALO, live=H4_LIVE)
-    logits = E.conv_cout1_any(h, pk.cls3_2)               # valid on the owned rows (only one halo row of h is live)
-    pred_q = E.softmax_regress(logits)                    # [B,1,Hb4,W4]
+    P27 = E.conv_taps27(cur, pk.cls3_0, pk.cls3_2)
+    if P27 is not None:
+        yield Rows(P27, 3, H4_HALO, live=H4_LIVE)
+        pred_q, logits = E.tap_gather_softmax_regress(P27, want_logits=not pk.cva)     # [B,1,Hb4,W4]
+    else:
+        h = E.conv(cur, pk.cls3_0, E.K3S1, E.ACT_RELU)
+        yield Rows(h.t, 3, H4_HALO, live=H4_LIVE)
+        logits = E.conv_cout1_any(h, pk.cls3_2)           # valid on the owned rows (only one halo row of h is live)
+        pred_q = E.softmax_regress(logits)                # [B,1,Hb4,W4]
     # the convex upsampling reads the 3x3 neighbourhood of the regressed disparity: one row from each neighbour, and
     # zero DISPARITY outside the image (F.unfold(padding=1) of the reference)
     yield Rows(pred_q, 2, H4_HALO, fill="zero", live=H4_LIVE)

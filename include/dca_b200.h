@@ -95,6 +95,18 @@ int dca_up2_tc(int kind, const void* x, int planes, const void* side, int side_c
 int dca_conv1_taps_tc(const void* x, int planes, const void* w_tc, float* P, int ntap, int B, int D, int H, int W,
                       void* stream);
 int dca_tap_gather3d(const float* P, float* out, int B, int D, int H, int W, void* stream);
+/* Fused tail, first half: Conv3d k3 s1 p1 (Cin in {32,64} -> 32) + BN + activation whose epilogue immediately applies
+ * the Conv3d(32 -> 1, k3) that follows it in classif3 (gwcnet_dca_g.py:166-168) / cva.classify (cva.py:51-53) tap by tap:
+ *   P[tap][v] = sum_c w27[tap][c] * act(scale * conv(x, w)[v][c] + shift)   (fp32, tap-major [27][B*D*H*W]).
+ * The 32-channel intermediate never reaches HBM.  use_march = 1: depth-marching kernel, w = dca_pack_weights_tc_march
+ * pack; 0: halo-slab kernel, w = dca_pack_weights_tc pack.  w27_host is a HOST pointer ([27][32] fp32, launch params). */
+int dca_conv3d_tc_taps27(const void* x, int planes, const void* w, int use_march, const float* scale, const float* shift,
+                         const float* w27_host, float* P, int act, int B, int Cin, int D, int H, int W, void* stream);
+/* Fused tail, second half: logits = 27-tap shifted sum of P, softmax over D, disparity regression
+ * (gwcnet_dca_g.py:235-239, submodule.py:127-131): pred [B,H,W]; logits_out optional [B,D,H,W].  Neither the logits nor
+ * the probability volume are materialised. */
+int dca_tap_gather_softmax_regress(const float* P, float* pred, float* logits_out, int B, int D, int H, int W,
+                                   void* stream);
 /* Depth-marching member of the family: Conv3d k3 s1 p1, Cout = 32, Cin in {32,64}.  A CTA walks the input planes of a
  * chunk of <= 16 output planes; each halo slab is read once per (kh,kw) for all three kd (N = 96).  Same epilogue
  * contract as dca_conv3d_tc.  w_march from dca_pack_weights_tc_march ([kh*3+kw][plane][kd][32][Cin] bf16). */

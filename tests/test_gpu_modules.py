@@ -74,7 +74,7 @@ def test_self_attention_block_matches_oracle_attention():
     blk.load_state_dict({k[len(pref):]: v for k, v in sd.items() if k.startswith(pref)})
     q, k = rnd(1, 32, 24, 4, 6, seed=1), rnd(1, 32, 24, 4, 6, seed=2)
     with torch.no_grad():
-        ref = O.disparity_attention(O._Ctx(sd), pref, q, k)
+        ref = O.disparity_attention(O._Ctx(sd), pref[:-1], q, k)
         got = blk.cuda().eval()(q.cuda(), k.cuda())
     close(got, ref, 3e-4, "attention vs oracle")
 
@@ -234,3 +234,38 @@ def test_cout1_conv_tensor_core_route(B, D, H, W):
     got = E.conv_cout1_any(xp, pc)
     close(got, ref, 2e-5, "32->1 tensor-core route")
     close(E.conv_cout1(xp, pc.host), ref, 2e-5, "32->1 CUDA-core route")
+
+
+@pytest.mark.parametrize("cin,B,D,H,W,march", [(32, 1, 6, 8, 12, False), (32, 1, 24, 40, 72, True), (64, 1, 9, 17, 21, False),
+                                               (32, 2, 5, 33, 9, False), (32, 1, 17, 48, 104, True), (64, 1, 20, 36, 100, True)])
+def test_fused_tail_conv_taps27(cin, B, D, H, W, march):
+    """dca_conv3d_tc_taps27 + dca_tap_gather3d == Conv3d(32->1,k3)(ReLU(BN(Conv3d(cin->32,k3)(x)))) (classif3
+    gwcnet_dca_g.py:166-168, cva.classify cva.py:51-53) on both kernels (halo-slab and depth-marching), ragged shapes;
+    and the fused gather + softmax + regression against torch on the same logits."""
+    d, E = _mods()
+    from importlib import import_module
+    sub = import_module("cost-volume-aggregation-in-stereo-matching-revisited_b200.submodule")
+    head = _init(torch.nn.Sequential(sub.convbn_3d(cin, 32, 3, 1, 1), torch.nn.ReLU(),
+                                     torch.nn.Conv3d(32, 1, 3, padding=1, bias=False)), 21)
+    x = rnd(B, cin, D, H, W, seed=8)
+    with torch.no_grad():
+        ref = head(x)[:, 0]
+        ref_pred = torch.sum(torch.softmax(ref, 1) * torch.arange(D, dtype=ref.dtype).view(1, D, 1, 1), 1, keepdim=True)
+    head.cuda()
+    pc = E.pack_convbn(head[0])
+    assert pc.pack_tc(2)
+    pc1 = E.PackedCout1(head[2].weight, 2)
+    xp = E.Planes.from_ncdhw(x.cuda(), 2)
+    saved = E.Options.march_min_items
+    E.Options.march_min_items = 0 if march else 1 << 30          # pick the kernel under test regardless of the size
+    try:
+        P = E.conv_taps27(xp, pc, pc1)
+    finally:
+        E.Options.march_min_items = saved
+    assert P is not None and P.shape == (27, B, D, H, W)
+    close(E.tap_gather(P), ref, 3e-5, "fused tail logits")
+    pred, lg = E.tap_gather_softmax_regress(P, want_logits=True)
+    close(lg, ref, 3e-5, "fused tail logits (fused gather)")
+    close(pred, ref_pred, 1e-4, "fused tail regression")
+    pred2, none = E.tap_gather_softmax_regress(P)
+    assert none is None and torch.equal(pred, pred2)

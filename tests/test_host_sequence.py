@@ -16,12 +16,12 @@ def _gold(name):
 
 
 def test_default_forward_launches_the_recorded_kernel_sequence():
-    """KITTI 384x1248 / maxdisp 192: 46 launches per pair (= bench.py's gpu_launches / steps in profiles/r1h_bench.json),
-    in the order recorded when the GPU parity suite was last green."""
+    """KITTI 384x1248 / maxdisp 192: 41 launches per pair (= bench.py's gpu_launches / steps), in the order recorded when
+    the GPU parity suite was last green (tests/golden/make_host_sequences.py)."""
     import dcanet_b200 as d
     tr, (pred4, pv) = _dryrun.forward_trace(d.GwcNet(192).eval(), 96, 312)
     assert pred4.shape == (1, 1, 384, 1248) and pv.shape == (1, 24, 48, 156)
-    assert len(tr) == 46
+    assert len(tr) == 41
     assert tr == _gold("kernel_sequence_kitti.json")
     tr, _ = _dryrun.forward_trace(d.GwcNet(48).eval(), 16, 32)
     assert tr == _gold("kernel_sequence_tiny.json")

@@ -54,13 +54,13 @@ def test_variant_state_dict_layout_matches_reference(n):
 
 @pytest.mark.parametrize("n", VARIANTS)
 def test_variant_kernel_sequence(n):
-    """N stages launch the 3-stage sequence with the cva block repeated N times (11 launches per stage)."""
+    """N stages launch the 3-stage sequence with the cva block repeated N times (10 launches per stage)."""
     import dcanet_b200 as d
     mod = importlib.import_module(f"cost-volume-aggregation-in-stereo-matching-revisited_b200.gwcnet_dca{n}_g")
     tr, (pred, pv) = _dryrun.forward_trace(mod.GwcNet(48).eval(), 16, 32)
     base, _ = _dryrun.forward_trace(d.GwcNet(48).eval(), 16, 32)
-    assert len(base) == 46 and len(tr) == 46 + 11 * (n - 3)
-    per_stage = collections.Counter(t[0] for t in base[5:16])
+    assert len(base) == 41 and len(tr) == 41 + 10 * (n - 3)
+    per_stage = collections.Counter(t[0] for t in base[5:15])
     got = collections.Counter(t[0] for t in tr)
     want = collections.Counter(t[0] for t in base)
     for k, v in per_stage.items():
