@@ -39,6 +39,7 @@ SIGNATURES = {
     "dca_pack_weights_tc2d": [_vp, _c_int, _c_int, _vp, _c_int, _vp],
     "dca_pack_weights_tc2d_bytes": [_c_int] * 3,
     "dca_tc_set_halo": [_c_int],
+    "dca_tc_set_deconv_pair": [_c_int],
     "dca_volume_set_v2": [_c_int],
     "dca_attention_set_team": [_c_int],
     "dca_tc_set_tuning": [_c_int, _c_int],

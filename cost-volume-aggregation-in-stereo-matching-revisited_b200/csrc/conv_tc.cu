@@ -63,6 +63,8 @@ struct TcParams {
   float inv_tiles_w, inv_tiles_h, inv_Dt, inv_ncls;   // reciprocals for the epilogue's tile decode (fast_divmod)
   int march_n;                     // > 0: depth-marching kernel, a work item = march_n consecutive output planes
   int cls_inner;                   // epilogue/work order: CTA owns whole tiles, classes inside (up2 kernel)
+  int pair;                        // cls_inner + TWO depth-adjacent tiles per work item (deconv pair kernel): items run
+                                   // (pair, class, sub-tile), 4 accumulator buffers, Dt counts depth PAIRS
   float cls_comp[8];               // per class: 1 + kappa * (MMA steps accumulated into the main block), see fill_comp()
   int linear;                      // 1x1x1 convs: tiles are 128 CONSECUTIVE voxels (8 KB bursts); rB/rD/rH/rW = real dims
   int rB, rD, rH, rW;
@@ -122,6 +124,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// L2 prefetch of a tensor-map box (no shared memory, no barrier): decouples the DRAM latency of an operand from the
+// availability of its smem slot
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -243,6 +252,15 @@ __device__ __forceinline__ void load_raw16(uint4* raw, const __nv_bfloat16* base
   if (planes == 2) ldg256(base + plane + off, raw[2], raw[3]);
 }
 
+// BN scale / shift live in shared memory; the epilogues get them as generic pointers, and a generic LD of shared memory
+// goes through the global-load path (long scoreboard: ncu showed 24 % of all stall samples of the deconv kernel on the
+// first FFMA after these loads).  Explicit ld.shared keeps them on the 20-cycle LDS path.
+__device__ __forceinline__ float4 lds_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+
 template <int COUT, int PLANES>
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, uint32_t tmem_base, uint64_t* tfull,
                                             uint64_t* tempty, const float* s_scale, const float* s_shift, int warp,
@@ -261,7 +279,8 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
   // the accumulator of plane j sits in TMEM columns 32*(n-1-j) and is announced by its own mbarrier tfull[j]
   const int mn = p.march_n;
   const int my_march = mn ? ((total_tiles > (int)blockIdx.x) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0) : 0;
-  const int n_items = mn ? my_march * mn : (p.cls_inner ? my_tiles * p.ncls : total_tiles);
+  const int n_items = mn ? my_march * mn : (p.cls_inner ? my_tiles * p.ncls * (p.pair ? 2 : 1) : total_tiles);
+  const uint32_t acc_mask = p.pair ? 3u : 1u, acc_shift = p.pair ? 2u : 1u;
   if (mn) {
     // march mode: clear this thread's slice of every accumulator plane once; afterwards a plane is cleared again right after
     // it has been drained (below) and handed back through ITS OWN mbarrier tempty[j], so the MMA warp starts the next
@@ -278,8 +297,9 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
       for (int jj = 0; jj < mn; ++jj) mbar_arrive(&tempty[jj]);
   }
   for (int item = (mn ? 0 : first); item < n_items; item += (mn ? 1 : step), ++it) {
-    int r, cls, mj = 0, mwi = 0;
+    int r, cls, mj = 0, mwi = 0, sub = 0;
     if (mn) { cls = 0; mwi = fast_divmod(item, mn, p.inv_ncls, mj); r = (int)blockIdx.x + mwi * (int)gridDim.x; }
+    else if (p.pair) { sub = item & 1; cls = (item >> 1) & 7; r = (int)blockIdx.x + (item >> 4) * (int)gridDim.x; }   // ncls == 8
     else if (p.cls_inner) { const int q = fast_divmod(item, p.ncls, p.inv_ncls, cls); r = (int)blockIdx.x + q * (int)gridDim.x; }
     else if (p.ncls > 1) { r = fast_divmod(item, p.ncls, p.inv_ncls, cls); }
     else { cls = 0; r = item; }
@@ -287,7 +307,8 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
     r = fast_divmod(r, p.tiles_w, p.inv_tiles_w, tw);
     r = fast_divmod(r, p.tiles_h, p.inv_tiles_h, th);
     const int b = fast_divmod(r, p.Dt, p.inv_Dt, td);
-    const uint32_t acc = it & 1;
+    if (p.pair) td = 2 * td + sub;
+    const uint32_t acc = it & acc_mask;
     const int ty = th * TC_TH + hh, tx = tw * TC_TW + ww;
     int oz = mn ? td * mn + mj : td * (p.out_stride_d ? p.out_stride_d : p.out_stride) + p.cls_off[cls][0],
         oy = ty * p.out_stride + p.cls_off[cls][1],
@@ -337,7 +358,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
       }
     }
     if (mn) mbar_wait(&tfull[mj], (uint32_t)(mwi & 1));
-    else mbar_wait(&tfull[acc], (it >> 1) & 1);
+    else mbar_wait(&tfull[acc], (it >> acc_shift) & 1);
     tc_fence_after();
     const float comp = p.cls_comp[cls];      // undo the accumulator's truncation shrink of the main block
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * 16 +
@@ -381,11 +402,9 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
           }   // (the fused upsample is only used with COUT == 32)
         }
         {
-          const float4* sc4 = reinterpret_cast<const float4*>(s_scale + cb);     // (16-float aligned: 4 LDS.128 each)
-          const float4* sh4 = reinterpret_cast<const float4*>(s_shift + cb);
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 a = sc4[j4], c = sh4[j4];
+            const float4 a = lds_f4(s_scale + cb + 4 * j4), c = lds_f4(s_shift + cb + 4 * j4);   // (16-float aligned)
             v[4 * j4 + 0] = fmaf(v[4 * j4 + 0], a.x, c.x); v[4 * j4 + 1] = fmaf(v[4 * j4 + 1], a.y, c.y);
             v[4 * j4 + 2] = fmaf(v[4 * j4 + 2], a.z, c.z); v[4 * j4 + 3] = fmaf(v[4 * j4 + 3], a.w, c.w);
           }
@@ -464,11 +483,9 @@ __device__ __forceinline__ void taps_load_act(uint32_t t_main, uint32_t t_corr, 
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rh[j]) * comp;
   }
-  const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
-  const float4* sh4 = reinterpret_cast<const float4*>(s_shift);
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {
-    const float4 a = sc4[j4], c = sh4[j4];
+    const float4 a = lds_f4(s_scale + 4 * j4), c = lds_f4(s_shift + 4 * j4);
     v[4 * j4 + 0] = apply_act(fmaf(v[4 * j4 + 0], a.x, c.x), act); v[4 * j4 + 1] = apply_act(fmaf(v[4 * j4 + 1], a.y, c.y), act);
     v[4 * j4 + 2] = apply_act(fmaf(v[4 * j4 + 2], a.z, c.z), act); v[4 * j4 + 3] = apply_act(fmaf(v[4 * j4 + 3], a.w, c.w), act);
   }
@@ -718,7 +735,7 @@ struct HaloCfg {
   static constexpr int A_SLOT = PLANES * SLAB_PITCH;
   static constexpr int B_ROWS = PLANES * COUT;
   static constexpr int B_BYTES = B_ROWS * ROWB;                                // one tap
-  static constexpr int BUDGET = 200 * 1024;
+  static constexpr int BUDGET = 200 * 1024;   // (a 4th slab slot was measured: same TMA-only time, the ring is not latency bound)
   static constexpr bool WRES = (27 * B_BYTES + 2 * A_SLOT) <= BUDGET;
   static constexpr int W_CHUNK = 3 * B_BYTES;
   static constexpr int A_SLOTS_RES = ((BUDGET - 27 * B_BYTES) / A_SLOT) > 4 ? 4 : ((BUDGET - 27 * B_BYTES) / A_SLOT);
@@ -1026,7 +1043,7 @@ conv_tc_s2slab_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 const uint64_t da = da_slab + (uint64_t)((a_off + k * 32) >> 4);
                 const uint64_t db = db_tap + (uint64_t)((k * 32) >> 4);
                 const uint32_t accum = (kd == 0 && kh == 0 && kw == 0 && k == 0) ? 0u : 1u;
-                if (leader) {
+                if (leader && !(p.dbg & 2)) {
                   umma_bf16(d_addr, da, db, idesc_full, accum);
                   if (PLANES == 2) umma_bf16(d_addr + COUT, da + (uint64_t)(Cfg::SLAB_PITCH >> 4), db, idesc_half, 1u);
                 }
@@ -1281,6 +1298,227 @@ conv_tc_up2_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const 
 
 
 // =====================================================================================================
+// ConvTranspose3d 64 -> 32 (+ redir side tap), TWO depth-adjacent low-res tiles per weight fetch
+// (Multi_Aggregation.conv3 + redir, cva.py:20-31).
+// The up2 kernel above streams 28 weight tiles of 8 KB per 128-voxel tile: 280 KB of weights against 92 KB of slabs and
+// 131 KB of side rows -- it sits on the L2->SMEM limit (8.3 TB/s at 133 us) with the tensor pipe 25 % busy.  Here a work
+// item is a PAIR of low-res tiles at depths (d, d+1):
+//   * three slabs (d, d+1, d+2) feed both tiles (tap slab index s of tile 0 = slab s, of tile 1 = slab s+1), and the
+//     slabs are 9 x 17 instead of 10 x 18 voxels (the taps of a transposed conv only reach offsets {0,1});
+//   * every streamed weight tile is used by TWO MMAs chains (M = 2 x 128), and the side (redir) weights stay resident;
+//   L2->SMEM bytes per tile: 503 KB -> 298 KB.  Four accumulator buffers (2 classes x 2 sub-tiles) in TMEM.
+// Class order inside a pair: even x-parity class = taps then side, odd class = side then taps, so the pair-row box of a
+// class pair is released early and the next one has >= 4 taps of MMA time to arrive.
+// =====================================================================================================
+constexpr int DP_W = TC_TW + 1, DP_H = TC_TH + 1;     // slab 9 x 17
+
+template <int PLANES>
+struct DeconvPairCfg {
+  static constexpr int CIN = 64, COUT = 32, ROWB = 128;
+  static constexpr int SLAB_BYTES = DP_W * DP_H * ROWB;
+  static constexpr int SLAB_PITCH = (SLAB_BYTES + 1023) / 1024 * 1024;
+  static constexpr int SLAB_SET = 3 * PLANES * SLAB_PITCH;
+  static constexpr int A_BYTES = TC_M * 128;                       // one plane of a side box: 128 w-pair rows of 128 B
+  static constexpr int SIDE_SLOT = PLANES * A_BYTES;
+  static constexpr int B_ROWS = PLANES * COUT;
+  static constexpr int B_BYTES = B_ROWS * ROWB;
+  static constexpr int FIXED = SLAB_SET + 2 * SIDE_SLOT + B_BYTES + 1024 + 512 + 2 * COUT * 4;
+  static constexpr int W_FIT = (227 * 1024 - FIXED) / B_BYTES;
+  static constexpr int W_SLOTS = W_FIT > 12 ? 12 : W_FIT;
+  static constexpr int NACC = PLANES * COUT;
+  static constexpr int TMEM_COLS = 4 * NACC;
+  static constexpr int SMEM_BYTES = FIXED + W_SLOTS * B_BYTES;
+};
+
+template <int PLANES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_deconv_pair_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const Up2Params u) {
+  using Cfg = DeconvPairCfg<PLANES>;
+  constexpr int COUT = Cfg::COUT;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* slab_base = smem;
+  uint8_t* side_base = slab_base + Cfg::SLAB_SET;
+  uint8_t* wside = side_base + 2 * Cfg::SIDE_SLOT;                 // resident side (redir) weights
+  uint8_t* w_base = wside + Cfg::B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_base + Cfg::W_SLOTS * Cfg::B_BYTES);
+  uint64_t* sfull = bars;                          // [1]
+  uint64_t* sempty = sfull + 1;                    // [1]
+  uint64_t* dfull = sempty + 1;                    // [2]
+  uint64_t* dempty = dfull + 2;                    // [2]
+  uint64_t* wsfull = dempty + 2;                   // [1]
+  uint64_t* wfull = wsfull + 1;                    // [W_SLOTS]
+  uint64_t* wempty = wfull + Cfg::W_SLOTS;         // [W_SLOTS]
+  uint64_t* tfull = wempty + Cfg::W_SLOTS;         // [4]
+  uint64_t* tempty = tfull + 4;                    // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 4);
+  float* s_scale = reinterpret_cast<float*>(w_base + Cfg::W_SLOTS * Cfg::B_BYTES + 512);
+  float* s_shift = s_scale + COUT;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_pairs = p.B * p.Dt * p.tiles_h * p.tiles_w;      // p.Dt = depth pairs
+
+  if (threadIdx.x < COUT) {
+    s_scale[threadIdx.x] = p.scale ? p.scale[threadIdx.x] : 1.f;
+    s_shift[threadIdx.x] = p.shift ? p.shift[threadIdx.x] : 0.f;
+  }
+  if (warp == 0 && lane == 0) {
+    mbar_init(sfull, 1); mbar_init(sempty, 1); mbar_init(wsfull, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&dfull[i], 1); mbar_init(&dempty[i], 1); }
+    for (int i = 0; i < Cfg::W_SLOTS; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&maps.a[0]);
+    prefetch_tmap(&maps.w);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(wsfull, Cfg::B_BYTES);
+      tma_load_2d(wside, &maps.w, wsfull, 0, u.side_widx * Cfg::B_ROWS);
+      uint32_t ps = 0, pd = 0, sw = 0, pw = 0;
+      for (int pair = blockIdx.x; pair < total_pairs; pair += gridDim.x) {
+        int r = pair;
+        const int tw = r % p.tiles_w; r /= p.tiles_w;
+        const int th = r % p.tiles_h; r /= p.tiles_h;
+        const int d0 = 2 * (r % p.Dt);
+        const int b = r / p.Dt;
+        mbar_wait(sempty, ps ^ 1);
+        mbar_expect_tx(sfull, 3 * PLANES * Cfg::SLAB_BYTES);
+        for (int sl = 0; sl < 3; ++sl)
+#pragma unroll
+          for (int pl = 0; pl < PLANES; ++pl)
+            tma_load_5d(slab_base + (sl * PLANES + pl) * Cfg::SLAB_PITCH, &maps.a[0], sfull, 0, tw * TC_TW, th * TC_TH,
+                        d0 + sl, pl * p.B + b);
+        ps ^= 1;
+        // (an L2 prefetch of this pair's side rows / the next pair's slabs was measured SLOWER: 163 vs 147 us -- the prefetch
+        //  requests queue in the same TMA unit in front of the loads the MMA warp is waiting for)
+        for (int cls = 0; cls < 8; ++cls) {
+          if ((cls & 1) == 0) {
+            // pair-row boxes of the two sub-tiles for the x-parity class pair (cls, cls+1): slot = sub-tile
+            for (int sub = 0; sub < 2; ++sub) {
+              mbar_wait(&dempty[sub], pd ^ 1);
+              mbar_expect_tx(&dfull[sub], PLANES * Cfg::A_BYTES);
+#pragma unroll
+              for (int pl = 0; pl < PLANES; ++pl)
+                tma_load_5d(side_base + sub * Cfg::SIDE_SLOT + pl * Cfg::A_BYTES, &maps.a[1 + (cls >> 1)], &dfull[sub], 0,
+                            tw * TC_TW, th * TC_TH, d0 + sub, pl * p.B + b);
+            }
+            pd ^= 1;
+          }
+          for (int t = u.cls_tap0[cls]; t < u.cls_tap0[cls + 1]; ++t) {
+            mbar_wait(&wempty[sw], pw ^ 1);
+            mbar_expect_tx(&wfull[sw], Cfg::B_BYTES);
+            tma_load_2d(w_base + sw * Cfg::B_BYTES, &maps.w, &wfull[sw], 0, u.taps[t].widx * Cfg::B_ROWS);
+            if (++sw == Cfg::W_SLOTS) { sw = 0; pw ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_full = make_idesc(TC_M, PLANES * COUT);
+    constexpr uint32_t idesc_half = make_idesc(TC_M, COUT);
+    constexpr uint64_t DA = desc_const<128>(DP_W * 128);        // slab views: 8-row groups 9 rows apart
+    constexpr uint64_t DD = desc_const<128>(8 * 128);           // dense tiles (side boxes, weights)
+    constexpr uint32_t NACC = Cfg::NACC;
+    const uint32_t slab_u32 = smem_u32(slab_base), side_u32 = smem_u32(side_base), w_u32 = smem_u32(w_base);
+    const uint64_t db_side = DD + (smem_u32(wside) >> 4);
+    uint32_t ps = 0, pd = 0, sw = 0, pw = 0, it = 0;
+    mbar_wait(wsfull, 0);
+    tc_fence_after();
+    for (int pair = blockIdx.x; pair < total_pairs; pair += gridDim.x) {
+      mbar_wait(sfull, ps);
+      tc_fence_after();
+      ps ^= 1;
+      for (int cls = 0; cls < 8; ++cls, it += 2) {
+        const uint32_t acc0 = it & 3, acc1 = (it + 1) & 3;
+        mbar_wait(&tempty[acc0], ((it >> 2) & 1) ^ 1);
+        mbar_wait(&tempty[acc1], (((it + 1) >> 2) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t dacc[2] = {tmem_base + acc0 * NACC, tmem_base + acc1 * NACC};
+        const bool odd = (cls & 1) != 0;
+        uint32_t started = 0;                                   // 0 until the first MMA of this class has been issued
+        auto side_taps = [&]() {
+          if (!odd) { mbar_wait(&dfull[0], pd); mbar_wait(&dfull[1], pd); tc_fence_after(); }
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            // A = pair rows (dense SWIZZLE_128B); the odd-x class reads the second voxel of each pair: K-offset +64 B
+            const uint64_t da0 = DD + ((side_u32 + (uint32_t)sub * Cfg::SIDE_SLOT + (odd ? 64u : 0u)) >> 4);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {                       // the side input has 32 channels
+              if (leader && !(p.dbg & 2)) {
+                umma_bf16(dacc[sub], da0 + (uint64_t)(k * 2), db_side + (uint64_t)(k * 2), idesc_full, (started || k > 0) ? 1u : 0u);
+                if (PLANES == 2)
+                  umma_bf16(dacc[sub] + COUT, da0 + (uint64_t)((Cfg::A_BYTES >> 4) + k * 2), db_side + (uint64_t)(k * 2), idesc_half, 1u);
+              }
+            }
+          }
+          started = 1;
+          if (odd) {                                            // both classes of the pair have read the boxes
+            __syncwarp();
+            if (leader) { umma_commit(&dempty[0]); umma_commit(&dempty[1]); }
+            pd ^= 1;
+          }
+        };
+        if (odd) side_taps();
+        for (int t = u.cls_tap0[cls]; t < u.cls_tap0[cls + 1]; ++t) {
+          const Up2Tap tp = u.taps[t];
+          mbar_wait(&wfull[sw], pw);
+          tc_fence_after();
+          const uint64_t db0 = DD + ((w_u32 + sw * Cfg::B_BYTES) >> 4);
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            const uint32_t a0 = slab_u32 + (uint32_t)((tp.slab + sub) * PLANES) * Cfg::SLAB_PITCH +
+                                (uint32_t)(tp.dy * DP_W + tp.dx) * 128u;
+            const uint64_t da0 = DA + (a0 >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (leader && !(p.dbg & 2)) {
+                umma_bf16(dacc[sub], da0 + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc_full, (started || k > 0) ? 1u : 0u);
+                if (PLANES == 2)
+                  umma_bf16(dacc[sub] + COUT, da0 + (uint64_t)((Cfg::SLAB_PITCH >> 4) + k * 2), db0 + (uint64_t)(k * 2), idesc_half, 1u);
+              }
+            }
+          }
+          started = 1;
+          __syncwarp();
+          if (leader) umma_commit(&wempty[sw]);
+          if (++sw == Cfg::W_SLOTS) { sw = 0; pw ^= 1; }
+        }
+        if (!odd) side_taps();
+        __syncwarp();
+        if (leader) { umma_commit(&tfull[acc0]); umma_commit(&tfull[acc1]); }
+        __syncwarp();
+      }
+      if (leader) umma_commit(sempty);              // all MMAs reading the slabs of this pair have been issued
+      __syncwarp();
+    }
+  } else {
+    tc_epilogue<COUT, PLANES>(p, total_pairs, tmem_base, tfull, tempty, s_scale, s_shift, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// =====================================================================================================
 // Depth-marching 3x3x3 stride-1 conv, Cout = 32: the three depth taps are folded into the GEMM's N.
 // A work item = one (h, w) tile column x a chunk of n <= 16 output planes.  The CTA walks the n+2 input planes of
 // the chunk; the halo slab of input plane d' is read ONCE per (kh, kw) and multiplied against the weights of all
@@ -1442,7 +1680,7 @@ conv_tc_march_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
 #pragma unroll
               for (int k = 0; k < CIN / 16; ++k) {
                 const uint64_t da = da_slab + (uint64_t)(((kh * HB_W + kw) * Cfg::ROWB + k * 32) >> 4);
-                if (leader && live) {
+                if (leader && live && !(p.dbg & 2)) {
                   umma_bf16(d_addr, da, db_hi + (uint64_t)(k * 2), idesc, 1u);
                   if (PLANES == 2) {     // the two small terms accumulate in their own block (truncation bias, see the header)
                     umma_bf16(d_addr + MARCH_CORR, da, db_lo + (uint64_t)(k * 2), idesc, 1u);
@@ -1690,9 +1928,36 @@ static int launch_up2(const TcMaps& maps, const TcParams& p, const Up2Params& u,
   return DCA_OK;
 }
 
+template <int PLANES>
+static int launch_deconv_pair(const TcMaps& maps, const TcParams& p, const Up2Params& u, cudaStream_t st) {
+  using Cfg = DeconvPairCfg<PLANES>;
+  static_assert(Cfg::W_SLOTS >= 3, "weight ring too shallow");
+  static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "smem plan");
+  static_assert(Cfg::TMEM_COLS <= 512 && (Cfg::TMEM_COLS & (Cfg::TMEM_COLS - 1)) == 0, "TMEM plan");
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  cudaFuncSetAttribute(conv_tc_deconv_pair_kernel<PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  const int total = p.B * p.Dt * p.tiles_h * p.tiles_w;
+  const int grid = total < g_num_sms ? total : g_num_sms;
+  TcParams q = p; fill_recips(q);
+  for (int c = 0; c < 8; ++c) fill_comp(q, c, ((int)u.cls_tap0[c + 1] - (int)u.cls_tap0[c]) * 4 + 2);
+  conv_tc_deconv_pair_kernel<PLANES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, q, u);
+  DCA_RETURN_IF_LAUNCH_FAILED();
+  return DCA_OK;
+}
+
+static int g_use_deconv_pair = 1;
+
 }  // namespace dca
 
 using namespace dca;
+
+// 1 (default): transposed conv 64 -> 32 with a side input runs the two-tiles-per-weight-fetch kernel; 0: the up2 kernel
+extern "C" int dca_tc_set_deconv_pair(int on) { g_use_deconv_pair = on ? 1 : 0; return DCA_OK; }
 
 // kind 0: y = act(scale * (conv_transpose3d_k3s2(x) + side 1x1x1) + shift) + res_post
 //         x [P][B][Dl][Hl][Wl][Cin], w_tc = 27 taps (+ tap 27 = side weights, Cin-padded) of [planes][32][Cin]
@@ -1814,6 +2079,14 @@ extern "C" int dca_up2_tc(int kind, const void* x, int planes, const void* side,
   }
   const int wt = (kind == 0) ? (side ? 28 : 27) : (kind == 1 ? 5 : 4);
   if (!make_w_map(&maps.w, w_tc, Cin, wt * P * Cout, P * Cout)) return DCA_ERR_LAUNCH;
+  if (kind == 0 && Cin == 64 && side && g_use_deconv_pair) {
+    // two depth-adjacent tiles per weight fetch over 9 x 17 slabs (conv_tc_deconv_pair_kernel)
+    if (!make_act_map(&maps.a[0], x, Cin, Wx, Hx, Dx, P * B, (size_t)Cin, (size_t)Wx * Cin, (size_t)Hx * Wx * Cin,
+                      (size_t)Dx * Hx * Wx * Cin, DP_W, DP_H))
+      return DCA_ERR_LAUNCH;
+    p.Dt = (Dl + 1) / 2; p.pair = 1;
+    return P == 2 ? launch_deconv_pair<2>(maps, p, u, st) : launch_deconv_pair<1>(maps, p, u, st);
+  }
   if (kind == 1) return P == 2 ? launch_up2<32, 2, 3>(maps, p, u, st) : launch_up2<32, 1, 3>(maps, p, u, st);
   if (kind == 2) return P == 2 ? launch_up2<32, 2, 2>(maps, p, u, st) : launch_up2<32, 1, 2>(maps, p, u, st);
   if (Cin == 64) return P == 2 ? launch_up2<64, 2, 2>(maps, p, u, st) : launch_up2<64, 1, 2>(maps, p, u, st);
@@ -1830,7 +2103,7 @@ extern "C" int dca_tc_set_halo(int on) { g_use_halo = on & 1; g_use_s2slab = (on
 // (the first argument is reserved and must be 1)
 extern "C" int dca_tc_set_tuning(int reserved, int flags) {
   if (reserved != 1) return DCA_ERR_ARG;
-  g_dbg = (flags >> 4) & 3;
+  g_dbg = (flags >> 4) & 7;
   return DCA_OK;
 }
 

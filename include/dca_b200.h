@@ -136,6 +136,9 @@ int dca_tc_set_tuning(int reserved, int flags);
  * accumulation step).  The tcgen05 conv epilogues multiply the main accumulator block by 1 + kappa * steps; this sets
  * kappa (default 1.56e-8f, 0 = off). */
 int dca_tc_set_trunc_comp(float kappa);
+/* dca_up2_tc kind 0 with Cin = 64 and a side input: 1 (default) = two depth-adjacent tiles per weight fetch
+ * (conv_tc_deconv_pair_kernel), 0 = one tile per fetch (conv_tc_up2_kernel); same results. */
+int dca_tc_set_deconv_pair(int on);
 
 /* (2) DCA module ------------------------------------------------------------------------------- */
 int dca_avgpool3d(const void* x, void* y, int planes, int B, int C, int Di, int Hi, int Wi, void* stream);

@@ -26,7 +26,10 @@ def main():
     wmul = mul.get(units[idx["dram__bytes_write.sum"]], 1.0)
     tmul = {"us": 1.0, "ns": 1e-3, "ms": 1e3}.get(units[idx["gpu__time_duration.sum"]], 1.0)
     out, traffic = [], collections.defaultdict(list)
-    for r in rows[2:]:
+    body = rows[2:]
+    if len(sys.argv) > 3 and sys.argv[3] == "--second-half":      # two forwards captured: keep the second (warm) one
+        body = body[len(body) // 2:]
+    for r in body:
         name = r[idx["Kernel Name"]].replace("dca::", "").replace("void ", "").split("(")[0]
         e = {"name": name, "t_us": g(r, "gpu__time_duration.sum") * tmul,
              "dram_read_MB": g(r, "dram__bytes_read.sum") * rmul / 1e6,
@@ -36,6 +39,7 @@ def main():
              "sm_pct": g(r, "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
              "issue_pct": g(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
              "inst_M": g(r, "smsp__inst_executed.sum") / 1e6,
+             "l2_MB": g(r, "lts__t_bytes.sum") * mul.get(units[idx["lts__t_bytes.sum"]], 1.0) / 1e6 if "lts__t_bytes.sum" in idx else None,
              "regs": g(r, "launch__registers_per_thread")}
         out.append(e)
         traffic[name].append({"dram_read_bytes": e["dram_read_MB"] * 1e6, "dram_write_bytes": e["dram_write_MB"] * 1e6,

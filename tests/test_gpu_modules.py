@@ -161,8 +161,10 @@ def test_run_convbn_3d(cin, cout, k, s):
 
 
 # --------------------------------------------------------------------------------------------------------- op level
-@pytest.mark.parametrize("B,Dl,Hl,Wl,with_res", [(1, 3, 5, 7, False), (2, 2, 17, 9, True), (1, 5, 16, 8, True), (1, 1, 1, 1, False)])
-def test_up2_kind0_transposed_conv_plus_redir(B, Dl, Hl, Wl, with_res):
+@pytest.mark.parametrize("pair", [1, 0])
+@pytest.mark.parametrize("B,Dl,Hl,Wl,with_res", [(1, 3, 5, 7, False), (2, 2, 17, 9, True), (1, 5, 16, 8, True), (1, 1, 1, 1, False),
+                                                 (1, 6, 40, 30, True)])
+def test_up2_kind0_transposed_conv_plus_redir(B, Dl, Hl, Wl, with_res, pair):
     """dca_up2_tc kind 0 = ReLU(BN(ConvTranspose3d(x)) + BN(redir(side))) + res_post (cva.py:20-31), the kernel
     cva_forward ships, at shapes that are not multiples of the 8x16 tile."""
     d, E = _mods()
@@ -177,8 +179,13 @@ def test_up2_kind0_transposed_conv_plus_redir(B, Dl, Hl, Wl, with_res):
         pk = E.PackedAgg(m, 2)
         assert pk.conv3_fused is not None
         fd = pk.conv3_fused
-        got = E.up2(0, E.Planes.from_ncdhw(x.cuda(), 2), E.Planes.from_ncdhw(side.cuda(), 2), fd.w_tc, fd.scale, fd.shift,
-                    E.ACT_RELU, 64, Dl, Hl, Wl, res_post=E.Planes.from_ncdhw(res.cuda(), 2) if with_res else None)
+        d._lib.call("dca_tc_set_deconv_pair", pair)       # 1: two depth-adjacent tiles per weight fetch, 0: the up2 kernel
+        try:
+            got = E.up2(0, E.Planes.from_ncdhw(x.cuda(), 2), E.Planes.from_ncdhw(side.cuda(), 2), fd.w_tc, fd.scale, fd.shift,
+                        E.ACT_RELU, 64, Dl, Hl, Wl, res_post=E.Planes.from_ncdhw(res.cuda(), 2) if with_res else None)
+            torch.cuda.synchronize()
+        finally:
+            d._lib.call("dca_tc_set_deconv_pair", 1)
     close(got.to_ncdhw(), ref, 3e-4, "up2 kind 0")
 
 
