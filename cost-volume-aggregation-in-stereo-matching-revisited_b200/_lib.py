@@ -45,6 +45,8 @@ SIGNATURES = {
     "dca_tc_set_tuning": [_c_int, _c_int],
     "dca_tc_set_trunc_comp": [_f],
     "dca_avgpool3d": [_vp, _vp] + [_c_int] * 6 + [_vp],
+    "dca_avgpool3d_simple": [_vp, _vp] + [_c_int] * 6 + [_vp],
+    "dca_pool_set_march": [_c_int],
     "dca_class_stats": [_vp, _vp, _vp, _vp, _vp] + [_c_int] * 4 + [_vp],
     "dca_disp_attention": [_vp, _vp, _vp, _vp, _vp, _c_int, _vp] + [_c_int] * 7 + [_vp],
     "dca_self_attention": [_vp, _vp, _vp, _vp] + [_c_int] * 6 + [_vp],

@@ -1928,6 +1928,98 @@ static int launch_up2(const TcMaps& maps, const TcParams& p, const Up2Params& u,
   return DCA_OK;
 }
 
+// =====================================================================================================
+// AvgPool3d(3, stride 2, pad 1, count_include_pad) of a 32-channel cost tensor (cva.downsample, cva.py:39).
+// The thread-per-output kernel re-reads every input element 27/8 times through L1/L2 (ncu: 428 MB L2->SM for a 184 MB
+// tensor, 6.6 TB/s = the fabric limit, 65 us).  Here a CTA owns an (8 w x 4 h) OUTPUT tile and marches along depth: every
+// input plane of its (17 x 9) footprint is TMA-loaded exactly once (out-of-tensor coordinates are zero filled = the
+// pool's zero padding), reduced 3x3 -> 1 in registers, and the three plane sums of an output depth are combined on the
+// fly (an odd input plane is the last plane of output d and the first of d+1).  L2->SM traffic 1.2x the tensor.
+// thread = (output voxel, 8-channel chunk); 2 slots of (hi, lo) boxes; several CTAs per SM hide the load latency.
+// =====================================================================================================
+constexpr int AP_TW = 8, AP_TH = 4, AP_BW = 2 * AP_TW + 1, AP_BH = 2 * AP_TH + 1;
+constexpr int AP_BOX = AP_BW * AP_BH * 64;          // one plane (hi or lo) of one input plane's footprint, 32 ch x 2 B rows
+constexpr int AP_PITCH = (AP_BOX + 127) / 128 * 128; // TMA destinations are 128-byte aligned
+
+template <int PLANES>
+__global__ void __launch_bounds__(AP_TW * AP_TH * 4)
+avgpool3d_march_kernel(const __grid_constant__ CUtensorMap xmap, __nv_bfloat16* __restrict__ y, int B, int Do, int Ho,
+                       int Wo, int tiles_w, int tiles_h, int nsplit) {
+  extern __shared__ uint8_t ap_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ap_smem_raw) + 127) & ~uintptr_t(127));
+  __shared__ uint64_t full[2];
+  const int tid = threadIdx.x;
+  int r = blockIdx.x;
+  const int tw = r % tiles_w; r /= tiles_w;
+  const int th = r % tiles_h; r /= tiles_h;
+  const int sp = r % nsplit;
+  const int b = r / nsplit;
+  const int dper = (Do + nsplit - 1) / nsplit;
+  const int da = sp * dper, db = min(Do, da + dper);
+  if (da >= db) return;
+  const int nplanes = 2 * (db - da) + 1;           // input planes 2*da - 1 .. 2*db - 1
+  if (tid == 0) {
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&xmap);
+  }
+  __syncthreads();
+  auto issue = [&](int i) {
+    uint8_t* dst = smem + (size_t)(i & 1) * PLANES * AP_PITCH;
+    mbar_expect_tx(&full[i & 1], PLANES * AP_BOX);
+#pragma unroll
+    for (int pl = 0; pl < PLANES; ++pl)
+      tma_load_5d(dst + pl * AP_PITCH, &xmap, &full[i & 1], 0, 2 * tw * AP_TW - 1, 2 * th * AP_TH - 1, 2 * da - 1 + i, pl * B + b);
+  };
+  if (tid == 0) { issue(0); if (nplanes > 1) issue(1); }
+  const int c8 = tid & 3, vox = tid >> 2;
+  const int ow = vox % AP_TW, oh = vox / AP_TW;
+  const int gw = tw * AP_TW + ow, gh = th * AP_TH + oh;
+  const bool valid = gw < Wo && gh < Ho;
+  const size_t yplane = (size_t)B * Do * Ho * Wo * 32;
+  float2 acc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc[k] = make_float2(0.f, 0.f);
+  for (int i = 0; i < nplanes; ++i) {
+    mbar_wait(&full[i & 1], (uint32_t)((i >> 1) & 1));
+    const uint8_t* src = smem + (size_t)(i & 1) * PLANES * AP_PITCH;
+    float2 rs[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) rs[k] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int off = ((2 * oh + dy) * AP_BW + (2 * ow + dx)) * 64 + c8 * 16;
+#pragma unroll
+        for (int pl = 0; pl < PLANES; ++pl) {
+          const uint4 v = *reinterpret_cast<const uint4*>(src + pl * AP_PITCH + off);
+          float f[8];
+          unpack8(v, f);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) rs[k] = __fadd2_rn(rs[k], make_float2(f[2 * k], f[2 * k + 1]));
+        }
+      }
+    __syncthreads();                                // every thread has read this slot
+    if (tid == 0 && i + 2 < nplanes) issue(i + 2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = __fadd2_rn(acc[k], rs[k]);
+    if ((i & 1) == 0 && i >= 2) {                   // plane 2d+1 closes output depth d = da + i/2 - 1 ...
+      if (valid) {
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { o[2 * k] = acc[k].x * (1.0f / 27.0f); o[2 * k + 1] = acc[k].y * (1.0f / 27.0f); }
+        const int od = da + (i >> 1) - 1;
+        store8<PLANES>(y, yplane, ((((size_t)b * Do + od) * Ho + gh) * Wo + gw) * 32 + c8 * 8, o);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] = rs[k];   // ... and opens d + 1
+    }
+  }
+}
+
+extern "C" int dca_avgpool3d_simple(const void* x, void* y, int planes, int B, int C, int Di, int Hi, int Wi, void* stream);
+
 template <int PLANES>
 static int launch_deconv_pair(const TcMaps& maps, const TcParams& p, const Up2Params& u, cudaStream_t st) {
   using Cfg = DeconvPairCfg<PLANES>;
@@ -1951,6 +2043,8 @@ static int launch_deconv_pair(const TcMaps& maps, const TcParams& p, const Up2Pa
 }
 
 static int g_use_deconv_pair = 1;
+static int g_use_pool_march = 1;
+static int g_pool_ctas_per_sm = 4;   // measured at KITTI: 2: 50 us, 4: 44 us, 8: 47 us (thread-per-output kernel: 66 us)
 
 }  // namespace dca
 
@@ -2458,3 +2552,54 @@ extern "C" int dca_conv3d_tc_taps27(const void* x, int planes, const void* w, in
   if (Cin == 32) return Pn == 2 ? launch_tc_halo<32, 32, 2, 1>(maps, p, st, &tw) : launch_tc_halo<32, 32, 1, 1>(maps, p, st, &tw);
   return Pn == 2 ? launch_tc_halo<64, 32, 2, 1>(maps, p, st, &tw) : launch_tc_halo<64, 32, 1, 1>(maps, p, st, &tw);
 }
+
+// AvgPool3d k3 s2 p1 (count_include_pad) of cost planes [planes][B][Di][Hi][Wi][C] -> [planes][B][ceil/2 ...][C].
+// C == 32: TMA-staged depth-marching kernel (every input plane read once); otherwise the thread-per-output kernel.
+extern "C" int dca_avgpool3d(const void* x, void* y, int planes, int B, int C, int Di, int Hi, int Wi, void* stream) {
+  if (!x || !y || C % 8 != 0 || B <= 0 || Di <= 0 || Hi <= 0 || Wi <= 0 || planes < 1 || planes > 2) return DCA_ERR_ARG;
+  if (C != 32 || !g_use_pool_march) return dca_avgpool3d_simple(x, y, planes, B, C, Di, Hi, Wi, stream);
+  const int Do = (Di + 1) / 2, Ho = (Hi + 1) / 2, Wo = (Wi + 1) / 2;
+  CUtensorMap xmap;
+  {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return DCA_ERR_LAUNCH;
+    cuuint64_t dims[5] = {32, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Di, (cuuint64_t)planes * B};
+    cuuint64_t strides[4] = {64, (cuuint64_t)Wi * 64, (cuuint64_t)Hi * Wi * 64, (cuuint64_t)Di * Hi * Wi * 64};
+    cuuint32_t box[5] = {32, AP_BW, AP_BH, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    if (enc(&xmap, (DCA_F16_PLANES ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 5,
+            const_cast<void*>(x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return dca_avgpool3d_simple(x, y, planes, B, C, Di, Hi, Wi, stream);     // (tensors smaller than one box)
+  }
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  const int tiles_w = (Wo + AP_TW - 1) / AP_TW, tiles_h = (Ho + AP_TH - 1) / AP_TH;
+  const long long cols = (long long)B * tiles_w * tiles_h;
+  int nsplit = (int)(((long long)g_pool_ctas_per_sm * g_num_sms + cols - 1) / cols);   // CTAs per SM so that loads and sums overlap
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > Do) nsplit = Do;
+  const long long grid = cols * nsplit;
+  if (grid > 0x7fffffffLL) return DCA_ERR_UNSUPPORTED;
+  const int smem = 2 * planes * AP_PITCH + 128;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (planes == 2) {
+    cudaFuncSetAttribute(avgpool3d_march_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    avgpool3d_march_kernel<2><<<(int)grid, AP_TW * AP_TH * 4, smem, st>>>(xmap, (__nv_bfloat16*)y, B, Do, Ho, Wo, tiles_w,
+                                                                          tiles_h, nsplit);
+  } else {
+    cudaFuncSetAttribute(avgpool3d_march_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    avgpool3d_march_kernel<1><<<(int)grid, AP_TW * AP_TH * 4, smem, st>>>(xmap, (__nv_bfloat16*)y, B, Do, Ho, Wo, tiles_w,
+                                                                          tiles_h, nsplit);
+  }
+  DCA_RETURN_IF_LAUNCH_FAILED();
+  return DCA_OK;
+}
+
+// 1 (default): dca_avgpool3d uses the depth-marching TMA kernel for C == 32; 0: always the thread-per-output kernel
+// on > 1 additionally sets the number of CTAs per SM the depth range is split for (default 4)
+extern "C" int dca_pool_set_march(int on) { g_use_pool_march = on ? 1 : 0; if (on > 1) g_pool_ctas_per_sm = on; return DCA_OK; }

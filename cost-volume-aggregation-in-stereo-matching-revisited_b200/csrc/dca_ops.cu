@@ -1060,7 +1060,8 @@ static inline int grid_for(size_t total, int threads) {
 
 using namespace dca;
 
-extern "C" int dca_avgpool3d(const void* x, void* y, int planes, int B, int C, int Di, int Hi, int Wi, void* stream) {
+// thread-per-output form (any C % 8 == 0); dca_avgpool3d (conv_tc.cu) takes the TMA-staged depth-marching kernel for C == 32
+extern "C" int dca_avgpool3d_simple(const void* x, void* y, int planes, int B, int C, int Di, int Hi, int Wi, void* stream) {
   if (!x || !y || C % 8 != 0 || B <= 0 || Di <= 0 || Hi <= 0 || Wi <= 0 || planes < 1 || planes > 2)
     return DCA_ERR_ARG;
   const int Do = (Di + 1) / 2, Ho = (Hi + 1) / 2, Wo = (Wi + 1) / 2;

@@ -141,7 +141,11 @@ int dca_tc_set_trunc_comp(float kappa);
 int dca_tc_set_deconv_pair(int on);
 
 /* (2) DCA module ------------------------------------------------------------------------------- */
+/* AvgPool3d(3, 2, 1) (cva.py:39).  C == 32: TMA-staged depth-marching kernel (each input plane read once); other C, or
+ * after dca_pool_set_march(0): the thread-per-output kernel dca_avgpool3d_simple.  Same results (sum order differs). */
 int dca_avgpool3d(const void* x, void* y, int planes, int B, int C, int Di, int Hi, int Wi, void* stream);
+int dca_avgpool3d_simple(const void* x, void* y, int planes, int B, int C, int Di, int Hi, int Wi, void* stream);
+int dca_pool_set_march(int on);
 /* logits fp32 [B,D,H,W] -> class map int32 [B,H,W], e = exp(P[k_p]) [B,H,W], S [B,D].  S is summed in 64-bit fixed
  * point (order-independent: two runs are bit-identical); scratch = (B*D + 1) x 8 bytes, 8-byte aligned, zeroed here. */
 int dca_class_stats(const float* logits, int* cls, float* e, float* S, void* scratch, int B, int D, int H, int W,

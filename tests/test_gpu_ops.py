@@ -246,6 +246,26 @@ def test_avgpool_and_planes_roundtrip():
     close(E.Planes.from_ncdhw(x.cuda(), 1).to_ncdhw(), x.to(E.plane_dtype()).float(), 1e-7, "16-bit roundtrip")
 
 
+@pytest.mark.parametrize("B,C,D,H,W,planes", [(1, 32, 12, 16, 32, 2), (2, 32, 5, 7, 19, 2), (1, 32, 48, 20, 36, 2), (1, 32, 6, 9, 21, 1),
+                                               (1, 32, 1, 1, 1, 2), (1, 32, 24, 48, 80, 2), (1, 64, 6, 10, 14, 2)])
+def test_avgpool_kernels(B, C, D, H, W, planes):
+    """AvgPool3d(3, 2, 1), count_include_pad (cva.py:39): the TMA depth-marching kernel (C == 32, odd and even sizes,
+    several depth splits) and the thread-per-output kernel against torch, and against each other."""
+    d, E, O = _mods()
+    x = rnd(B, C, D, H, W, seed=12)
+    xp = E.Planes.from_ncdhw(x.cuda(), planes)
+    ref = F.avg_pool3d(x if planes == 2 else x.to(E.plane_dtype()).float(), 3, 2, 1)
+    tol = 3e-5 if planes == 2 else 2e-3
+    got = E.avgpool(xp)
+    close(got.to_ncdhw(), ref, tol, "avgpool (default kernel)")
+    d._lib.call("dca_pool_set_march", 0)
+    try:
+        simple = E.avgpool(xp)
+    finally:
+        d._lib.call("dca_pool_set_march", 1)
+    close(simple.to_ncdhw(), ref, tol, "avgpool (thread-per-output kernel)")
+
+
 def test_class_stats_exact_mask():
     d, E, O = _mods()
     logits = rnd(3, 24, 13, 29, seed=12) * 2.0
