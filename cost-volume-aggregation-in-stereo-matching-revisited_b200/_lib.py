@@ -39,6 +39,8 @@ SIGNATURES = {
     "dca_pack_weights_tc2d": [_vp, _c_int, _c_int, _vp, _c_int, _vp],
     "dca_pack_weights_tc2d_bytes": [_c_int] * 3,
     "dca_tc_set_halo": [_c_int],
+    "dca_set_pdl": [_c_int],
+    "dca_pdl_enabled": [],
     "dca_tc_set_deconv_pair": [_c_int],
     "dca_volume_set_v2": [_c_int],
     "dca_attention_set_team": [_c_int],
@@ -96,6 +98,8 @@ def load():
         fn.argtypes = args
         fn.restype = _RESTYPES.get(name, ctypes.c_int)
     _lib = lib
+    if os.environ.get("DCA_PDL", "1") == "0":       # diagnostics: plain stream order instead of programmatic dependent launch
+        lib.dca_set_pdl(0)
     return lib
 
 

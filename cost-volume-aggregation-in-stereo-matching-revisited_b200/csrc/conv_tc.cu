@@ -633,6 +633,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();                 // persistent single-wave grid: let the next kernel's CTAs take over SMs as ours retire
+  if (warp != 0) pdl_wait();     // (the producer warp waits after its loads of static weights, see below)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -641,6 +643,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       // single-tap launches (1x1x1 convs, per-tap GEMMs): every stage slot always holds the same weight tile, so it is
       // loaded only on the first pass over the ring (148 SMs re-reading one 4 KB tile per 128 voxels is an L2 hot spot)
       const bool one_tap = (p.ntaps == 1 && p.ncls == 1);
+      pdl_wait();
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int r = tile;
         const int cls = r % p.ncls; r /= p.ncls;
@@ -799,6 +802,8 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();                 // persistent single-wave grid: let the next kernel's CTAs take over SMs as ours retire
+  if (warp != 0) pdl_wait();     // (the producer warp waits after its loads of static weights, see below)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -807,6 +812,7 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
         mbar_expect_tx(&wfull[0], p.nslab * 9 * Cfg::B_BYTES);
         for (int t = 0; t < p.nslab * 9; ++t) tma_load_2d(w_base + t * Cfg::B_BYTES, &maps.w, &wfull[0], 0, t * Cfg::B_ROWS);
       }
+      pdl_wait();                // weights are static; everything below reads the previous kernel's output
       uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int r = tile;
@@ -981,10 +987,13 @@ conv_tc_s2slab_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();                 // persistent single-wave grid: let the next kernel's CTAs take over SMs as ours retire
+  if (warp != 0) pdl_wait();     // (the producer warp waits after its loads of static weights, see below)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      pdl_wait();
       uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int r = tile;
@@ -1167,6 +1176,8 @@ conv_tc_up2_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();                 // persistent single-wave grid: let the next kernel's CTAs take over SMs as ours retire
+  if (warp != 0) pdl_wait();     // (the producer warp waits after its loads of static weights, see below)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -1176,6 +1187,7 @@ conv_tc_up2_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const 
         mbar_expect_tx(&wfull[0], u.nw * Cfg::B_BYTES);
         for (int i = 0; i < u.nw; ++i) tma_load_2d(w_base + i * Cfg::B_BYTES, &maps.w, &wfull[0], 0, i * Cfg::B_ROWS);
       }
+      pdl_wait();
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int r = tile;
         const int tw = r % p.tiles_w; r /= p.tiles_w;
@@ -1381,12 +1393,15 @@ conv_tc_deconv_pair_kernel(const __grid_constant__ TcMaps maps, const TcParams p
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();                 // persistent single-wave grid: let the next kernel's CTAs take over SMs as ours retire
+  if (warp != 0) pdl_wait();     // (the producer warp waits after its loads of static weights, see below)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       mbar_expect_tx(wsfull, Cfg::B_BYTES);
       tma_load_2d(wside, &maps.w, wsfull, 0, u.side_widx * Cfg::B_ROWS);
+      pdl_wait();
       uint32_t ps = 0, pd = 0, sw = 0, pw = 0;
       for (int pair = blockIdx.x; pair < total_pairs; pair += gridDim.x) {
         int r = pair;
@@ -1599,6 +1614,8 @@ conv_tc_march_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();                 // persistent single-wave grid: let the next kernel's CTAs take over SMs as ours retire
+  if (warp != 0) pdl_wait();     // (the producer warp waits after its loads of static weights, see below)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -1608,6 +1625,7 @@ conv_tc_march_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
         for (int t = 0; t < 9; ++t)
           tma_load_2d(w_base + t * Cfg::TAP_BYTES, &maps.w, &wfull[0], 0, t * PLANES * 3 * COUT);
       }
+      pdl_wait();
       uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         int r = item;
@@ -1754,7 +1772,7 @@ static int launch_tc_march(const TcMaps& maps, const TcParams& p, cudaStream_t s
   TcParams q = p; fill_recips(q);
   for (int c = 0; c < 8; ++c) fill_comp(q, c, 27 * (CIN / 16));
   typename TapArg<TAPS>::type none{};
-  conv_tc_march_kernel<CIN, PLANES, TAPS><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, q, tw ? *tw : none);
+  dca_launch(conv_tc_march_kernel<CIN, PLANES, TAPS>, grid, TC_THREADS, Cfg::SMEM_BYTES, st, maps, q, tw ? *tw : none);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }
@@ -1840,7 +1858,7 @@ static int launch_tc(const TcMaps& maps, const TcParams& p, cudaStream_t st) {
   TcParams q = p; fill_recips(q);
   for (int c = 0; c < 8; ++c)
     fill_comp(q, c, (c < q.ncls ? (int)q.cls_tap0[c + 1] - (int)q.cls_tap0[c] : 0) * (CIN / 16));
-  conv_tc_kernel<CIN, COUT, PLANES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, q);
+  dca_launch(conv_tc_kernel<CIN, COUT, PLANES>, grid, TC_THREADS, Cfg::SMEM_BYTES, st, maps, q);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }
@@ -1860,7 +1878,7 @@ static int launch_tc_s2slab(const TcMaps& maps, const TcParams& p, cudaStream_t 
   const int grid = total < g_num_sms ? total : g_num_sms;
   TcParams q = p; fill_recips(q);
   for (int c = 0; c < 8; ++c) fill_comp(q, c, 27 * 2);
-  conv_tc_s2slab_kernel<PLANES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, q);
+  dca_launch(conv_tc_s2slab_kernel<PLANES>, grid, TC_THREADS, Cfg::SMEM_BYTES, st, maps, q);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }
@@ -1884,7 +1902,7 @@ static int launch_tc_halo(const TcMaps& maps, const TcParams& p, cudaStream_t st
   TcParams q = p; fill_recips(q);
   for (int c = 0; c < 8; ++c) fill_comp(q, c, q.nslab * 9 * (CIN / 16));
   typename TapArg<TAPS>::type none{};
-  conv_tc_halo_kernel<CIN, COUT, PLANES, TAPS><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, q, tw ? *tw : none);
+  dca_launch(conv_tc_halo_kernel<CIN, COUT, PLANES, TAPS>, grid, TC_THREADS, Cfg::SMEM_BYTES, st, maps, q, tw ? *tw : none);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }
@@ -1923,7 +1941,7 @@ static int launch_up2(const TcMaps& maps, const TcParams& p, const Up2Params& u,
   TcParams q = p; fill_recips(q);
   for (int c = 0; c < 8; ++c)
     fill_comp(q, c, (c < q.ncls ? (int)u.cls_tap0[c + 1] - (int)u.cls_tap0[c] : 0) * (CIN / 16) + (u.has_side ? 2 : 0));
-  conv_tc_up2_kernel<CIN, PLANES, NSLAB><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, q, u);
+  dca_launch(conv_tc_up2_kernel<CIN, PLANES, NSLAB>, grid, TC_THREADS, Cfg::SMEM_BYTES, st, maps, q, u);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }
@@ -1971,6 +1989,7 @@ avgpool3d_march_kernel(const __grid_constant__ CUtensorMap xmap, __nv_bfloat16* 
     for (int pl = 0; pl < PLANES; ++pl)
       tma_load_5d(dst + pl * AP_PITCH, &xmap, &full[i & 1], 0, 2 * tw * AP_TW - 1, 2 * th * AP_TH - 1, 2 * da - 1 + i, pl * B + b);
   };
+  pdl_wait();
   if (tid == 0) { issue(0); if (nplanes > 1) issue(1); }
   const int c8 = tid & 3, vox = tid >> 2;
   const int ow = vox % AP_TW, oh = vox / AP_TW;
@@ -2037,7 +2056,7 @@ static int launch_deconv_pair(const TcMaps& maps, const TcParams& p, const Up2Pa
   const int grid = total < g_num_sms ? total : g_num_sms;
   TcParams q = p; fill_recips(q);
   for (int c = 0; c < 8; ++c) fill_comp(q, c, ((int)u.cls_tap0[c + 1] - (int)u.cls_tap0[c]) * 4 + 2);
-  conv_tc_deconv_pair_kernel<PLANES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(maps, q, u);
+  dca_launch(conv_tc_deconv_pair_kernel<PLANES>, grid, TC_THREADS, Cfg::SMEM_BYTES, st, maps, q, u);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }
@@ -2589,12 +2608,12 @@ extern "C" int dca_avgpool3d(const void* x, void* y, int planes, int B, int C, i
   cudaStream_t st = (cudaStream_t)stream;
   if (planes == 2) {
     cudaFuncSetAttribute(avgpool3d_march_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    avgpool3d_march_kernel<2><<<(int)grid, AP_TW * AP_TH * 4, smem, st>>>(xmap, (__nv_bfloat16*)y, B, Do, Ho, Wo, tiles_w,
-                                                                          tiles_h, nsplit);
+    dca_launch(avgpool3d_march_kernel<2>, (int)grid, AP_TW * AP_TH * 4, smem, st, xmap, (__nv_bfloat16*)y, B, Do, Ho, Wo,
+               tiles_w, tiles_h, nsplit);
   } else {
     cudaFuncSetAttribute(avgpool3d_march_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    avgpool3d_march_kernel<1><<<(int)grid, AP_TW * AP_TH * 4, smem, st>>>(xmap, (__nv_bfloat16*)y, B, Do, Ho, Wo, tiles_w,
-                                                                          tiles_h, nsplit);
+    dca_launch(avgpool3d_march_kernel<1>, (int)grid, AP_TW * AP_TH * 4, smem, st, xmap, (__nv_bfloat16*)y, B, Do, Ho, Wo,
+               tiles_w, tiles_h, nsplit);
   }
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;

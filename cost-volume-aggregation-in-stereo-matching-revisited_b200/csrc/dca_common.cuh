@@ -9,6 +9,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <string.h>
 
 #define DCA_OK 0
 #define DCA_ERR_ARG (-1)
@@ -20,6 +21,31 @@
     cudaError_t e__ = cudaGetLastError();                  \
     if (e__ != cudaSuccess) return DCA_ERR_LAUNCH;         \
   } while (0)
+
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------
+// Every kernel of the forward is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it may start while the
+// previous kernel of the stream is still draining, runs its prologue (mbarrier init, TMEM allocation, tensor-map
+// prefetch, loads of STATIC data such as resident weights) and then executes griddepcontrol.wait, which returns once the
+// previous grid has completed and its memory is visible.  Persistent single-wave kernels call
+// griddepcontrol.launch_dependents at their very start, so the successor's CTAs take over SMs as this kernel's CTAs
+// retire.  A kernel must not read data produced by, nor write data read by, an earlier kernel before pdl_wait().
+// dca_set_pdl(0) launches everything fully serialised (same results).
+extern "C" int dca_pdl_enabled(void);
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... Exp, typename... Act>
+static inline cudaError_t dca_launch(void (*kern)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Act&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = dca_pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<Exp>(args)...);
+}
 
 namespace dca {
 

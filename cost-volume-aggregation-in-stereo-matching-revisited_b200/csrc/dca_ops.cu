@@ -82,6 +82,7 @@ class_stats_kernel(const float* __restrict__ logits, int* __restrict__ cls, floa
                    int D, int HW, int BD) {
   __shared__ unsigned long long s_sum[CS_MAXD];
   __shared__ int s_last;
+  pdl_wait();
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < D; i += blockDim.x) s_sum[i] = 0ull;
   __syncthreads();
@@ -300,6 +301,8 @@ disp_attention_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict
   for (int i = threadIdx.x; i < 6 * 64; i += blockDim.x) ss[i] = __ldg(wts + AT_NMAT * AT_C * AT_C + i);
   // zero this warp's buffers once: rows [D, ROWS) are never loaded and must stay finite
   for (int i = lane + 32 * wip; i < TEAM_BYTES / 4; i += 32 * WPP) reinterpret_cast<uint32_t*>(wbase)[i] = 0u;
+  pdl_trigger();       // persistent single-wave grid; the weight staging above only read static data
+  pdl_wait();
   __syncthreads();
   const __nv_bfloat16* Wq0 = Wsm, *Wq1 = Wsm + 2 * AT_WPLANE, *Wk0 = Wsm + 4 * AT_WPLANE, *Wk1 = Wsm + 6 * AT_WPLANE,
                       *Wv = Wsm + 8 * AT_WPLANE, *Wo = Wsm + 10 * AT_WPLANE, *Wa = Wsm + 12 * AT_WPLANE;
@@ -843,6 +846,7 @@ __global__ void __launch_bounds__(256)
 convex_upsample_kernel(const float* __restrict__ mask, const float* __restrict__ disp, float* __restrict__ out, int B,
                        int H, int W) {
   const size_t total = (size_t)B * H * W * 4;
+  pdl_wait();
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
     const int i = (int)(idx & 3);
@@ -952,6 +956,7 @@ __global__ void __launch_bounds__(256)
 tap_gather3d_kernel(const float* __restrict__ P, float* __restrict__ out, int B, int D, int H, int W) {
   const size_t nvox = (size_t)B * D * H * W;
   const int HW = H * W;
+  pdl_wait();
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
     const int w = (int)(v % W);
     size_t r = v / W;
@@ -997,6 +1002,7 @@ tap_gather_softmax_regress_kernel(const float* __restrict__ P, float* __restrict
   const int chunk = (D + TG_DG - 1) / TG_DG;
   const int d0 = g * chunk, d1 = min(D, d0 + chunk);
   float m = -INFINITY, sum = 0.f, acc = 0.f;
+  pdl_wait();
   if (w < W) {
     // in-plane validity of the 9 (kh, kw) neighbours and their clamped offsets (an invalid tap reads the centre voxel,
     // its value is discarded): the 27 loads of a voxel are UNCONDITIONAL and independent, so they are all in flight
@@ -1086,8 +1092,8 @@ extern "C" int dca_class_stats(const float* logits, int* cls, float* e, float* S
   cudaStream_t st = (cudaStream_t)stream;
   if (cudaMemsetAsync(scratch, 0, ((size_t)B * D + 1) * sizeof(unsigned long long), st) != cudaSuccess) return DCA_ERR_LAUNCH;
   const int HW = H * W;
-  class_stats_kernel<<<dim3((HW + 255) / 256, B), 256, 0, st>>>(logits, cls, e, S, (unsigned long long*)scratch, D, HW,
-                                                                B * D);
+  dca_launch(class_stats_kernel, dim3((HW + 255) / 256, B), 256, 0, st, logits, cls, e, S, (unsigned long long*)scratch, D,
+             HW, B * D);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }
@@ -1119,8 +1125,8 @@ static int attention_launch(const void* x, const int* cls, const float* e, const
   do {                                                                                                           \
     auto kern = disp_attention_kernel<P_, MT_, DT_, WPP_, CORE_>;                                                          \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
-    kern<<<grid, warps * 32 * WPP_, smem, st>>>((const __nv_bfloat16*)x, cls, e, S, weights, has_wa,              \
-                                                (__nv_bfloat16*)y, B, D, H, W, pad, (const __nv_bfloat16*)key);   \
+    dca_launch(kern, grid, warps * 32 * WPP_, smem, st, (const __nv_bfloat16*)x, cls, e, S, weights, has_wa,       \
+               (__nv_bfloat16*)y, B, D, H, W, pad, (const __nv_bfloat16*)key);                                    \
   } while (0)
 #define DCA_AT_LAUNCH(P_, MT_) DCA_AT_LAUNCH2(P_, MT_, 0, 1, 0)
   if (D == 24 && g_attention_team == 1) {          // two warps per pixel, tensor-core attention core
@@ -1193,7 +1199,7 @@ extern "C" int dca_convex_upsample(const float* mask, const float* disp, float* 
                                    void* stream) {
   if (!mask || !disp || !out || B <= 0 || H <= 0 || W <= 0) return DCA_ERR_ARG;
   const size_t total = (size_t)B * H * W * 4;
-  convex_upsample_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mask, disp, out, B, H, W);
+  dca_launch(convex_upsample_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, mask, disp, out, B, H, W);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }
@@ -1201,7 +1207,7 @@ extern "C" int dca_convex_upsample(const float* mask, const float* disp, float* 
 extern "C" int dca_tap_gather3d(const float* P, float* out, int B, int D, int H, int W, void* stream) {
   if (!P || !out || B <= 0 || D <= 0 || H <= 0 || W <= 0) return DCA_ERR_ARG;
   const size_t total = (size_t)B * D * H * W;
-  tap_gather3d_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(P, out, B, D, H, W);
+  dca_launch(tap_gather3d_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, P, out, B, D, H, W);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }
@@ -1211,8 +1217,8 @@ extern "C" int dca_tap_gather3d(const float* P, float* out, int B, int D, int H,
 extern "C" int dca_tap_gather_softmax_regress(const float* P, float* pred, float* logits_out, int B, int D, int H, int W,
                                               void* stream) {
   if (!P || !pred || B <= 0 || D <= 0 || H <= 0 || W <= 0 || H > 65535 || B > 65535) return DCA_ERR_ARG;
-  tap_gather_softmax_regress_kernel<<<dim3((W + 31) / 32, H, B), 32 * TG_DG, 0, (cudaStream_t)stream>>>(P, pred,
-                                                                                                    logits_out, B, D, H, W);
+  dca_launch(tap_gather_softmax_regress_kernel, dim3((W + 31) / 32, H, B), 32 * TG_DG, 0, (cudaStream_t)stream, P, pred,
+             logits_out, B, D, H, W);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }
@@ -1258,6 +1264,11 @@ extern "C" int dca_fold_bn(const float* gamma, const float* beta, const float* m
   return DCA_OK;
 }
 
-extern "C" int dca_version(void) { return 101; }
+static int g_pdl = 1;
+extern "C" int dca_pdl_enabled(void) { return g_pdl; }
+// 1 (default): kernels are launched with programmatic stream serialization (PDL, dca_common.cuh); 0: fully serialised
+extern "C" int dca_set_pdl(int on) { g_pdl = on ? 1 : 0; return DCA_OK; }
+
+extern "C" int dca_version(void) { return 102; }
 // 16-bit format of the cost planes and operand packs this build was compiled for: 1 = IEEE fp16 (default), 0 = bf16
 extern "C" int dca_plane_format(void) { return DCA_F16_PLANES ? 1 : 0; }

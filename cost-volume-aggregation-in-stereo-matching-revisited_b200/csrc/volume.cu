@@ -289,6 +289,8 @@ volume_fused3_kernel(const __grid_constant__ VolMaps maps, __nv_bfloat16* __rest
     }
   };
 
+  pdl_trigger();      // persistent single-wave grid (dca_common.cuh)
+  pdl_wait();         // the feature maps come from the previous kernel / copy of the stream
   if (tid == 0) {
     v_mbar_init(&full[0], 1); v_mbar_init(&full[1], 1);
     cnt[0] = 0; cnt[1] = 0;
@@ -487,11 +489,11 @@ static int launch_volume3(const float* gl, const float* gr, const float* cl, con
   if (planes == 2) {
     auto kern = volume_fused3_kernel<2, G, CPG, CC, CV>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    kern<<<grid, V3_THREADS, Cfg::SMEM_BYTES, st>>>(maps, (__nv_bfloat16*)vol, B, D, H, W, g_volume_v2 >> 1);
+    dca_launch(kern, grid, V3_THREADS, Cfg::SMEM_BYTES, st, maps, (__nv_bfloat16*)vol, B, D, H, W, g_volume_v2 >> 1);
   } else {
     auto kern = volume_fused3_kernel<1, G, CPG, CC, CV>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    kern<<<grid, V3_THREADS, Cfg::SMEM_BYTES, st>>>(maps, (__nv_bfloat16*)vol, B, D, H, W, g_volume_v2 >> 1);
+    dca_launch(kern, grid, V3_THREADS, Cfg::SMEM_BYTES, st, maps, (__nv_bfloat16*)vol, B, D, H, W, g_volume_v2 >> 1);
   }
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;

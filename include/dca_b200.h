@@ -136,6 +136,11 @@ int dca_tc_set_tuning(int reserved, int flags);
  * accumulation step).  The tcgen05 conv epilogues multiply the main accumulator block by 1 + kappa * steps; this sets
  * kappa (default 1.56e-8f, 0 = off). */
 int dca_tc_set_trunc_comp(float kappa);
+/* Programmatic dependent launch: 1 (default) = every kernel of the forward is launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization and waits (griddepcontrol.wait) after its prologue, so prologues
+ * and launch latency overlap the previous kernel's tail; 0 = plain stream order.  Same results. */
+int dca_set_pdl(int on);
+int dca_pdl_enabled(void);
 /* dca_up2_tc kind 0 with Cin = 64 and a side input: 1 (default) = two depth-adjacent tiles per weight fetch
  * (conv_tc_deconv_pair_kernel), 0 = one tile per fetch (conv_tc_up2_kernel); same results. */
 int dca_tc_set_deconv_pair(int on);
