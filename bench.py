@@ -118,9 +118,14 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
-def common_config(cfg, n_gpus):
+def common_config(cfg, n_gpus, batch=0):
     """The workload description shared, key for key, by both arms (the driver compares the dicts)."""
     H, W, maxdisp, B = workloads.CONFIGS[cfg]
+    if batch:
+        z = common_config(cfg, n_gpus)
+        z["batch_total"] = batch
+        z["parallelism"] = f"{batch} pairs per step, {batch // n_gpus} per GPU over {n_gpus} GPU(s), no collective"
+        return z
     return {"workload": cfg, "H": H, "W": W, "maxdisp": maxdisp, "batch_per_gpu": B, "groups": 40,
             "precision": "parity (|d disp| <= 0.05 px of the fp32 torch forward)",
             "parallelism": f"pairs sharded over {n_gpus} GPU(s), no collective",
@@ -274,6 +279,9 @@ def main():
     ap.add_argument("--hshard", action="store_true",
                     help="configs[4] mode: ONE pair per step, its rows split over the N ranks (halo exchange + 3 "
                          "all-reduces per forward, strong scaling); needs torchrun with N > 1")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="configs[2] mode: a step is BATCH pairs in total, split BATCH/N per GPU (each rank runs its share "
+                         "as consecutive single-pair forwards); 0 (default) = one pair per GPU per step")
     ap.add_argument("--latency-steps", type=int, default=200,
                     help="extra latency loop after the K timed steps (p50/p90 in the `latency` key; 0 = skip)")
     ap.add_argument("--no-hshard-record", action="store_true",
@@ -298,7 +306,7 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
                 "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": common_config(args.config, args.gpus),
+                "config": common_config(args.config, args.gpus, args.batch),
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -320,6 +328,9 @@ def main():
     if args.no_tc:
         d.engine.Options.use_tc = False
     K, Wm = max(1, args.steps), max(3, args.warmup)
+    if args.batch and args.batch % world:
+        raise SystemExit(f"--batch {args.batch} does not split over {world} ranks")
+    ppr = args.batch // world if args.batch else 1          # pairs per rank and step
     net = workloads.init_bench_weights_(d.GwcNet(maxdisp, precision=args.precision), 0).to(dev).eval()
     H4, W4 = H // 4, W // 4
 
@@ -356,8 +367,12 @@ def main():
 
     # ---------------- device-resident throughput ----------------
     with torch.no_grad():
+        def step(i):
+            for j in range(ppr):
+                net.hot_path(*dev_sets[(i * ppr + j) % nsets])
+
         for i in range(Wm):
-            net.hot_path(*dev_sets[i % nsets])
+            step(i)
         d._lib.LAUNCHES = 0
         gc.collect()
         gc.disable()                     # no collector pause inside the timed regions
@@ -368,7 +383,7 @@ def main():
         barrier()
         ev[0].record()
         for i in range(K):
-            net.hot_path(*dev_sets[i % nsets])
+            step(i)
             ev[i + 1].record()
         barrier()
         launches = d._lib.LAUNCHES
@@ -390,7 +405,7 @@ def main():
         barrier()
         e0.record(pipe.copy_stream)
         last = 0
-        for i in range(K):
+        for i in range(K * ppr):
             last = pipe.submit(i, host_sets[i % nsets])
         pipe.wait(last)
         e1.record(pipe.compute_stream)
@@ -476,7 +491,7 @@ def main():
 
     # ---------------- configs[4] sub-record: one Middlebury pair H-sharded over the N ranks ----------------
     hrec = None
-    if dist is not None and not args.no_hshard_record:
+    if dist is not None and not args.no_hshard_record and not args.batch:
         del dev_sets, host_sets, pipe
         torch.cuda.empty_cache()
         mcfg = "middlebury_1536x2048"
@@ -506,20 +521,20 @@ def main():
     if dist is not None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms = float(tt[0]), float(tt[1])
-    pairs = K * B * world
+    pairs = K * B * ppr * world
     if rank == 0:
         line = {"metric": METRIC, "value": pairs / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
-                "warmup": Wm, "ms_per_step": total_ms / K, "p50_ms_per_pair": statistics.median(step_ms) / B,
+                "warmup": Wm, "ms_per_step": total_ms / K, "p50_ms_per_pair": statistics.median(step_ms) / B / ppr,
                 "max_step_ms": max(step_ms), "max_step_index": step_ms.index(max(step_ms)),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16x2 split operands (hi+lo fp16 planes, 22-bit significand), fp32 accumulate" if args.precision == "parity"
                 else "f16 operands, fp32 accumulate",
                 "data": "synthetic",
-                "config": common_config(args.config, world),
+                "config": common_config(args.config, world, args.batch),
                 "precision_mode": args.precision,
                 "clocks": sampler.summary(),
-                "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K,
+                "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * ppr,
+                        "d2h_bytes_per_step": d2h * ppr, "ms_per_step": e2e_ms / K,
                         "what": "HotPathPipeline: pinned host feature maps -> H2D (copy stream, overlapped) -> hot path -> D2H of pred4 + prob_volume2 into pinned host buffers"},
                 "gpu_launches": launches,
                 "roofline": roof}
