@@ -224,6 +224,10 @@ def measure_hshard(cfg, transport, d, net, dist, dev, rank, world, barrier, K, W
         e1.record()
         t_issue = time.perf_counter() - t_host0          # host time to ISSUE the K forwards (no sync inside)
         barrier()
+        t1 = time.perf_counter()                         # one forward issued into an IDLE device: the host-side cost alone
+        net.hot_path_hsharded(*slabs[0], rank=rank, world=world, transport=transport)
+        t_single = time.perf_counter() - t1
+        barrier()
     for peer in hs._PEERS.values():      # p2p transport: a timed-out wait (neighbour never pushed) invalidates the run
         peer.check()
     launches = d._lib.LAUNCHES
@@ -236,7 +240,7 @@ def measure_hshard(cfg, transport, d, net, dist, dev, rank, world, barrier, K, W
     torch.cuda.empty_cache()
     return {"workload": cfg, "H": H, "W": W, "maxdisp": maxdisp, "batch": B, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_pair": ms / K / B, "pairs_per_s": K * B / (ms * 1e-3), "transport": transport,
-            "host_issue_ms_per_pair": float(tt[1]) / K / B,
+            "host_issue_ms_per_pair": float(tt[1]) / K / B, "host_issue_ms_idle_device": t_single * 1e3,
             "rows_per_rank": r1 - r0, "halo_rows_per_side": 2,
             "halo_bytes_per_neighbour_per_step": halo,
             "exchanges_per_step": 36, "allreduces_per_step": 3,

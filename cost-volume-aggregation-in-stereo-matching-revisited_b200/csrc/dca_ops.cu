@@ -882,6 +882,72 @@ convex_upsample_kernel(const float* __restrict__ mask, const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
+// softmax + disparity regression + convex 4x upsampling in ONE kernel (gwcnet_dca_g.py:238-239 + :117-124) for callers
+// that hold the classif3 LOGITS: a CTA owns a 32 x 8 tile of 1/4-res pixels, regresses the disparity of the tile and its
+// 1-pixel ring (recomputed by the neighbouring CTAs: 1.33x the 5.75 MB logits, instead of a grid-wide dependency)
+// into shared memory (zero outside the image = F.unfold(padding=1)), writes the tile's own 1/4-res disparities, then
+// upsamples from shared memory.  Same formulas as softmax_regress_kernel / convex_upsample_kernel: bit-identical.
+// ------------------------------------------------------------------------------------------------
+constexpr int RU_TW = 32, RU_TH = 8;
+__global__ void __launch_bounds__(RU_TW * RU_TH)
+softmax_regress_upsample_kernel(const float* __restrict__ logits, const float* __restrict__ mask, float* __restrict__ pred_q,
+                                float* __restrict__ out, int B, int D, int H, int W) {
+  __shared__ float s_d[RU_TH + 2][RU_TW + 2];
+  const int b = blockIdx.z, h0 = blockIdx.y * RU_TH, w0 = blockIdx.x * RU_TW;
+  const size_t HW = (size_t)H * W;
+  pdl_wait();
+  for (int i = threadIdx.x; i < (RU_TH + 2) * (RU_TW + 2); i += blockDim.x) {
+    const int ly = i / (RU_TW + 2), lx = i - ly * (RU_TW + 2);
+    const int h = h0 + ly - 1, w = w0 + lx - 1;
+    float v = 0.f;
+    if (h >= 0 && h < H && w >= 0 && w < W) {
+      const float* lp = logits + (size_t)b * D * HW + (size_t)h * W + w;
+      float m = -INFINITY;
+      for (int d = 0; d < D; ++d) m = fmaxf(m, lp[(size_t)d * HW]);
+      float sum = 0.f, acc = 0.f;
+      for (int d = 0; d < D; ++d) {
+        const float ev = expf(lp[(size_t)d * HW] - m);
+        sum += ev;
+        acc = fmaf(ev, (float)d, acc);
+      }
+      v = acc / sum;
+      if (ly >= 1 && ly <= RU_TH && lx >= 1 && lx <= RU_TW) pred_q[(size_t)b * HW + (size_t)h * W + w] = v;
+    }
+    s_d[ly][lx] = v;
+  }
+  __syncthreads();
+  for (int it = threadIdx.x; it < RU_TW * RU_TH * 4; it += blockDim.x) {
+    const int i = it & 3, px = it >> 2;
+    const int lx = px % RU_TW, ly = px / RU_TW;
+    const int h = h0 + ly, w = w0 + lx;
+    if (h >= H || w >= W) continue;
+    const float* mp = mask + (((size_t)b * H + h) * W + w) * 144 + i * 4;
+    float4 mv[9];
+    float dv[9];
+#pragma unroll
+    for (int n = 0; n < 9; ++n) {
+      mv[n] = *reinterpret_cast<const float4*>(mp + n * 16);
+      dv[n] = 4.f * s_d[ly + n / 3][lx + n % 3];
+    }
+    float4 mx = mv[0];
+#pragma unroll
+    for (int n = 1; n < 9; ++n) {
+      mx.x = fmaxf(mx.x, mv[n].x); mx.y = fmaxf(mx.y, mv[n].y); mx.z = fmaxf(mx.z, mv[n].z); mx.w = fmaxf(mx.w, mv[n].w);
+    }
+    float4 sm = make_float4(0, 0, 0, 0), a = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int n = 0; n < 9; ++n) {
+      const float ex = expf(mv[n].x - mx.x), ey = expf(mv[n].y - mx.y), ez = expf(mv[n].z - mx.z),
+                  ew = expf(mv[n].w - mx.w);
+      sm.x += ex; sm.y += ey; sm.z += ez; sm.w += ew;
+      a.x = fmaf(ex, dv[n], a.x); a.y = fmaf(ey, dv[n], a.y); a.z = fmaf(ez, dv[n], a.z); a.w = fmaf(ew, dv[n], a.w);
+    }
+    *reinterpret_cast<float4*>(out + ((size_t)b * 4 * H + 4 * h + i) * (4 * W) + 4 * w) =
+        make_float4(a.x / sm.x, a.y / sm.y, a.z / sm.z, a.w / sm.w);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // layout conversion between the reference's fp32 NCDHW tensors and cost planes
 // ------------------------------------------------------------------------------------------------
 template <int PLANES>
@@ -1183,6 +1249,17 @@ extern "C" int dca_softmax_regress(const float* logits, float* pred, int B, int 
   if (!logits || !pred || B <= 0 || D <= 0 || H <= 0 || W <= 0) return DCA_ERR_ARG;
   const int HW = H * W;
   softmax_regress_kernel<<<dim3((HW + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(logits, pred, D, HW);
+  DCA_RETURN_IF_LAUNCH_FAILED();
+  return DCA_OK;
+}
+
+// logits fp32 [B,D,H,W], mask fp32 channels-last [B,H,W,144] -> pred_q [B,1,H,W] (1/4-res disparity) and out [B,1,4H,4W],
+// one launch (softmax_regress_upsample_kernel).
+extern "C" int dca_softmax_regress_upsample(const float* logits, const float* mask, float* pred_q, float* out, int B, int D,
+                                            int H, int W, void* stream) {
+  if (!logits || !mask || !pred_q || !out || B <= 0 || D <= 0 || H <= 0 || W <= 0 || B > 65535) return DCA_ERR_ARG;
+  dca_launch(softmax_regress_upsample_kernel, dim3((W + RU_TW - 1) / RU_TW, (H + RU_TH - 1) / RU_TH, B), RU_TW * RU_TH, 0,
+             (cudaStream_t)stream, logits, mask, pred_q, out, B, D, H, W);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }

@@ -203,8 +203,9 @@ int dca_conv3d_igemm(int mode, const void* x, int planes_in, const void* w_tc, c
  * folded BN + act on it; y and pooled are [planes][B][(Di+1)/2][(Hi+1)/2][(Wi+1)/2][C]. */
 int dca_pool_conv(const void* x, void* pooled, const void* w_tc, const float* scale, const float* shift, void* y,
                   int planes, int act, int B, int C, int Di, int Hi, int Wi, void* stream);
-/* dca_softmax_regress_upsample: gwcnet_dca_g.py:238-239 + :120-124 = dca_softmax_regress into pred_q [B,1,H,W] (kept as
- * the 1/4-res result), then dca_convex_upsample to out [B,1,4H,4W]. */
+/* dca_softmax_regress_upsample: gwcnet_dca_g.py:238-239 + :117-124 in ONE kernel: softmax over D + disparity regression
+ * of a 32 x 8 pixel tile and its 1-pixel ring into shared memory, convex 4x upsampling from there.  pred_q [B,1,H,W] =
+ * the 1/4-res disparity, out [B,1,4H,4W].  Bit-identical to dca_softmax_regress + dca_convex_upsample. */
 int dca_softmax_regress_upsample(const float* logits, const float* mask, float* pred_q, float* out, int B, int D, int H,
                                  int W, void* stream);
 
