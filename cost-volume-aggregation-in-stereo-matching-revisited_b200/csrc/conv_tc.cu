@@ -1104,7 +1104,7 @@ struct Up2Params {
   Up2Tap taps[64];
 };
 
-template <int CIN, int PLANES, int NSLAB>
+template <int CIN, int PLANES, int NSLAB, int NSIDE = 2>
 struct Up2Cfg {
   static constexpr int COUT = 32;
   static constexpr int ROWB = CIN * 2;
@@ -1115,7 +1115,7 @@ struct Up2Cfg {
   static constexpr int SIDE_SLOT = PLANES * A_BYTES;
   static constexpr int B_ROWS = PLANES * COUT;
   static constexpr int B_BYTES = B_ROWS * ROWB;
-  static constexpr int SIDE_SLOTS = 2;
+  static constexpr int SIDE_SLOTS = NSIDE;     // pair-row boxes in flight (a DRAM stream: the deeper, the more bytes in flight)
   static constexpr int OTHER = SIDE_SLOTS * SIDE_SLOT + 1024 + 512 + 2 * COUT * 4;
   static constexpr int NBUF = (2 * SLAB_SET + OTHER + 6 * B_BYTES <= 225 * 1024) ? 2 : 1;
   // weight ring: whatever is left, 6..12 taps deep (the streamed 64->32 parity taps are 8 KB each and one tap is only
@@ -1127,10 +1127,10 @@ struct Up2Cfg {
   static constexpr int SMEM_BYTES = NBUF * SLAB_SET + FIXED;
 };
 
-template <int CIN, int PLANES, int NSLAB>
+template <int CIN, int PLANES, int NSLAB, int NSIDE = 2>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_up2_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const Up2Params u) {
-  using Cfg = Up2Cfg<CIN, PLANES, NSLAB>;
+  using Cfg = Up2Cfg<CIN, PLANES, NSLAB, NSIDE>;
   constexpr int COUT = Cfg::COUT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1925,9 +1925,9 @@ __global__ void pack_weight_tc2d_kernel(const float* __restrict__ w, int Co, int
   }
 }
 
-template <int CIN, int PLANES, int NSLAB>
+template <int CIN, int PLANES, int NSLAB, int NSIDE = 2>
 static int launch_up2(const TcMaps& maps, const TcParams& p, const Up2Params& u, cudaStream_t st) {
-  using Cfg = Up2Cfg<CIN, PLANES, NSLAB>;
+  using Cfg = Up2Cfg<CIN, PLANES, NSLAB, NSIDE>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "smem plan");
   if (!g_num_sms) {
     int dev = 0;
@@ -1935,13 +1935,13 @@ static int launch_up2(const TcMaps& maps, const TcParams& p, const Up2Params& u,
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
   }
-  cudaFuncSetAttribute(conv_tc_up2_kernel<CIN, PLANES, NSLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_up2_kernel<CIN, PLANES, NSLAB, NSIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   const int total = p.B * p.Dt * p.tiles_h * p.tiles_w;
   const int grid = total < g_num_sms ? total : g_num_sms;
   TcParams q = p; fill_recips(q);
   for (int c = 0; c < 8; ++c)
     fill_comp(q, c, (c < q.ncls ? (int)u.cls_tap0[c + 1] - (int)u.cls_tap0[c] : 0) * (CIN / 16) + (u.has_side ? 2 : 0));
-  dca_launch(conv_tc_up2_kernel<CIN, PLANES, NSLAB>, grid, TC_THREADS, Cfg::SMEM_BYTES, st, maps, q, u);
+  dca_launch(conv_tc_up2_kernel<CIN, PLANES, NSLAB, NSIDE>, grid, TC_THREADS, Cfg::SMEM_BYTES, st, maps, q, u);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }
@@ -2063,6 +2063,7 @@ static int launch_deconv_pair(const TcMaps& maps, const TcParams& p, const Up2Pa
 
 static int g_use_deconv_pair = 1;
 static int g_use_pool_march = 1;
+static int g_up2_side_slots = 2;   // (4 was measured: 91.2 us either way -- the stream is not ring-depth bound)
 static int g_pool_ctas_per_sm = 4;   // measured at KITTI: 2: 50 us, 4: 44 us, 8: 47 us (thread-per-output kernel: 66 us)
 
 }  // namespace dca
@@ -2071,6 +2072,8 @@ using namespace dca;
 
 // 1 (default): transposed conv 64 -> 32 with a side input runs the two-tiles-per-weight-fetch kernel; 0: the up2 kernel
 extern "C" int dca_tc_set_deconv_pair(int on) { g_use_deconv_pair = on ? 1 : 0; return DCA_OK; }
+// side-box ring depth of dca_up2_tc kind 2 (2 or 4; timing experiments)
+extern "C" int dca_tc_set_up2_side_slots(int n) { g_up2_side_slots = (n == 4) ? 4 : 2; return DCA_OK; }
 
 // kind 0: y = act(scale * (conv_transpose3d_k3s2(x) + side 1x1x1) + shift) + res_post
 //         x [P][B][Dl][Hl][Wl][Cin], w_tc = 27 taps (+ tap 27 = side weights, Cin-padded) of [planes][32][Cin]
@@ -2201,7 +2204,10 @@ extern "C" int dca_up2_tc(int kind, const void* x, int planes, const void* side,
     return P == 2 ? launch_deconv_pair<2>(maps, p, u, st) : launch_deconv_pair<1>(maps, p, u, st);
   }
   if (kind == 1) return P == 2 ? launch_up2<32, 2, 3>(maps, p, u, st) : launch_up2<32, 1, 3>(maps, p, u, st);
-  if (kind == 2) return P == 2 ? launch_up2<32, 2, 2>(maps, p, u, st) : launch_up2<32, 1, 2>(maps, p, u, st);
+  if (kind == 2) {      // one slab per tile: the smem goes into a deeper ring of side boxes (the `cost` stream from DRAM)
+    if (g_up2_side_slots == 4) return P == 2 ? launch_up2<32, 2, 1, 4>(maps, p, u, st) : launch_up2<32, 1, 1, 4>(maps, p, u, st);
+    return P == 2 ? launch_up2<32, 2, 2>(maps, p, u, st) : launch_up2<32, 1, 2>(maps, p, u, st);
+  }
   if (Cin == 64) return P == 2 ? launch_up2<64, 2, 2>(maps, p, u, st) : launch_up2<64, 1, 2>(maps, p, u, st);
   return P == 2 ? launch_up2<32, 2, 2>(maps, p, u, st) : launch_up2<32, 1, 2>(maps, p, u, st);
 }
