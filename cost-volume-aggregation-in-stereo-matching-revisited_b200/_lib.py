@@ -68,6 +68,7 @@ SIGNATURES = {
     "dca_halo_push_ctas": [],
     "dca_halo_set_timeout_ms": [_c_int],
     "dca_halo_push": [_vp, _ll, _ll, _ll, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
+    "dca_halo_exchange": [_vp, _ll, _ll, _ll, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_ulonglong, _vp, _vp],
     "dca_halo_wait_unpack": [_vp, _ll, _ll, _ll, _c_int, _c_int, _vp, _vp, _vp, _vp, ctypes.c_ulonglong, _vp, _vp],
     "dca_fold_bn": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _c_int, _c_int, _vp],
 }

@@ -85,6 +85,40 @@ halo_wait_unpack_kernel(const HaloMsg top, const HaloMsg bottom, const unsigned 
   halo_copy(m);                        // src is the local staging slot the neighbour stored into
 }
 
+// Both halves in ONE launch: CTA (x, y) pushes its share of the rows for direction y into the neighbour's staging slot,
+// releases them, then acquires the own arrival counter of direction y and unpacks its share of the staged rows.  No CTA
+// waits for another CTA of its own grid (only for the neighbours' grids, which run on other GPUs), and every push
+// precedes the wait of the same CTA, so two neighbouring ranks cannot block each other.
+__global__ void __launch_bounds__(HALO_THREADS)
+halo_exchange_kernel(const HaloMsg push_up, const HaloMsg push_down, unsigned long long* pflag_up,
+                     unsigned long long* pflag_down, const HaloMsg top, const HaloMsg bottom,
+                     const unsigned long long* flag_top, const unsigned long long* flag_bottom, unsigned long long target,
+                     int* err, unsigned long long timeout_ns) {
+  pdl_wait();                          // the rows come from the previous kernel of the stream
+  {
+    const HaloMsg& m = blockIdx.y ? push_down : push_up;
+    unsigned long long* flag = blockIdx.y ? pflag_down : pflag_up;
+    if (m.src != nullptr) {
+      halo_copy(m);
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) atomicAdd_system(flag, 1ULL);
+    }
+  }
+  const HaloMsg& m = blockIdx.y ? bottom : top;
+  const unsigned long long* flag = blockIdx.y ? flag_bottom : flag_top;
+  if (m.src == nullptr) return;
+  if (threadIdx.x == 0) {
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(flag) < target) {
+      __nanosleep(100);
+      if (global_ns() - t0 > timeout_ns) { atomicExch(err, 1); break; }
+    }
+  }
+  __syncthreads();
+  halo_copy(m);
+}
+
 }  // namespace dca
 
 using namespace dca;
@@ -146,6 +180,38 @@ extern "C" int dca_halo_wait_unpack(void* t, long long outer, long long rows, lo
   halo_wait_unpack_kernel<<<dim3(PUSH_CTAS, 2), HALO_THREADS, 0, (cudaStream_t)stream>>>(
       top, bottom, (const unsigned long long*)flag_top, (const unsigned long long*)flag_bottom, target, (int*)err,
       g_halo_timeout_ns);
+  DCA_RETURN_IF_LAUNCH_FAILED();
+  return DCA_OK;
+}
+
+// dca_halo_push + dca_halo_wait_unpack as ONE launch (same arguments, same semantics): the default of hshard.PeerHalo.
+extern "C" int dca_halo_exchange(void* t, long long outer, long long rows, long long inner_bytes, int h, int live,
+                                 void* peer_up_stage, void* peer_down_stage, void* peer_up_flag, void* peer_down_flag,
+                                 const void* stage_top, const void* stage_bottom, const void* flag_top,
+                                 const void* flag_bottom, unsigned long long target, void* err, void* stream) {
+  if (!t || !err || outer <= 0 || h <= 0 || live <= 0 || live > h || rows < 2LL * h + live || inner_bytes <= 0)
+    return DCA_ERR_ARG;
+  const long long chunk = (long long)live * inner_bytes;
+  if ((chunk & 15) || ((rows * inner_bytes) & 15) || (inner_bytes & 15) || ((uintptr_t)t & 15) ||
+      ((uintptr_t)peer_up_stage & 15) || ((uintptr_t)peer_down_stage & 15) || ((uintptr_t)stage_top & 15) ||
+      ((uintptr_t)stage_bottom & 15))
+    return DCA_ERR_UNSUPPORTED;
+  if ((peer_up_stage && !peer_up_flag) || (peer_down_stage && !peer_down_flag) || (stage_top && !flag_top) ||
+      (stage_bottom && !flag_bottom))
+    return DCA_ERR_ARG;
+  if (!peer_up_stage && !peer_down_stage && !stage_top && !stage_bottom) return DCA_OK;
+  char* base = (char*)t;
+  HaloMsg up{peer_up_stage ? base + (long long)h * inner_bytes : nullptr, (char*)peer_up_stage, outer, rows * inner_bytes,
+             chunk, chunk};
+  HaloMsg down{peer_down_stage ? base + (rows - h - (long long)live) * inner_bytes : nullptr, (char*)peer_down_stage, outer,
+               rows * inner_bytes, chunk, chunk};
+  HaloMsg top{(const char*)stage_top, base + (long long)(h - live) * inner_bytes, outer, chunk, rows * inner_bytes, chunk};
+  HaloMsg bottom{(const char*)stage_bottom, base + (rows - (long long)h) * inner_bytes, outer, chunk, rows * inner_bytes,
+                 chunk};
+  dca_launch(halo_exchange_kernel, dim3(PUSH_CTAS, 2), HALO_THREADS, 0, (cudaStream_t)stream, up, down,
+             (unsigned long long*)peer_up_flag, (unsigned long long*)peer_down_flag, top, bottom,
+             (const unsigned long long*)flag_top, (const unsigned long long*)flag_bottom, target, (int*)err,
+             g_halo_timeout_ns);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }

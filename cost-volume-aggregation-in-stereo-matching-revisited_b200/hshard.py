@@ -34,6 +34,7 @@ import torch
 from . import _lib
 from . import engine as E
 
+FUSED_EXCHANGE = os.environ.get("DCA_HALO_FUSED", "1") != "0"   # one launch per exchange instead of push + wait/unpack
 H4_HALO = 2      # halo rows at 1/4 resolution (even: keeps the stride-2 alignment)
 H8_HALO = 1      # halo rows at 1/8 resolution
 H4_LIVE = 1      # 1/4-res halo rows that are ever read for an owned output (the outer one only keeps the alignment)
@@ -212,13 +213,16 @@ class PeerHalo:
         up, down = r - 1, r + 1
         has_up, has_down = up >= 0, down < self.world
         st = E._stream()
-        _lib.call("dca_halo_push", t.data_ptr(), outer, rows, inner, req.h, req.nlive,
-                  self._slot(up, par, 1) if has_up else 0, self._slot(down, par, 0) if has_down else 0,
-                  self._flag(up, 1) if has_up else 0, self._flag(down, 0) if has_down else 0, st)
-        _lib.call("dca_halo_wait_unpack", t.data_ptr(), outer, rows, inner, req.h, req.nlive,
-                  self._slot(r, par, 0) if has_up else 0, self._slot(r, par, 1) if has_down else 0,
-                  self._flag(r, 0) if has_up else 0, self._flag(r, 1) if has_down else 0,
-                  self.epoch * self.ctas, self.ptrs[r] + 4 * self.slot + 16, st)
+        push = (self._slot(up, par, 1) if has_up else 0, self._slot(down, par, 0) if has_down else 0,
+                self._flag(up, 1) if has_up else 0, self._flag(down, 0) if has_down else 0)
+        wait = (self._slot(r, par, 0) if has_up else 0, self._slot(r, par, 1) if has_down else 0,
+                self._flag(r, 0) if has_up else 0, self._flag(r, 1) if has_down else 0,
+                self.epoch * self.ctas, self.ptrs[r] + 4 * self.slot + 16)
+        if FUSED_EXCHANGE:       # push + wait/unpack in one launch (halo_exchange_kernel)
+            _lib.call("dca_halo_exchange", t.data_ptr(), outer, rows, inner, req.h, req.nlive, *push, *wait, st)
+        else:
+            _lib.call("dca_halo_push", t.data_ptr(), outer, rows, inner, req.h, req.nlive, *push, st)
+            _lib.call("dca_halo_wait_unpack", t.data_ptr(), outer, rows, inner, req.h, req.nlive, *wait, st)
 
     def _err_word(self):
         return self.buf[4 * self.slot + 16:4 * self.slot + 20].view(torch.int32)

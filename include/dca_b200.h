@@ -144,6 +144,8 @@ int dca_pdl_enabled(void);
 /* dca_up2_tc kind 0 with Cin = 64 and a side input: 1 (default) = two depth-adjacent tiles per weight fetch
  * (conv_tc_deconv_pair_kernel), 0 = one tile per fetch (conv_tc_up2_kernel); same results. */
 int dca_tc_set_deconv_pair(int on);
+/* dca_up2_tc kind 2: depth of the side-box ring, 2 (default) or 4 (timing experiments; measured: no difference). */
+int dca_tc_set_up2_side_slots(int n);
 
 /* (2) DCA module ------------------------------------------------------------------------------- */
 /* AvgPool3d(3, 2, 1) (cva.py:39).  C == 32: TMA-staged depth-marching kernel (each input plane read once); other C, or
@@ -191,6 +193,12 @@ int dca_halo_wait_unpack(void* t, long long outer, long long rows, long long inn
                          const void* stage_top,
                          const void* stage_bottom, const void* flag_top, const void* flag_bottom,
                          unsigned long long target, void* err, void* stream);
+
+/* the two calls above as ONE launch (same arguments and semantics): what hshard.PeerHalo issues per exchange */
+int dca_halo_exchange(void* t, long long outer, long long rows, long long inner_bytes, int h, int live,
+                      void* peer_up_stage, void* peer_down_stage, void* peer_up_flag, void* peer_down_flag,
+                      const void* stage_top, const void* stage_bottom, const void* flag_top, const void* flag_bottom,
+                      unsigned long long target, void* err, void* stream);
 
 /* (6) compositions under the family names of SURVEY.md section 8(b) -------------------------------- */
 /* dca_conv3d_igemm: the implicit-GEMM family (convbn_3d / Conv3d s2 / ConvTranspose3d / 1x1x1, submodule.py:121-124,

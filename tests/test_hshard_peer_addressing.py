@@ -29,6 +29,9 @@ class _Emu:
                 c.value += CTAS
         elif name == "dca_halo_wait_unpack":
             self.waits.append(a)
+        elif name == "dca_halo_exchange":                 # one launch: its push half now, its wait half with the others
+            self.call("dca_halo_push", *a[:10], a[-1])
+            self.waits.append(a[:6] + a[10:])
         else:
             raise AssertionError(name)
 
@@ -55,10 +58,12 @@ def _peers(world, slot):
     return peers, bufs
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("live", [0, 1])
-def test_peer_halo_slots_counters_and_parity(monkeypatch, live):
+def test_peer_halo_slots_counters_and_parity(monkeypatch, live, fused):
     world, h = 3, 2
     emu = _Emu()
+    monkeypatch.setattr(hs, "FUSED_EXCHANGE", fused)
     monkeypatch.setattr(hs._lib, "call", emu.call)
     monkeypatch.setattr(hs.E, "_stream", lambda: 0)
     peers, bufs = _peers(world, 4096)
