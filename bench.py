@@ -288,6 +288,7 @@ def main():
                          "as consecutive single-pair forwards); 0 (default) = one pair per GPU per step")
     ap.add_argument("--latency-steps", type=int, default=200,
                     help="extra latency loop after the K timed steps (p50/p90 in the `latency` key; 0 = skip)")
+    ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph latency record (`graph` key)")
     ap.add_argument("--no-hshard-record", action="store_true",
                     help="N > 1: skip the H-sharded Middlebury sub-record (configs[4]) appended to the line")
     ap.add_argument("--hshard-transport", default="p2p", choices=["nccl", "p2p"],
@@ -435,6 +436,35 @@ def main():
             lat = {"steps": n_lat, "warmup": 20, "p50_ms_per_pair": ls[n_lat // 2], "p90_ms_per_pair": ls[int(0.9 * n_lat)],
                    "p99_ms_per_pair": ls[min(n_lat - 1, int(0.99 * n_lat))], "mean_ms_per_pair": sum(ls) / n_lat,
                    "pairs_per_s": n_lat * B / (evl[0].elapsed_time(evl[n_lat]) * 1e-3)}
+        # ---------------- the same forward as ONE CUDA graph (engine.GraphedHotPath), extra key only ----------
+        graph_rec = None
+        if n_lat and not args.no_graph:
+            def p50_of(fn, n, warm, sync=barrier):
+                evg = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+                for i in range(warm):
+                    fn(i)
+                sync()
+                evg[0].record()
+                for i in range(n):
+                    fn(i)
+                    evg[i + 1].record()
+                sync()
+                ts = sorted(evg[i].elapsed_time(evg[i + 1]) for i in range(n))
+                return ts[n // 2], ts[int(0.9 * n)], n / (evg[0].elapsed_time(evg[n]) * 1e-3)
+
+            p50, p90, pps = p50_of(lambda i: net.hot_path_graphed(*dev_sets[i % nsets]), n_lat, 20)
+            graph_rec = {"what": "hot_path_graphed: the whole forward as one cudaGraphLaunch per pair (one graph per input "
+                                 "set, shared pool); results copied out of the graph's buffers",
+                         "steps": n_lat, "p50_ms_per_pair": p50 / B, "p90_ms_per_pair": p90 / B, "pairs_per_s": pps * B}
+            if rank == 0:
+                # the launch-bound regime: tiny_64x128 (maxdisp 48), eager launches vs graph replay
+                tH, tW, tD, tB = workloads.CONFIGS["tiny_64x128"]
+                tnet = workloads.init_bench_weights_(d.GwcNet(tD, precision=args.precision), 0).to(dev).eval()
+                tf = [t.to(dev) for t in workloads.feature_maps(7, tB, tH // 4, tW // 4)]
+                e50, e90, _ = p50_of(lambda i: tnet.hot_path(*tf), 100, 10, torch.cuda.synchronize)
+                g50, g90, _ = p50_of(lambda i: tnet.hot_path_graphed(*tf), 100, 10, torch.cuda.synchronize)
+                graph_rec["tiny_64x128"] = {"eager_p50_ms": e50, "eager_p90_ms": e90, "graph_p50_ms": g50, "graph_p90_ms": g90}
+                del tnet, tf
         gc.enable()
 
         # ---------------- roofline of the dominant kernel: conv3d k3 s1 32->32 at 1/4 res ----------------
@@ -545,6 +575,8 @@ def main():
         line.update(extra)
         if lat is not None:
             line["latency"] = lat
+        if graph_rec is not None:
+            line["graph"] = graph_rec
         if hrec is not None:
             line["hshard"] = hrec
         line["host"] = {"numa_node_bound": numa, "cpus": len(os.sched_getaffinity(0)) if affinity0 is not None else None}

@@ -24,6 +24,19 @@ def run(tag):
 
 E = d.engine
 run("default")
+run("default again")
+with torch.no_grad():
+    a = net.hot_path(*gf)[0]; b = net.hot_path(*gf)[0]
+print("bit-reproducible:", bool(torch.equal(a, b)), "max diff", float((a - b).abs().max()), flush=True)
+d._lib.call("dca_set_pdl", 0); run("no PDL")
+with torch.no_grad():
+    a = net.hot_path(*gf)[0]; b = net.hot_path(*gf)[0]
+print("no PDL bit-reproducible:", bool(torch.equal(a, b)), flush=True)
+d._lib.call("dca_set_pdl", 1)
+d._lib.call("dca_tc_set_deconv_pair", 0); run("deconv single-tile"); d._lib.call("dca_tc_set_deconv_pair", 1)
+d._lib.call("dca_pool_set_march", 0); run("avgpool simple"); d._lib.call("dca_pool_set_march", 1)
+E.Options.fuse_tail = False; run("no fused 32->1 tail"); E.Options.fuse_tail = True
+E.Options.prop_side_stream = False; run("no side stream"); E.Options.prop_side_stream = True
 d._lib.call("dca_volume_set_v2", 0); run("volume generic"); d._lib.call("dca_volume_set_v2", 1)
 d._lib.call("dca_attention_set_team", 0); run("attention 1 warp"); d._lib.call("dca_attention_set_team", 1)
 d._lib.call("dca_tc_set_halo", 3); run("s2 per-tap"); d._lib.call("dca_tc_set_halo", 1)

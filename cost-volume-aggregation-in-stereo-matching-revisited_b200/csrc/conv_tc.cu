@@ -2001,7 +2001,7 @@ avgpool3d_march_kernel(const __grid_constant__ CUtensorMap xmap, __nv_bfloat16* 
   for (int k = 0; k < 4; ++k) acc[k] = make_float2(0.f, 0.f);
   for (int i = 0; i < nplanes; ++i) {
     mbar_wait(&full[i & 1], (uint32_t)((i >> 1) & 1));
-    const uint8_t* src = smem + (size_t)(i & 1) * PLANES * AP_PITCH;
+    const uint32_t src = smem_u32(smem) + (uint32_t)(i & 1) * PLANES * AP_PITCH;
     float2 rs[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) rs[k] = make_float2(0.f, 0.f);
@@ -2012,14 +2012,24 @@ avgpool3d_march_kernel(const __grid_constant__ CUtensorMap xmap, __nv_bfloat16* 
         const int off = ((2 * oh + dy) * AP_BW + (2 * ow + dx)) * 64 + c8 * 16;
 #pragma unroll
         for (int pl = 0; pl < PLANES; ++pl) {
-          const uint4 v = *reinterpret_cast<const uint4*>(src + pl * AP_PITCH + off);
+          uint4 v;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src + pl * AP_PITCH + off));
           float f[8];
           unpack8(v, f);
 #pragma unroll
           for (int k = 0; k < 4; ++k) rs[k] = __fadd2_rn(rs[k], make_float2(f[2 * k], f[2 * k + 1]));
         }
       }
-    __syncthreads();                                // every thread has read this slot
+    // WAR on the slot across proxies: the refill below is an ASYNC-proxy write, which is not ordered behind shared loads
+    // that were issued but have not returned yet, and ptxas sinks the last (register-only) adds below a plain BAR.SYNC.
+    // About one launch in 200 at KITTI size then had one voxel summed from a half-refilled slot -- always the last lanes
+    // of a warp, whose loads are served last.  The barrier therefore takes a predicate computed from every plane sum:
+    // "arrived at the barrier" now means "all my loads of this slot have returned".
+    float chk = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) chk += rs[k].x + rs[k].y;
+    (void)__syncthreads_or(chk != chk);             // every thread has read this slot
     if (tid == 0 && i + 2 < nplanes) issue(i + 2);
 #pragma unroll
     for (int k = 0; k < 4; ++k) acc[k] = __fadd2_rn(acc[k], rs[k]);

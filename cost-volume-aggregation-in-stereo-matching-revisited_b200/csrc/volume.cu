@@ -257,7 +257,7 @@ volume_fused3_kernel(const __grid_constant__ VolMaps maps, __nv_bfloat16* __rest
                      int dbg) {
   using Cfg = Vol3Cfg<G, CPG, CC>;
   constexpr int HG = Cfg::HG, LW4 = Cfg::LW4, UW4 = Cfg::UW4, LW8 = Cfg::LW8, UW8 = Cfg::UW8;
-  static_assert(G % 8 == 0, "swap bit must be a per-lane constant");
+  static_assert(G % 4 == 0, "a 128-byte smem row holds 4 slots: the swap bit is ((slot >> 2) + octet * G / 4) & 1");
   extern __shared__ __align__(1024) uint8_t smem_v3[];
   uint8_t* base = smem_v3;                 // (kept a shared-space pointer: no generic loads in the inner loop)
   if (threadIdx.x == 0 && (v_smem_u32(base) & 255u) != 0) __trap();            // SWIZZLE_32B pattern repeats every 256 bytes
@@ -336,11 +336,15 @@ volume_fused3_kernel(const __grid_constant__ VolMaps maps, __nv_bfloat16* __rest
         uint32_t lo_[2], ro_[2][3];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
+          // SWIZZLE_32B swaps the two float4 of a unit in odd 128-byte rows; row = unit / 4 = (octet * G + slot) / 4, so
+          // with G % 8 == 0 the bit is a per-lane constant and with G % 8 == 4 (20 groups) it flips with the octet
           const int slot = lane + q * HG, sw = (slot >> 2) & 1;
-          lo_[q] = (uint32_t)((((wq >> 1) * G + slot) << 5) + (((wq & 1) ^ sw) << 4));
+          constexpr int OSW = (G >> 2) & 1;
+          lo_[q] = (uint32_t)((((wq >> 1) * G + slot) << 5) + (((wq & 1) ^ sw ^ (OSW & (wq >> 1))) << 4));
 #pragma unroll
           for (int kk = 0; kk < 3; ++kk)
-            ro_[q][kk] = (uint32_t)(((((ub4 + kk) >> 1) * G + slot) << 5) + ((((ub4 + kk) & 1) ^ sw) << 4));
+            ro_[q][kk] = (uint32_t)(((((ub4 + kk) >> 1) * G + slot) << 5) +
+                                    ((((ub4 + kk) & 1) ^ sw ^ (OSW & ((ub4 + kk) >> 1))) << 4));
         }
 #pragma unroll
         for (int c = 0; c < CPG; ++c) {
@@ -570,6 +574,8 @@ extern "C" int dca_volume_gwc_concat(const float* gwc_l, const float* gwc_r, con
   const int cpg = C / G, gp = G + 1, UW = VOL_TW + VOL_DC - 1;
   if ((W % 8) == 0 && Cc == 12 && C == 320 && (g_volume_v2 & 1)) {      // DCANet's shape and the 20-group point of config 4's sweep (8 groups x 40 channels does not fit two buffers)
     if (G == 40 && Cv == 64) return launch_volume3<40, 8, 12, 64>(gwc_l, gwc_r, cat_l, cat_r, vol, B, D, H, W, planes, (cudaStream_t)stream);
+    if (G == 20 && Cv == 64) return launch_volume3<20, 16, 12, 64>(gwc_l, gwc_r, cat_l, cat_r, vol, B, D, H, W, planes, (cudaStream_t)stream);
+    if (G == 20 && Cv == 48) return launch_volume3<20, 16, 12, 48>(gwc_l, gwc_r, cat_l, cat_r, vol, B, D, H, W, planes, (cudaStream_t)stream);
   }
   size_t smem = ((size_t)cpg * (VOL_TW + UW) * gp + (size_t)Cc * (VOL_TW + UW)) * sizeof(float);
   if (smem > 220 * 1024) return DCA_ERR_UNSUPPORTED;

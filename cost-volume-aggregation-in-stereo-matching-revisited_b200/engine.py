@@ -608,7 +608,7 @@ def cva_forward(pk: PackedCva, cost: Planes, res_post: Planes = None, keep=None)
         fused = upsample_fuse(t, cost, pk.fuse_wcT, pk.fuse_scale, pk.fuse_shift)
     out = agg_forward(pk.agg, fused, res_post=res_post)
     if keep is not None:
-        keep.update(cost_down=cost_down, logits=logits, class_map=cls, e=e, S=S, t=t, fused=fused, out=out)
+        keep.update(pooled=pooled, cost_down=cost_down, logits=logits, class_map=cls, e=e, S=S, t=t, fused=fused, out=out)
     return logits, out
 
 
@@ -660,7 +660,8 @@ def _prop_mask_start(pk, g, P):
     if side is None:
         side = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=g.device)
     side.wait_stream(main)                 # g is ready, and the previous forward no longer reads the buffers below
-    g.record_stream(side)
+    if not torch.cuda.is_current_stream_capturing():
+        g.record_stream(side)
     # persistent buffers per shape: no caching-allocator traffic on the side stream (cross-stream frees made single
     # steps stall for 8-100 ms in 2 of 10 bench runs)
     B, Cg, H, W = g.shape
@@ -759,3 +760,62 @@ def _hot_path_stages(pk, vol, side_job, tc0, keep):
         keep.update(volume=vol, dres0=c, cost0=cost0, out1=out1, classif3_logits=logits, pred_quarter=pred_q, mask=mask)
         keep.update({f"cva{i + 1}": k for i, k in enumerate(kept)})
     return pred4, (logits if not pk.cva else logits2)     # no cva stage (gwcnet_dca0_g.py:190): the head's own logits
+
+
+# --------------------------------------------------------------------------------------------
+# the forward as ONE CUDA graph
+# --------------------------------------------------------------------------------------------
+class GraphedHotPath:
+    """`hot_path_forward` captured once per (input buffers, shapes) into a CUDA graph and replayed: the ~46 launches of
+    a forward (programmatic-dependent-launch edges included) become one `cudaGraphLaunch`, so the host cost per pair
+    drops from ~0.9 ms of ctypes calls to ~10 us and the launch-bound small shapes stop being launch bound.
+
+    The graph reads the caller's input tensors IN PLACE (their addresses are baked in): calling again with the same
+    tensors (new contents) replays; other tensors capture another graph (a small LRU of them, all sharing one memory
+    pool -- their replays are ordered on the calling stream, so they may reuse each other's activations).  Results are
+    returned as copies, so they survive the next replay.  Weights are baked in as well: `GwcNet` drops its graphs
+    whenever it drops its packed parameters."""
+    MAX_GRAPHS = 8
+
+    def __init__(self, pk: "PackedHotPath"):
+        self.pk = pk
+        self.graphs = {}          # key -> (graph, static outputs, input tensors kept alive)
+        self.pool = None
+        self.replays = 0
+
+    @staticmethod
+    def _key(tensors):
+        return tuple((0, ()) if t is None else (t.data_ptr(), tuple(t.shape)) for t in tensors)
+
+    def _capture(self, ins):
+        s = torch.cuda.Stream(device=ins[0].device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):                 # warm-up outside the capture: lazy module loads, persistent side buffers
+            for _ in range(2):
+                hot_path_forward(self.pk, *ins)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize(ins[0].device)
+        g = torch.cuda.CUDAGraph()
+        if self.pool is None:
+            self.pool = torch.cuda.graph_pool_handle()
+        with torch.cuda.graph(g, pool=self.pool):
+            out = hot_path_forward(self.pk, *ins)
+        return g, out
+
+    def __call__(self, gwc_l, gwc_r, cat_l, cat_r, g):
+        ins = (gwc_l, gwc_r, cat_l, cat_r, g)
+        _require_cuda(*ins)
+        for t in ins:
+            if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+                raise _lib.DcaError("the graphed forward reads its inputs in place: contiguous fp32 tensors only")
+        key = self._key(ins)
+        hit = self.graphs.pop(key, None)
+        if hit is None:
+            if len(self.graphs) >= self.MAX_GRAPHS:
+                self.graphs.pop(next(iter(self.graphs)))
+            graph, out = self._capture(ins)
+            hit = (graph, out, ins)
+        self.graphs[key] = hit                     # most recently used last
+        hit[0].replay()
+        self.replays += 1
+        return tuple(o.clone() for o in hit[1])

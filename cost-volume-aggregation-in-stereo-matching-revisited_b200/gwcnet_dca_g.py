@@ -130,6 +130,7 @@ class GwcNet(nn.Module):
                 nn.Conv3d(32, 1, kernel_size=3, padding=1, stride=1, bias=False)))
         self.guidance = Guidance(64)
         self.prop = PropgationNet_4x(64)
+        self._graphed = None
         self.set_precision(precision)
         self._packed = None
 
@@ -172,6 +173,14 @@ class GwcNet(nn.Module):
     def hot_path(self, gwc_l, gwc_r, cat_l, cat_r, g, keep=None):
         """feature maps -> (pred4 [B,1,H,W], prob_volume2 [B,D8,H8,W8]); the graded path."""
         return engine.hot_path_forward(self.packed(), gwc_l, gwc_r, cat_l, cat_r, g, keep)
+
+    def hot_path_graphed(self, gwc_l, gwc_r, cat_l, cat_r, g):
+        """`hot_path` as one CUDA graph per set of input buffers (captured on first use, replayed afterwards; the inputs
+        are read in place, results are returned as copies).  Same kernels, same results, one launch."""
+        pk = self.packed()
+        if self._graphed is None or self._graphed.pk is not pk:
+            self._graphed = engine.GraphedHotPath(pk)
+        return self._graphed(gwc_l, gwc_r, cat_l, cat_r, g)
 
     def hot_path_hsharded(self, gwc_l, gwc_r, cat_l, cat_r, g, rank, world, group=None, transport="nccl"):
         """One rank of the H-sharded single-pair mode (BASELINE configs[4]): this rank's OWNED 1/4-res rows of the

@@ -56,8 +56,11 @@ def bind_host_to_gpu_numa(device_index):
 
 
 class HotPathPipeline:
-    def __init__(self, net, depth=2):
+    def __init__(self, net, depth=2, graph=False):
+        """graph=True: each slot's forward is one CUDA graph (the slot's device input buffers are fixed, so `depth`
+        graphs are captured on first use and replayed afterwards: one launch per pair instead of ~46)."""
         self.net = net
+        self.graph = graph
         self.depth = depth
         self.dev = next(net.parameters()).device
         self.copy_stream = torch.cuda.Stream(device=self.dev)
@@ -88,7 +91,7 @@ class HotPathPipeline:
         with torch.cuda.stream(self.compute_stream):
             self.compute_stream.wait_event(self.h2d_done[slot])
             with torch.no_grad():
-                pred4, pv = self.net.hot_path(*self.slots[slot])
+                pred4, pv = (self.net.hot_path_graphed if self.graph else self.net.hot_path)(*self.slots[slot])
             self.slot_free[slot].record(self.compute_stream)
             if self.out_host[slot] is None:
                 self.out_host[slot] = (torch.empty(pred4.shape, dtype=torch.float32).pin_memory(),

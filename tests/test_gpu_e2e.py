@@ -155,3 +155,31 @@ def test_module_forward_from_images_runs():
         pred4, pv2 = net(left, torch.roll(left, -4, 3))
     assert pred4.shape == (1, 1, 64, 128) and pv2.shape == (1, 6, 8, 16)
     assert torch.isfinite(pred4).all()
+
+
+def test_graphed_forward_is_bit_identical_to_the_launch_sequence():
+    """hot_path_graphed (the forward as one CUDA graph) = hot_path, bit for bit; replays see NEW contents of the same input
+    buffers, other buffers get their own graph, and a re-pack (weights changed) drops the graphs."""
+    import dcanet_b200 as d
+    import workloads
+    net = workloads.init_bench_weights_(d.GwcNet(96), 0).cuda().eval()
+    fa = [t.cuda() for t in workloads.feature_maps(1, 1, 32, 64)]
+    fb = [t.cuda() for t in workloads.feature_maps(2, 1, 32, 64)]
+    with torch.no_grad():
+        ea, eb = net.hot_path(*fa), net.hot_path(*fb)
+        ga = net.hot_path_graphed(*fa)
+        gb = net.hot_path_graphed(*fb)                      # second set of buffers: second graph, same pool
+        assert all(torch.equal(x, y) for x, y in zip(ea, ga)) and all(torch.equal(x, y) for x, y in zip(eb, gb))
+        assert all(torch.equal(x, y) for x, y in zip(ea, ga)), "results must survive the next replay (copies)"
+        for t, u in zip(fa, fb):                            # same buffers, new contents -> replay of graph A
+            t.copy_(u)
+        ga2 = net.hot_path_graphed(*fa)
+        assert net._graphed.replays == 3 and len(net._graphed.graphs) == 2
+        assert all(torch.equal(x, y) for x, y in zip(eb, ga2))
+        pipe = d.HotPathPipeline(net, depth=2, graph=True)  # streaming API on graphs
+        hs = [[t.cpu().pin_memory() for t in fb] for _ in range(3)]
+        out = pipe.run(hs)
+        assert torch.equal(out[0], eb[0].cpu()) and torch.equal(out[1], eb[1].cpu())
+        net.invalidate()
+        g3 = net.hot_path_graphed(*fb)
+        assert net._graphed.replays == 1 and all(torch.equal(x, y) for x, y in zip(eb, g3))
