@@ -288,6 +288,7 @@ def main():
                          "as consecutive single-pair forwards); 0 (default) = one pair per GPU per step")
     ap.add_argument("--latency-steps", type=int, default=200,
                     help="extra latency loop after the K timed steps (p50/p90 in the `latency` key; 0 = skip)")
+    ap.add_argument("--no-images", action="store_true", help="skip the images -> disparity record (`e2e_images` key)")
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph latency record (`graph` key)")
     ap.add_argument("--no-hshard-record", action="store_true",
                     help="N > 1: skip the H-sharded Middlebury sub-record (configs[4]) appended to the line")
@@ -418,6 +419,45 @@ def main():
         e2e_ms = e0.elapsed_time(e1)
         if rank == 0:
             sampler.stop()
+
+        # ---------------- end to end from IMAGES ("including the front end, reported separately") -------
+        img_rec = None
+        if not args.no_images and not args.batch:
+            gi = torch.Generator().manual_seed(1234 + rank)
+            imgs = [(torch.randn(B, 3, H, W, generator=gi).pin_memory(), torch.randn(B, 3, H, W, generator=gi).pin_memory())
+                    for _ in range(2)]
+
+            def img_steps(n):
+                for i in range(n):
+                    l, r = imgs[i % 2]
+                    p4, pv_ = net(l.to(dev, non_blocking=True), r.to(dev, non_blocking=True))
+                    out4.copy_(p4, non_blocking=True)
+                    outpv.copy_(pv_, non_blocking=True)
+
+            def fe_steps(n):
+                for i in range(n):
+                    l, r = imgs[i % 2]
+                    ld = l.to(dev, non_blocking=True)
+                    net.feature_extraction(torch.cat((ld, r.to(dev, non_blocking=True)), 0))
+                    net.guidance(ld)
+
+            img_rec = {"h2d_bytes_per_step": 2 * B * 3 * H * W * 4, "d2h_bytes_per_step": d2h,
+                       "what": "GwcNet(left, right): pinned host images -> H2D -> feature_extraction (left+right as one batch) "
+                               "+ Guidance -> hot path -> D2H of pred4 + prob_volume2; front end = torch/cuDNN fp32 (TF32 off) "
+                               "stem at 1/2 res + the 1/4-res layers on dca_conv2d_tc* (frontend.py)"}
+            for tag, on in (("kernel_front_end", True), ("torch_front_end", False)):
+                d.frontend.Options.enabled = on
+                for fn, key in ((img_steps, "pairs_per_s"), (fe_steps, "front_end_ms")):
+                    fn(8)                   # (cuDNN picks its algorithms and the allocator grows during the first calls)
+                    a_, b__ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    barrier()
+                    a_.record()
+                    fn(K)
+                    b__.record()
+                    barrier()
+                    ms_ = a_.elapsed_time(b__) / K
+                    img_rec.setdefault(tag, {})[key] = (B / (ms_ * 1e-3)) if key == "pairs_per_s" else ms_
+            d.frontend.Options.enabled = True
 
         # ---------------- latency distribution (20 warm-up + 200 timed), extra key only ----------
         n_lat = max(0, args.latency_steps)
@@ -577,6 +617,8 @@ def main():
             line["latency"] = lat
         if graph_rec is not None:
             line["graph"] = graph_rec
+        if img_rec is not None:
+            line["e2e_images"] = img_rec
         if hrec is not None:
             line["hshard"] = hrec
         line["host"] = {"numa_node_bound": numa, "cpus": len(os.sched_getaffinity(0)) if affinity0 is not None else None}

@@ -36,6 +36,10 @@ SIGNATURES = {
     "dca_tap_gather_softmax_regress": [_vp, _vp, _vp] + [_c_int] * 4 + [_vp],
     "dca_tap_gather3d": [_vp, _vp] + [_c_int] * 4 + [_vp],
     "dca_conv2d_tc": [_vp, _c_int, _vp, _vp, _vp, _vp, _c_int, _c_int] + [_c_int] * 5 + [_vp],
+    "dca_conv2d_tc_ex": [_vp, _c_int, _vp, _vp, _vp, _vp, _c_int, _vp, _c_int, _c_int] + [_c_int] * 6 + [_vp],
+    "dca_conv2d_tc_cat": [_vp, _c_int, _vp, _c_int, _vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _c_int, _c_int]
+                         + [_c_int] * 4 + [_vp],
+    "dca_planes_to_nchw_slice": [_vp, _c_int, _vp] + [_c_int] * 5 + [_ll, _vp],
     "dca_pack_weights_tc2d": [_vp, _c_int, _c_int, _vp, _c_int, _vp],
     "dca_pack_weights_tc2d_bytes": [_c_int] * 3,
     "dca_tc_set_halo": [_c_int],

@@ -58,7 +58,9 @@ struct TcParams {
   const __nv_bfloat16* res_pre; const __nv_bfloat16* res_post; size_t res_plane; int planes_res;
   __nv_bfloat16* y; size_t y_plane; int planes_out; int act;
   const __nv_bfloat16* up; int planes_up;   // optional half-resolution tensor added (trilinear x2) before BN
-  int nslab; int slab_c0[3]; int slab_dz[3];   // halo kernel: slabs per tile (3 depth slabs, or channel halves in 2-D)
+  int nslab; int slab_c0[5]; int slab_dz[5];   // halo kernel: slabs per tile (3 depth slabs, or up to 5 64-channel slabs in 2-D)
+  int slab_map[5];                 // ... and the input view (TcMaps::a index) each slab is read from (2-D channel concat)
+  int act_post;                    // activation applied once more AFTER res_post (ResidualBlock: relu(x + relu(bn(conv))))
   int ldc, co_base, cout_valid, out_f32;        // output row pitch / first channel / valid channels / fp32 output
   float inv_tiles_w, inv_tiles_h, inv_Dt, inv_ncls;   // reciprocals for the epilogue's tile decode (fast_divmod)
   int march_n;                     // > 0: depth-marching kernel, a work item = march_n consecutive output planes
@@ -418,6 +420,10 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
         if (p.res_post) {
           if (c0 != 0) load_raw16(post_raw, p.res_post, p.res_plane, p.planes_res, off);
           add_raw16(v, post_raw, p.planes_res);
+          if (p.act_post) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act_post);
+          }
         }
         if (p.out_f32 == 2) {                 // fp32 CHANNEL-major output [Cout][nvox] (per-tap partial sums of the 32->1 convs)
           const size_t nvox = (size_t)p.B * p.Do * p.Ho * p.Wo;
@@ -825,7 +831,7 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
           mbar_expect_tx(&afull[sa], PLANES * Cfg::SLAB_BYTES);
 #pragma unroll
           for (int pl = 0; pl < PLANES; ++pl)
-            tma_load_5d(a_base + sa * Cfg::A_SLOT + pl * Cfg::SLAB_PITCH, &maps.a[0], &afull[sa], p.slab_c0[kd],
+            tma_load_5d(a_base + sa * Cfg::A_SLOT + pl * Cfg::SLAB_PITCH, &maps.a[p.slab_map[kd]], &afull[sa], p.slab_c0[kd],
                         tw * TC_TW - 1, th * TC_TH - 1, td + p.slab_dz[kd], pl * p.B + b);
           if (++sa == Cfg::A_SLOTS) { sa = 0; pa ^= 1; }
           if (!Cfg::WRES) {
@@ -2421,7 +2427,7 @@ extern "C" int dca_conv3d_tc(int mode, const void* x, int planes_in, const void*
 }
 
 extern "C" long long dca_pack_weights_tc2d_bytes(int Co, int Ci, int planes) {
-  if (Co <= 0 || (Ci != 64 && Ci != 128) || planes < 1 || planes > 2) return 0;
+  if (Co <= 0 || Ci <= 0 || (Ci % 64) != 0 || Ci > 320 || planes < 1 || planes > 2) return 0;
   return (long long)((Co + 63) / 64) * (Ci / 64) * 9 * planes * 64 * 64 * 2;
 }
 
@@ -2434,38 +2440,91 @@ extern "C" int dca_pack_weights_tc2d(const float* w, int Co, int Ci, void* out, 
   return DCA_OK;
 }
 
-// y = act(scale * conv2d_3x3(x) + shift): x cost planes [P][B][1][H][W][Cin], Cin in {64,128}; y = cost planes
-// [P][B][1][H][W][Cout] (Cout % 64 == 0) or, with out_f32, fp32 channels-last [B][H][W][Cout] (any Cout).
-// Runs the halo-slab tcgen05 kernel once per 64-channel output chunk; Cin = 128 is two channel slabs.
-extern "C" int dca_conv2d_tc(const void* x, int planes, const void* w_tc2d, const float* scale, const float* shift,
-                             void* y, int out_f32, int act, int B, int Cin, int Cout, int H, int W, void* stream) {
-  if (!x || !w_tc2d || !y || B <= 0 || planes < 1 || planes > 2 || H <= 0 || W <= 0) return DCA_ERR_ARG;
-  if ((Cin != 64 && Cin != 128) || Cout <= 0 || (!out_f32 && (Cout % 64) != 0)) return DCA_ERR_UNSUPPORTED;
-  cudaStream_t st = (cudaStream_t)stream;
+// y = act_post(act(scale * conv2d_3x3(x, dilation dil) + shift) + res):
+//   x cost planes [P][B][1][H][W][Cin], Cin a multiple of 64 up to 320 (one 64-channel slab per accumulation pass);
+//   y = cost planes [P][B][1][H][W][Cout] (Cout % 64 == 0) or, with out_f32, fp32 channels-last [B][H][W][Cout];
+//   res (optional) = cost planes shaped like y, added after `act`; act_post is applied after that add.
+// Runs the halo-slab tcgen05 kernel once per 64-channel output chunk.  dil == 2 (feature_extraction.layer4,
+// gwcnet_dca_g.py:24): a dilation-2 3x3 conv is four independent dilation-1 convs on the (row parity, column parity)
+// sub-images, so the same kernel runs on four strided tensor-map views (H and W even) and the epilogue scatters with
+// out_stride 2 -- no gather, no second kernel.
+static int conv2d_tc_run(const void* const* xs, const int* cs, int nsrc, int planes, const void* w_tc2d,
+                         const float* scale, const float* shift, const void* res, int act_post, void* y, int out_f32,
+                         int act, int B, int Cout, int H, int W, int dil, cudaStream_t st) {
+  if (!w_tc2d || !y || B <= 0 || planes < 1 || planes > 2 || H <= 0 || W <= 0 || nsrc < 1 || nsrc > 3) return DCA_ERR_ARG;
+  int Cin = 0;
+  for (int i = 0; i < nsrc; ++i) {
+    if (!xs[i]) return DCA_ERR_ARG;
+    if (cs[i] <= 0 || (cs[i] % 64) != 0) return DCA_ERR_UNSUPPORTED;
+    Cin += cs[i];
+  }
+  if (Cin > 320 || Cout <= 0 || (!out_f32 && (Cout % 64) != 0)) return DCA_ERR_UNSUPPORTED;
+  if (dil != 1 && !(dil == 2 && (H % 2) == 0 && (W % 2) == 0)) return DCA_ERR_UNSUPPORTED;
+  if (res && out_f32) return DCA_ERR_UNSUPPORTED;
   const int P = planes, nslab = Cin / 64, nchunk = (Cout + 63) / 64;
-  TcMaps maps;
-  if (!make_act_map(&maps.a[0], x, Cin, W, H, 1, P * B, (size_t)Cin, (size_t)W * Cin, (size_t)H * W * Cin,
-                    (size_t)H * W * Cin, HB_W, HB_H, 64))
-    return DCA_ERR_LAUNCH;
-  for (int i = 1; i < 9; ++i) maps.a[i] = maps.a[0];
-  for (int j = 0; j < nchunk; ++j) {
-    TcParams p;
-    memset(&p, 0, sizeof(p));
-    p.B = B; p.Do = 1; p.Ho = H; p.Wo = W;
-    p.scale = scale ? scale + j * 64 : nullptr; p.shift = shift ? shift + j * 64 : nullptr;
-    p.y = (__nv_bfloat16*)y; p.y_plane = (size_t)B * H * W * Cout; p.res_plane = p.y_plane; p.planes_res = 1;
-    p.planes_out = P; p.act = act; p.dbg = g_dbg;
-    p.ldc = Cout; p.co_base = j * 64; p.cout_valid = Cout; p.out_f32 = out_f32;
-    p.nslab = nslab; p.slab_c0[0] = 0; p.slab_c0[1] = 64; p.slab_dz[0] = p.slab_dz[1] = 0;
-    p.Dt = 1; p.Ht = H; p.Wt = W; p.out_stride = 1; p.ntaps = 9 * nslab; p.ncls = 1;
-    p.cls_tap0[0] = 0; p.cls_tap0[1] = (unsigned char)(9 * nslab);
-    p.tiles_w = (W + TC_TW - 1) / TC_TW; p.tiles_h = (H + TC_TH - 1) / TC_TH;
-    const __nv_bfloat16* wj = (const __nv_bfloat16*)w_tc2d + (size_t)j * nslab * 9 * P * 64 * 64;
-    if (!make_w_map(&maps.w, wj, 64, nslab * 9 * P * 64, P * 64)) return DCA_ERR_LAUNCH;
-    const int rc = P == 2 ? launch_tc_halo<64, 64, 2>(maps, p, st) : launch_tc_halo<64, 64, 1>(maps, p, st);
-    if (rc != DCA_OK) return rc;
+  const int Hs = H / dil, Ws = W / dil;                       // sub-image extent (dil == 1: the image itself)
+  for (int par = 0; par < dil * dil; ++par) {
+    const int pa = par / dil, pb = par % dil;                 // row / column parity of this sub-image
+    TcMaps maps;
+    for (int i = 0; i < nsrc; ++i) {
+      const int C = cs[i];
+      const __nv_bfloat16* xb = (const __nv_bfloat16*)xs[i] + ((size_t)pa * W + pb) * C;
+      if (!make_act_map(&maps.a[i], xb, C, Ws, Hs, 1, P * B, (size_t)dil * C, (size_t)dil * W * C, (size_t)H * W * C,
+                        (size_t)H * W * C, HB_W, HB_H, 64))
+        return DCA_ERR_LAUNCH;
+    }
+    for (int i = nsrc; i < 9; ++i) maps.a[i] = maps.a[0];
+    for (int j = 0; j < nchunk; ++j) {
+      TcParams p;
+      memset(&p, 0, sizeof(p));
+      p.B = B; p.Do = 1; p.Ho = H; p.Wo = W;
+      p.scale = scale ? scale + j * 64 : nullptr; p.shift = shift ? shift + j * 64 : nullptr;
+      p.y = (__nv_bfloat16*)y; p.y_plane = (size_t)B * H * W * Cout; p.res_plane = p.y_plane; p.planes_res = res ? P : 1;
+      p.res_post = (const __nv_bfloat16*)res; p.act_post = res ? act_post : 0;
+      p.planes_out = P; p.act = act; p.dbg = g_dbg;
+      p.ldc = Cout; p.co_base = j * 64; p.cout_valid = Cout; p.out_f32 = out_f32;
+      p.nslab = nslab;
+      for (int i = 0, sl = 0; i < nsrc; ++i)
+        for (int c0 = 0; c0 < cs[i]; c0 += 64, ++sl) { p.slab_map[sl] = i; p.slab_c0[sl] = c0; p.slab_dz[sl] = 0; }
+      p.Dt = 1; p.Ht = Hs; p.Wt = Ws; p.out_stride = dil; p.out_stride_d = 1; p.ntaps = 9 * nslab; p.ncls = 1;
+      p.cls_off[0][0] = 0; p.cls_off[0][1] = (signed char)pa; p.cls_off[0][2] = (signed char)pb;
+      p.cls_tap0[0] = 0; p.cls_tap0[1] = (unsigned char)(9 * nslab);
+      p.tiles_w = (Ws + TC_TW - 1) / TC_TW; p.tiles_h = (Hs + TC_TH - 1) / TC_TH;
+      const __nv_bfloat16* wj = (const __nv_bfloat16*)w_tc2d + (size_t)j * nslab * 9 * P * 64 * 64;
+      if (!make_w_map(&maps.w, wj, 64, nslab * 9 * P * 64, P * 64)) return DCA_ERR_LAUNCH;
+      const int rc = P == 2 ? launch_tc_halo<64, 64, 2>(maps, p, st) : launch_tc_halo<64, 64, 1>(maps, p, st);
+      if (rc != DCA_OK) return rc;
+    }
   }
   return DCA_OK;
+}
+
+extern "C" int dca_conv2d_tc_ex(const void* x, int planes, const void* w_tc2d, const float* scale, const float* shift,
+                                const void* res, int act_post, void* y, int out_f32, int act, int B, int Cin, int Cout,
+                                int H, int W, int dil, void* stream) {
+  const void* xs[1] = {x};
+  const int cs[1] = {Cin};
+  return conv2d_tc_run(xs, cs, 1, planes, w_tc2d, scale, shift, res, act_post, y, out_f32, act, B, Cout, H, W, dil,
+                       (cudaStream_t)stream);
+}
+
+// The same conv over the CHANNEL CONCATENATION of up to three plane tensors (each a multiple of 64 channels, 320 in
+// total at most) without materialising it: every 64-channel slab of the accumulation is read through its own tensor map.
+// feature_extraction.lastconv reads cat(l2, l3, l4) (gwcnet_dca_g.py:60-65) this way.
+extern "C" int dca_conv2d_tc_cat(const void* x0, int C0, const void* x1, int C1, const void* x2, int C2, int planes,
+                                 const void* w_tc2d, const float* scale, const float* shift, void* y, int out_f32, int act,
+                                 int B, int Cout, int H, int W, void* stream) {
+  const void* xs[3] = {x0, x1, x2};
+  const int cs[3] = {C0, C1, C2};
+  const int nsrc = x2 ? 3 : (x1 ? 2 : 1);
+  return conv2d_tc_run(xs, cs, nsrc, planes, w_tc2d, scale, shift, nullptr, 0, y, out_f32, act, B, Cout, H, W, 1,
+                       (cudaStream_t)stream);
+}
+
+// y = act(scale * conv2d_3x3(x) + shift) (PropgationNet_4x.conv): dca_conv2d_tc_ex without residual and dilation
+extern "C" int dca_conv2d_tc(const void* x, int planes, const void* w_tc2d, const float* scale, const float* shift,
+                             void* y, int out_f32, int act, int B, int Cin, int Cout, int H, int W, void* stream) {
+  return dca_conv2d_tc_ex(x, planes, w_tc2d, scale, shift, nullptr, 0, y, out_f32, act, B, Cin, Cout, H, W, 1, stream);
 }
 
 // 1x1x1 conv 32 -> ntap (<= 32) "per-tap partial products" of a 3x3x3 conv to ONE channel (cva.classify.2 cva.py:53,

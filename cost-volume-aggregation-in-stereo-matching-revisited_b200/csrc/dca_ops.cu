@@ -974,7 +974,7 @@ planes_from_ncdhw_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict_
 
 __global__ void __launch_bounds__(256)
 planes_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ x, int planes, float* __restrict__ y, int B, int C, int Cp,
-                       size_t V) {
+                       size_t V, size_t ybs) {
   const size_t total = (size_t)B * C * V;
   const size_t plane = (size_t)B * V * Cp;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -984,7 +984,7 @@ planes_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ x, int planes, float* _
     const size_t off = ((size_t)b * V + v) * Cp + c;
     float r = h16_bits_to_float(__bfloat16_as_ushort(x[off]));
     if (planes == 2) r += h16_bits_to_float(__bfloat16_as_ushort(x[plane + off]));
-    y[i] = r;
+    y[(size_t)b * ybs + (size_t)c * V + v] = r;
   }
 }
 
@@ -1318,7 +1318,21 @@ extern "C" int dca_planes_to_ncdhw(const void* x, int planes, float* y, int B, i
   if (!x || !y || planes < 1 || planes > 2 || B <= 0 || C <= 0 || Cp < C) return DCA_ERR_ARG;
   const size_t V = (size_t)D * H * W, total = (size_t)B * C * V;
   planes_to_ncdhw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, planes, y, B,
-                                                                                 C, Cp, V);
+                                                                                 C, Cp, V, (size_t)C * V);
+  DCA_RETURN_IF_LAUNCH_FAILED();
+  return DCA_OK;
+}
+
+// Same, into a CHANNEL SLICE of a wider fp32 NCHW tensor: y points at the slice's first channel of batch 0 and
+// y_batch_stride (elements) is the batch pitch of the wide tensor -- how feature_extraction's torch.cat((l2, l3, l4))
+// (gwcnet_dca_g.py:60) is written without a copy.
+extern "C" int dca_planes_to_nchw_slice(const void* x, int planes, float* y, int B, int C, int Cp, int H, int W,
+                                        long long y_batch_stride, void* stream) {
+  if (!x || !y || planes < 1 || planes > 2 || B <= 0 || C <= 0 || Cp < C || y_batch_stride < (long long)C * H * W)
+    return DCA_ERR_ARG;
+  const size_t V = (size_t)H * W, total = (size_t)B * C * V;
+  planes_to_ncdhw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, planes, y, B,
+                                                                                 C, Cp, V, (size_t)y_batch_stride);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }

@@ -198,32 +198,51 @@ def conv(x: Planes, pc: PackedConv, mode=K3S1, act=ACT_NONE, res_pre: Planes = N
 
 
 class PackedConv2dTc:
-    """3x3 Conv2d (+ optional BN) packed for dca_conv2d_tc: bf16 hi/lo weights in 64x64 (Cout chunk, Cin slab) tiles,
-    BN folded to fp32 scale/shift padded to a multiple of 64."""
+    """Conv2d 3x3 (or 1x1, embedded as the centre tap of a 3x3) + optional bias + optional eval-mode BN packed for
+    dca_conv2d_tc*: 16-bit hi/lo weights in 64x64 (Cout chunk, Cin slab) tiles; bias and BN folded to fp32 scale/shift
+    padded to a multiple of 64 (BN(conv + b) = s*conv + (s*b + t)).  Cin a multiple of 64, at most 320."""
 
-    def __init__(self, weight, bn, planes):
+    def __init__(self, weight, bn, planes, bias=None, pad_cout=False):
         w = weight.detach().contiguous().float()
+        if w.shape[-1] == 1:                       # 1x1 -> 3x3 with a single non-zero tap (memory plumbing only)
+            w3 = torch.zeros((w.shape[0], w.shape[1], 3, 3), dtype=torch.float32, device=w.device)
+            w3[:, :, 1, 1] = w[:, :, 0, 0]
+            w = w3
+        self.cout_valid = w.shape[0]
+        if pad_cout and w.shape[0] % 64:           # plane outputs are whole 64-channel rows: zero output channels on top
+            assert bn is None and bias is None
+            wp = torch.zeros(((w.shape[0] + 63) // 64 * 64,) + tuple(w.shape[1:]), dtype=torch.float32, device=w.device)
+            wp[:w.shape[0]] = w
+            w = wp
         self.cout, self.cin = w.shape[0], w.shape[1]
         dev = w.device
         nb = _lib.load().dca_pack_weights_tc2d_bytes(self.cout, self.cin, planes)
         if nb <= 0:
-            raise _lib.DcaError("dca_conv2d_tc supports Cin in {64,128}")
+            raise _lib.DcaError("dca_conv2d_tc supports Cin = 64, 128, ... 320")
         self.w = torch.empty(nb, dtype=torch.uint8, device=dev)
         _lib.call("dca_pack_weights_tc2d", w.data_ptr(), self.cout, self.cin, self.w.data_ptr(), planes, _stream())
         self.planes = planes
         self.scale = self.shift = None
+        cpad = (self.cout + 63) // 64 * 64
         if bn is not None:
-            cpad = (self.cout + 63) // 64 * 64
             self.scale = torch.empty(cpad, dtype=torch.float32, device=dev)
             self.shift = torch.empty(cpad, dtype=torch.float32, device=dev)
             g, b = bn.weight.detach().float().contiguous(), bn.bias.detach().float().contiguous()
             m, v = bn.running_mean.detach().float().contiguous(), bn.running_var.detach().float().contiguous()
             _lib.call("dca_fold_bn", g.data_ptr(), b.data_ptr(), m.data_ptr(), v.data_ptr(), float(bn.eps),
                       self.scale.data_ptr(), self.shift.data_ptr(), self.cout, cpad, _stream())
+        if bias is not None:                       # load-time parameter folding on [Cout] vectors
+            b = bias.detach().float()
+            if self.scale is None:
+                self.scale = torch.ones(cpad, dtype=torch.float32, device=dev)
+                self.shift = torch.zeros(cpad, dtype=torch.float32, device=dev)
+            self.shift[:self.cout] += self.scale[:self.cout] * b
         torch.cuda.current_stream().synchronize()
 
 
-def conv2d_tc(x: Planes, pc: PackedConv2dTc, act=ACT_NONE, out_fp32=False, out=None):
+def conv2d_tc(x: Planes, pc: PackedConv2dTc, act=ACT_NONE, out_fp32=False, out=None, res: Planes = None, act_post=ACT_NONE,
+              dil=1):
+    """y = act_post(act(scale * conv3x3(x, dilation dil) + shift) + res) on the halo-slab tcgen05 kernel."""
     assert x.D == 1 and x.C == pc.cin and x.planes == pc.planes
     dev = x.t.device
     if out_fp32:
@@ -232,9 +251,37 @@ def conv2d_tc(x: Planes, pc: PackedConv2dTc, act=ACT_NONE, out_fp32=False, out=N
     else:
         y = out if out is not None else Planes(x.B, 1, x.H, x.W, pc.cout, x.planes, dev)
         yptr = y.ptr
-    _lib.call("dca_conv2d_tc", x.ptr, x.planes, pc.w.data_ptr(), _ptr(pc.scale), _ptr(pc.shift), yptr, int(out_fp32),
-              act, x.B, pc.cin, pc.cout, x.H, x.W, _stream())
+    if res is None and dil == 1:
+        _lib.call("dca_conv2d_tc", x.ptr, x.planes, pc.w.data_ptr(), _ptr(pc.scale), _ptr(pc.shift), yptr, int(out_fp32),
+                  act, x.B, pc.cin, pc.cout, x.H, x.W, _stream())
+        return y
+    if res is not None:
+        assert (res.B, res.H, res.W, res.C, res.planes) == (x.B, x.H, x.W, pc.cout, x.planes)
+    _lib.call("dca_conv2d_tc_ex", x.ptr, x.planes, pc.w.data_ptr(), _ptr(pc.scale), _ptr(pc.shift),
+              res.ptr if res is not None else 0, int(act_post), yptr, int(out_fp32), act, x.B, pc.cin, pc.cout, x.H, x.W,
+              int(dil), _stream())
     return y
+
+
+def conv2d_tc_cat(xs, pc: PackedConv2dTc, act=ACT_NONE):
+    """conv3x3 over the channel concatenation of up to three plane tensors, without materialising it."""
+    x0 = xs[0]
+    assert 1 <= len(xs) <= 3 and sum(x.C for x in xs) == pc.cin
+    assert all((x.B, x.H, x.W, x.planes) == (x0.B, x0.H, x0.W, x0.planes) for x in xs) and x0.planes == pc.planes
+    y = Planes(x0.B, 1, x0.H, x0.W, pc.cout, x0.planes, x0.t.device)
+    a = [(x.ptr, x.C) for x in xs] + [(0, 0)] * (3 - len(xs))
+    _lib.call("dca_conv2d_tc_cat", a[0][0], a[0][1], a[1][0], a[1][1], a[2][0], a[2][1], x0.planes, pc.w.data_ptr(),
+              _ptr(pc.scale), _ptr(pc.shift), y.ptr, 0, act, x0.B, pc.cout, x0.H, x0.W, _stream())
+    return y
+
+
+def planes_to_nchw_slice(x: Planes, out, c0, channels=None):
+    """Write x (2-D planes) as channels [c0, c0 + C) of the fp32 NCHW tensor `out` (the torch.cat of the reference)."""
+    C = channels or x.C
+    assert x.D == 1 and out.is_contiguous() and out.dtype == torch.float32 and out.shape[0] == x.B
+    assert out.shape[2:] == (x.H, x.W) and c0 + C <= out.shape[1]
+    _lib.call("dca_planes_to_nchw_slice", x.ptr, x.planes, out.data_ptr() + 4 * c0 * x.H * x.W, x.B, C, x.C, x.H, x.W,
+              out.shape[1] * x.H * x.W, _stream())
 
 
 def tc_supported(mode, cin, cout):

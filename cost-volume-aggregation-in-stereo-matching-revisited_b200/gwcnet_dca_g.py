@@ -26,6 +26,7 @@ class feature_extraction(nn.Module):
             self.lastconv = nn.Sequential(convbn(320, 128, 3, 1, 1, 1), nn.ReLU(inplace=True),
                                           nn.Conv2d(128, concat_feature_channel, kernel_size=1, padding=0, stride=1,
                                                     bias=False))
+        self.precision_planes = 2
 
     def _make_layer(self, block, planes, blocks, stride, pad, dilation):
         downsample = None
@@ -39,6 +40,10 @@ class feature_extraction(nn.Module):
         return nn.Sequential(*layers)
 
     def forward(self, x):
+        from . import frontend
+        if frontend.use_kernels(self, x) and x.shape[2] % 8 == 0 and x.shape[3] % 8 == 0:
+            # CUDA + eval: the 1/4-resolution layers (layer2[1:], layer3, layer4, lastconv) on the tcgen05 2-D conv kernel
+            return frontend.feature_extraction_forward(self, x, self.precision_planes)
         x = self.layer1(self.firstconv(x))
         l2 = self.layer2(x)
         l3 = self.layer3(l2)
@@ -194,9 +199,11 @@ class GwcNet(nn.Module):
         if self.training:
             raise NotImplementedError("dcanet_b200 is an inference engine: call .eval() (training-mode heads "
                                       "classif0-2 exist only so checkpoints load)")
-        fl = self.feature_extraction(left)
-        fr = self.feature_extraction(right)
-        g = self.guidance(left)["g"]
-        pred, pv = self.hot_path(fl["gwc_feature"], fr["gwc_feature"], fl.get("concat_feature"),
-                                 fr.get("concat_feature"), g)
+        from . import frontend
+        B = left.shape[0]
+        with frontend._no_tf32():          # whatever part of the front end runs on cuDNN runs in true fp32
+            f = self.feature_extraction(torch.cat((left, right), dim=0))      # eval-mode BN: batching changes nothing
+            g = self.guidance(left)["g"]
+        gwc, cat = f["gwc_feature"], f.get("concat_feature")
+        pred, pv = self.hot_path(gwc[:B], gwc[B:], None if cat is None else cat[:B], None if cat is None else cat[B:], g)
         return (pred.squeeze(1) if self.SQUEEZE_PRED else pred), pv

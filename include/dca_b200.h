@@ -121,6 +121,21 @@ int dca_conv2d_tc(const void* x, int planes, const void* w_tc2d, const float* sc
                   int out_f32, int act, int B, int Cin, int Cout, int H, int W, void* stream);
 int dca_pack_weights_tc2d(const float* w, int Co, int Ci, void* out, int planes, void* stream);
 long long dca_pack_weights_tc2d_bytes(int Co, int Ci, int planes);
+/* The 2-D family member behind the 1/4-resolution part of the front end: feature_extraction.layer2[1:],
+ * layer3, layer4 (dilation 2) and lastconv (gwcnet_dca_g.py:22-29, BasicBlock submodule.py:251-273), Guidance.layer2[1],
+ * conv_g0 and guidance (submodule.py:395-460, ResidualBlock :305-347).
+ *   y = act_post(act(scale * conv2d_3x3(x, dilation dil) + shift) + res)
+ * Cin a multiple of 64 up to 320 (64-channel slabs), dil in {1, 2} (2: H and W even; four parity sub-images through
+ * strided tensor maps), res = optional cost planes shaped like y.  1x1 convs are passed as 3x3 weights whose only
+ * non-zero tap is the centre. */
+int dca_conv2d_tc_ex(const void* x, int planes, const void* w_tc2d, const float* scale, const float* shift,
+                     const void* res, int act_post, void* y, int out_f32, int act, int B, int Cin, int Cout, int H, int W,
+                     int dil, void* stream);
+/* The same conv over the channel concatenation cat(x0, x1, x2) (each a multiple of 64 channels, <= 320 in total; unused
+ * sources NULL) without materialising it: feature_extraction.lastconv on cat(l2, l3, l4) (gwcnet_dca_g.py:60-65). */
+int dca_conv2d_tc_cat(const void* x0, int C0, const void* x1, int C1, const void* x2, int C2, int planes,
+                      const void* w_tc2d, const float* scale, const float* shift, void* y, int out_f32, int act, int B,
+                      int Cout, int H, int W, void* stream);
 /* k3 s1 main loop selector: 1 = halo'd slab reuse (default), 0 = one TMA box per tap. */
 int dca_tc_set_halo(int on);
 /* 1 (default): DCANet-shaped volumes (C=320, Cc=12, G in {8,20,40}, W % 4 == 0) use the 16-byte-staged group-pair
@@ -221,6 +236,10 @@ int dca_softmax_regress_upsample(const float* logits, const float* mask, float* 
 int dca_planes_from_ncdhw(const float* x, void* y, int planes, int B, int C, int Cp, int D, int H, int W,
                           void* stream);
 int dca_planes_to_ncdhw(const void* x, int planes, float* y, int B, int C, int Cp, int D, int H, int W, void* stream);
+/* cost planes [planes][B][1][H][W][Cp] -> a C-channel slice of a wider fp32 NCHW tensor (batch pitch y_batch_stride
+ * elements): torch.cat((l2, l3, l4), dim=1) of feature_extraction.forward (gwcnet_dca_g.py:60) without the copy. */
+int dca_planes_to_nchw_slice(const void* x, int planes, float* y, int B, int C, int Cp, int H, int W,
+                             long long y_batch_stride, void* stream);
 int dca_pack_weights(const float* w, int transposed, int Co, int Ci, int taps, float* out, int CoPad, void* stream);
 int dca_fold_bn(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale,
                 float* shift, int C, int Cpad, void* stream);
