@@ -1915,19 +1915,20 @@ static int launch_tc_halo(const TcMaps& maps, const TcParams& p, cudaStream_t st
 
 
 // ------------------------------------------------------------------ 2-D 3x3 convs (PropgationNet_4x.conv, gwcnet_dca_g.py:112-115)
-// weight pack for the 2-D path: [Cout chunk of 64][channel slab of 64][tap 9][plane][64][64] bf16 (zero padded)
+// weight pack for the 2-D path: [Cout chunk of T][channel slab of T][tap 9][plane][T][T] 16-bit (zero padded); T = 64, or 32
+// for the 32-channel layers of the 1/2-resolution stem
 __global__ void pack_weight_tc2d_kernel(const float* __restrict__ w, int Co, int Ci, __nv_bfloat16* __restrict__ out,
-                                        int planes, int nchunk, int nslab) {
-  const int total = nchunk * nslab * 9 * 64 * 64;
+                                        int planes, int nchunk, int nslab, int T) {
+  const int TT = T * T, total = nchunk * nslab * 9 * TT;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int ci = i % 64, co = (i / 64) % 64, t = (i / 4096) % 9, sl = (i / (4096 * 9)) % nslab, j = i / (4096 * 9 * nslab);
-    const int gco = j * 64 + co, gci = sl * 64 + ci;
+    const int ci = i % T, co = (i / T) % T, t = (i / TT) % 9, sl = (i / (TT * 9)) % nslab, j = i / (TT * 9 * nslab);
+    const int gco = j * T + co, gci = sl * T + ci;
     const float v = (gco < Co && gci < Ci) ? w[((size_t)gco * Ci + gci) * 9 + t] : 0.f;
     uint32_t lo;
     const uint32_t hi = split_bf16(v, lo);
     const size_t tapbase = ((size_t)(j * nslab + sl) * 9 + t) * planes;
-    out[((tapbase + 0) * 64 + co) * 64 + ci] = __ushort_as_bfloat16((unsigned short)hi);
-    if (planes == 2) out[((tapbase + 1) * 64 + co) * 64 + ci] = __ushort_as_bfloat16((unsigned short)lo);
+    out[((tapbase + 0) * T + co) * T + ci] = __ushort_as_bfloat16((unsigned short)hi);
+    if (planes == 2) out[((tapbase + 1) * T + co) * T + ci] = __ushort_as_bfloat16((unsigned short)lo);
   }
 }
 
@@ -2426,16 +2427,21 @@ extern "C" int dca_conv3d_tc(int mode, const void* x, int planes_in, const void*
   return run();
 }
 
+// channel tile of the 2-D family: 64 (Cin a multiple of 64, up to 320) or 32 (Cin == 32: the 1/2-resolution stem)
+static inline int tc2d_tile(int Ci) { return (Ci > 0 && Ci % 64 == 0 && Ci <= 320) ? 64 : (Ci == 32 ? 32 : 0); }
+
 extern "C" long long dca_pack_weights_tc2d_bytes(int Co, int Ci, int planes) {
-  if (Co <= 0 || Ci <= 0 || (Ci % 64) != 0 || Ci > 320 || planes < 1 || planes > 2) return 0;
-  return (long long)((Co + 63) / 64) * (Ci / 64) * 9 * planes * 64 * 64 * 2;
+  const int T = tc2d_tile(Ci);
+  if (Co <= 0 || !T || planes < 1 || planes > 2) return 0;
+  return (long long)((Co + T - 1) / T) * (Ci / T) * 9 * planes * T * T * 2;
 }
 
 extern "C" int dca_pack_weights_tc2d(const float* w, int Co, int Ci, void* out, int planes, void* stream) {
   if (!w || !out || dca_pack_weights_tc2d_bytes(Co, Ci, planes) == 0) return DCA_ERR_ARG;
-  const int nchunk = (Co + 63) / 64, nslab = Ci / 64, total = nchunk * nslab * 9 * 4096;
+  const int T = tc2d_tile(Ci);
+  const int nchunk = (Co + T - 1) / T, nslab = Ci / T, total = nchunk * nslab * 9 * T * T;
   pack_weight_tc2d_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, Co, Ci, (__nv_bfloat16*)out, planes,
-                                                                                 nchunk, nslab);
+                                                                                 nchunk, nslab, T);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }
@@ -2448,20 +2454,11 @@ extern "C" int dca_pack_weights_tc2d(const float* w, int Co, int Ci, void* out, 
 // gwcnet_dca_g.py:24): a dilation-2 3x3 conv is four independent dilation-1 convs on the (row parity, column parity)
 // sub-images, so the same kernel runs on four strided tensor-map views (H and W even) and the epilogue scatters with
 // out_stride 2 -- no gather, no second kernel.
-static int conv2d_tc_run(const void* const* xs, const int* cs, int nsrc, int planes, const void* w_tc2d,
-                         const float* scale, const float* shift, const void* res, int act_post, void* y, int out_f32,
-                         int act, int B, int Cout, int H, int W, int dil, cudaStream_t st) {
-  if (!w_tc2d || !y || B <= 0 || planes < 1 || planes > 2 || H <= 0 || W <= 0 || nsrc < 1 || nsrc > 3) return DCA_ERR_ARG;
-  int Cin = 0;
-  for (int i = 0; i < nsrc; ++i) {
-    if (!xs[i]) return DCA_ERR_ARG;
-    if (cs[i] <= 0 || (cs[i] % 64) != 0) return DCA_ERR_UNSUPPORTED;
-    Cin += cs[i];
-  }
-  if (Cin > 320 || Cout <= 0 || (!out_f32 && (Cout % 64) != 0)) return DCA_ERR_UNSUPPORTED;
-  if (dil != 1 && !(dil == 2 && (H % 2) == 0 && (W % 2) == 0)) return DCA_ERR_UNSUPPORTED;
-  if (res && out_f32) return DCA_ERR_UNSUPPORTED;
-  const int P = planes, nslab = Cin / 64, nchunk = (Cout + 63) / 64;
+template <int T>
+static int conv2d_tc_run_t(const void* const* xs, const int* cs, int nsrc, int planes, const void* w_tc2d,
+                           const float* scale, const float* shift, const void* res, int act_post, void* y, int out_f32,
+                           int act, int B, int Cin, int Cout, int H, int W, int dil, cudaStream_t st) {
+  const int P = planes, nslab = Cin / T, nchunk = (Cout + T - 1) / T;
   const int Hs = H / dil, Ws = W / dil;                       // sub-image extent (dil == 1: the image itself)
   for (int par = 0; par < dil * dil; ++par) {
     const int pa = par / dil, pb = par % dil;                 // row / column parity of this sub-image
@@ -2470,7 +2467,7 @@ static int conv2d_tc_run(const void* const* xs, const int* cs, int nsrc, int pla
       const int C = cs[i];
       const __nv_bfloat16* xb = (const __nv_bfloat16*)xs[i] + ((size_t)pa * W + pb) * C;
       if (!make_act_map(&maps.a[i], xb, C, Ws, Hs, 1, P * B, (size_t)dil * C, (size_t)dil * W * C, (size_t)H * W * C,
-                        (size_t)H * W * C, HB_W, HB_H, 64))
+                        (size_t)H * W * C, HB_W, HB_H, T))
         return DCA_ERR_LAUNCH;
     }
     for (int i = nsrc; i < 9; ++i) maps.a[i] = maps.a[0];
@@ -2478,25 +2475,47 @@ static int conv2d_tc_run(const void* const* xs, const int* cs, int nsrc, int pla
       TcParams p;
       memset(&p, 0, sizeof(p));
       p.B = B; p.Do = 1; p.Ho = H; p.Wo = W;
-      p.scale = scale ? scale + j * 64 : nullptr; p.shift = shift ? shift + j * 64 : nullptr;
+      p.scale = scale ? scale + j * T : nullptr; p.shift = shift ? shift + j * T : nullptr;
       p.y = (__nv_bfloat16*)y; p.y_plane = (size_t)B * H * W * Cout; p.res_plane = p.y_plane; p.planes_res = res ? P : 1;
       p.res_post = (const __nv_bfloat16*)res; p.act_post = res ? act_post : 0;
       p.planes_out = P; p.act = act; p.dbg = g_dbg;
-      p.ldc = Cout; p.co_base = j * 64; p.cout_valid = Cout; p.out_f32 = out_f32;
+      p.ldc = Cout; p.co_base = j * T; p.cout_valid = Cout; p.out_f32 = out_f32;
       p.nslab = nslab;
       for (int i = 0, sl = 0; i < nsrc; ++i)
-        for (int c0 = 0; c0 < cs[i]; c0 += 64, ++sl) { p.slab_map[sl] = i; p.slab_c0[sl] = c0; p.slab_dz[sl] = 0; }
+        for (int c0 = 0; c0 < cs[i]; c0 += T, ++sl) { p.slab_map[sl] = i; p.slab_c0[sl] = c0; p.slab_dz[sl] = 0; }
       p.Dt = 1; p.Ht = Hs; p.Wt = Ws; p.out_stride = dil; p.out_stride_d = 1; p.ntaps = 9 * nslab; p.ncls = 1;
       p.cls_off[0][0] = 0; p.cls_off[0][1] = (signed char)pa; p.cls_off[0][2] = (signed char)pb;
       p.cls_tap0[0] = 0; p.cls_tap0[1] = (unsigned char)(9 * nslab);
       p.tiles_w = (Ws + TC_TW - 1) / TC_TW; p.tiles_h = (Hs + TC_TH - 1) / TC_TH;
-      const __nv_bfloat16* wj = (const __nv_bfloat16*)w_tc2d + (size_t)j * nslab * 9 * P * 64 * 64;
-      if (!make_w_map(&maps.w, wj, 64, nslab * 9 * P * 64, P * 64)) return DCA_ERR_LAUNCH;
-      const int rc = P == 2 ? launch_tc_halo<64, 64, 2>(maps, p, st) : launch_tc_halo<64, 64, 1>(maps, p, st);
+      const __nv_bfloat16* wj = (const __nv_bfloat16*)w_tc2d + (size_t)j * nslab * 9 * P * T * T;
+      if (!make_w_map(&maps.w, wj, T, nslab * 9 * P * T, P * T)) return DCA_ERR_LAUNCH;
+      const int rc = P == 2 ? launch_tc_halo<T, T, 2>(maps, p, st) : launch_tc_halo<T, T, 1>(maps, p, st);
       if (rc != DCA_OK) return rc;
     }
   }
   return DCA_OK;
+}
+
+static int conv2d_tc_run(const void* const* xs, const int* cs, int nsrc, int planes, const void* w_tc2d,
+                         const float* scale, const float* shift, const void* res, int act_post, void* y, int out_f32,
+                         int act, int B, int Cout, int H, int W, int dil, cudaStream_t st) {
+  if (!w_tc2d || !y || B <= 0 || planes < 1 || planes > 2 || H <= 0 || W <= 0 || nsrc < 1 || nsrc > 3) return DCA_ERR_ARG;
+  int Cin = 0;
+  for (int i = 0; i < nsrc; ++i) {
+    if (!xs[i]) return DCA_ERR_ARG;
+    Cin += cs[i];
+  }
+  const int T = tc2d_tile(Cin);
+  if (!T) return DCA_ERR_UNSUPPORTED;
+  for (int i = 0; i < nsrc; ++i)
+    if (cs[i] <= 0 || (cs[i] % T) != 0) return DCA_ERR_UNSUPPORTED;
+  if (Cout <= 0 || (!out_f32 && (Cout % T) != 0)) return DCA_ERR_UNSUPPORTED;
+  if (dil != 1 && !(dil == 2 && (H % 2) == 0 && (W % 2) == 0)) return DCA_ERR_UNSUPPORTED;
+  if (res && out_f32) return DCA_ERR_UNSUPPORTED;
+  return T == 64 ? conv2d_tc_run_t<64>(xs, cs, nsrc, planes, w_tc2d, scale, shift, res, act_post, y, out_f32, act, B, Cin,
+                                       Cout, H, W, dil, st)
+                 : conv2d_tc_run_t<32>(xs, cs, nsrc, planes, w_tc2d, scale, shift, res, act_post, y, out_f32, act, B, Cin,
+                                       Cout, H, W, dil, st);
 }
 
 extern "C" int dca_conv2d_tc_ex(const void* x, int planes, const void* w_tc2d, const float* scale, const float* shift,

@@ -8,14 +8,17 @@ shape family of `dca_conv2d_tc*` -- and hold 80 % of the front end's FLOPs:
                        layer3       3 BasicBlocks, 64 -> 128 -> 128 (+ 1x1 downsample)   6 + 1
                        layer4       3 BasicBlocks, 128 -> 128, dilation 2         6 convs (four parity sub-images each)
                        lastconv     320 -> 128 (+BN+ReLU) on cat(l2, l3, l4), 1x1 128 -> 12
-  Guidance             layer2[1]    ResidualBlock 64 -> 64 (conv bias + BN + ReLU, relu(x + y))
+  feature_extraction   firstconv[2,4], layer1 (3 BasicBlocks), 32 -> 32 at 1/2 resolution        8 convs
+  Guidance             layer1       2 ResidualBlocks 32 -> 32 at 1/2 resolution              4 convs
+                       layer2[1]    ResidualBlock 64 -> 64 (conv bias + BN + ReLU, relu(x + y))
                        conv_g0      2 x BasicConv 64 -> 64, guidance 64 -> 64
 
 BN (eval) and conv biases are folded into the epilogue's fp32 scale/shift; residual adds (`out += x`, BasicBlock
 submodule.py:272; `relu(x + y)`, ResidualBlock :347) are epilogue terms; the channel concat is never materialised in
 the plane layout (the 320-channel conv reads its five 64-channel slabs through three tensor maps) and is written once,
-as fp32 NCHW, for the volume kernel.  The 1/2-resolution stem (3-channel and 32-channel convs, the stride-2 convs)
-stays on torch/cuDNN with TF32 switched off -- its kernels are the next step.
+as fp32 NCHW, for the volume kernel.  The 32-channel stride-1 layers of the 1/2-resolution stem (firstconv[2], firstconv[4],
+feature_extraction.layer1, Guidance.layer1) run on the same kernel with a 32-channel tile.  What stays on torch/cuDNN (true
+fp32, TF32 switched off) are the five strided convs: the 3-channel stems (3x3 s2, 7x7 s2) and the two stride-2 blocks.
 
 torch here: device memory, the stem modules, and load-time parameter folding.  No arithmetic of the layers listed above.
 """
@@ -54,9 +57,36 @@ class _Block:
         return E.conv2d_tc(h, self.c2, E.ACT_NONE, res=r, dil=self.dil)
 
 
+class _ResBlock:
+    """ResidualBlock with stride 1 (submodule.py:305-347): relu(x + relu(bn2(conv2(relu(bn1(conv1 x)))))), convs with bias."""
+
+    def __init__(self, rb, planes):
+        for n in (rb.norm1, rb.norm2):
+            if not isinstance(n, torch.nn.BatchNorm2d):
+                raise _lib.DcaError("Guidance on the tcgen05 kernels needs norm_fn='batch' (eval-mode BN folds into the epilogue)")
+        if rb.downsample is not None:
+            raise _lib.DcaError("stride-2 ResidualBlocks stay on torch")
+        self.c1 = E.PackedConv2dTc(rb.conv1.weight, rb.norm1, planes, bias=rb.conv1.bias)
+        self.c2 = E.PackedConv2dTc(rb.conv2.weight, rb.norm2, planes, bias=rb.conv2.bias)
+
+    def __call__(self, x):
+        y = E.conv2d_tc(x, self.c1, E.ACT_RELU)
+        return E.conv2d_tc(y, self.c2, E.ACT_RELU, res=x, act_post=E.ACT_RELU)
+
+
+def _planes_to_nchw(p, channels=None):
+    C = channels or p.C
+    out = torch.empty((p.B, C, p.H, p.W), dtype=torch.float32, device=p.t.device)
+    E.planes_to_nchw_slice(p, out, 0, channels=C)
+    return out
+
+
 class PackedFeatureExtraction:
     def __init__(self, fe, planes):
         self.planes = planes
+        # 1/2-resolution stem: firstconv's two 32 -> 32 convs and layer1 (3 BasicBlocks) on the 32-channel tile
+        self.first = [E.PackedConv2dTc(fe.firstconv[i][0].weight, fe.firstconv[i][1], planes) for i in (2, 4)]
+        self.layer1 = [_Block(b, planes) for b in fe.layer1]
         self.layer2 = [_Block(b, planes) for b in list(fe.layer2)[1:]]
         self.layer3 = [_Block(b, planes) for b in fe.layer3]
         self.layer4 = [_Block(b, planes) for b in fe.layer4]
@@ -84,7 +114,14 @@ def feature_extraction_forward(fe, x, planes=2):
     """feature_extraction.forward (gwcnet_dca_g.py:53-66) for a CUDA batch in eval mode."""
     pk = E.cached_pack(fe, ("frontend", planes), lambda: PackedFeatureExtraction(fe, planes))
     with _no_tf32():
-        s = fe.layer2[0](fe.layer1(fe.firstconv(x)))          # 1/2-res stem + the stride-2 block: [B,64,H/4,W/4]
+        s = fe.firstconv[1](fe.firstconv[0](x))               # 3 -> 32, stride 2 (+BN+ReLU): cuDNN, true fp32
+    p = E.Planes.from_ncdhw(s, planes=planes)
+    for pc in pk.first:
+        p = E.conv2d_tc(p, pc, E.ACT_RELU)
+    for blk in pk.layer1:
+        p = blk(p)
+    with _no_tf32():
+        s = fe.layer2[0](_planes_to_nchw(p))                  # the stride-2 block (32 -> 64, 1x1 s2 downsample): cuDNN
     p = E.Planes.from_ncdhw(s, planes=planes)
     for blk in pk.layer2:
         p = blk(p)
@@ -111,12 +148,8 @@ def feature_extraction_forward(fe, x, planes=2):
 
 class PackedGuidance:
     def __init__(self, g, planes):
-        rb = g.layer2[1]
-        for n in (rb.norm1, rb.norm2, g.conv_g0[0].bn, g.conv_g0[1].bn):
-            if not isinstance(n, torch.nn.BatchNorm2d):
-                raise _lib.DcaError("Guidance on the tcgen05 kernels needs norm_fn='batch' (eval-mode BN folds into the epilogue)")
-        self.r1 = E.PackedConv2dTc(rb.conv1.weight, rb.norm1, planes, bias=rb.conv1.bias)
-        self.r2 = E.PackedConv2dTc(rb.conv2.weight, rb.norm2, planes, bias=rb.conv2.bias)
+        self.layer1 = [_ResBlock(rb, planes) for rb in g.layer1]          # 32 channels at 1/2 resolution
+        self.rb = _ResBlock(g.layer2[1], planes)
         self.g0 = E.PackedConv2dTc(g.conv_g0[0].conv.weight, g.conv_g0[0].bn, planes)
         self.g1 = E.PackedConv2dTc(g.conv_g0[1].conv.weight, g.conv_g0[1].bn, planes)
         self.out = E.PackedConv2dTc(g.guidance.weight, None, planes, bias=g.guidance.bias)
@@ -127,16 +160,17 @@ def guidance_forward(g, x, planes=2):
     """Guidance.forward (submodule.py:452-460) for a CUDA batch in eval mode -> {'g': [B,64,H/4,W/4]}."""
     pk = E.cached_pack(g, ("frontend", planes), lambda: PackedGuidance(g, planes))
     with _no_tf32():
-        s = g.layer2[0](g.layer1(g.conv_start(x)))            # 7x7 s2 stem, 1/2-res blocks, the stride-2 block
+        s = g.conv_start(x)                                   # 7x7 stride-2 stem (+BN+ReLU): cuDNN, true fp32
     p = E.Planes.from_ncdhw(s, planes=planes)
-    y = E.conv2d_tc(p, pk.r1, E.ACT_RELU)
-    p = E.conv2d_tc(y, pk.r2, E.ACT_RELU, res=p, act_post=E.ACT_RELU)      # relu(x + relu(bn(conv2)))
+    for rb in pk.layer1:
+        p = rb(p)
+    with _no_tf32():
+        s = g.layer2[0](_planes_to_nchw(p))                   # the stride-2 ResidualBlock: cuDNN
+    p = pk.rb(E.Planes.from_ncdhw(s, planes=planes))
     p = E.conv2d_tc(p, pk.g0, E.ACT_RELU)
     p = E.conv2d_tc(p, pk.g1, E.ACT_RELU)
     p = E.conv2d_tc(p, pk.out, E.ACT_NONE)
-    out = torch.empty((p.B, pk.cout, p.H, p.W), dtype=torch.float32, device=x.device)
-    E.planes_to_nchw_slice(p, out, 0, channels=pk.cout)
-    return {"g": out}
+    return {"g": _planes_to_nchw(p, pk.cout)}
 
 
 def use_kernels(module, x):

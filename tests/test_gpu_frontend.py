@@ -25,6 +25,9 @@ def _planes_to_nchw(E, y):
     (2, 128, 128, 10, 52, 2, False, True, False, 0),
     (1, 64, 64, 19, 33, 1, True, True, True, 1),       # ResidualBlock.conv2: bias + BN + ReLU, relu(x + y)
     (1, 64, 64, 16, 24, 1, True, False, False, 0),     # conv with bias, no BN
+    (2, 32, 32, 30, 44, 1, False, True, True, 0),      # the 1/2-res stem: 32-channel tile (firstconv, layer1)
+    (1, 32, 32, 17, 25, 1, True, True, True, 1),       # Guidance.layer1 ResidualBlock at 32 channels
+    (1, 32, 64, 12, 20, 1, False, True, False, 0),     # 32 -> 64: two 32-channel output chunks
 ])
 def test_conv2d_tc_ex_matches_torch(B, Cin, Cout, H, W, dil, bias, bn, res, act_post):
     d, E = _mods()
