@@ -435,16 +435,18 @@ def main():
                     outpv.copy_(pv_, non_blocking=True)
 
             def fe_steps(n):
-                for i in range(n):
-                    l, r = imgs[i % 2]
-                    ld = l.to(dev, non_blocking=True)
-                    net.feature_extraction(torch.cat((ld, r.to(dev, non_blocking=True)), 0))
-                    net.guidance(ld)
+                with d.frontend._no_tf32():          # as GwcNet.forward runs it: cuDNN in true fp32
+                    for i in range(n):
+                        l, r = imgs[i % 2]
+                        ld = l.to(dev, non_blocking=True)
+                        net.feature_extraction(torch.cat((ld, r.to(dev, non_blocking=True)), 0))
+                        net.guidance(ld)
 
             img_rec = {"h2d_bytes_per_step": 2 * B * 3 * H * W * 4, "d2h_bytes_per_step": d2h,
                        "what": "GwcNet(left, right): pinned host images -> H2D -> feature_extraction (left+right as one batch) "
-                               "+ Guidance -> hot path -> D2H of pred4 + prob_volume2; front end = torch/cuDNN fp32 (TF32 off) "
-                               "stem at 1/2 res + the 1/4-res layers on dca_conv2d_tc* (frontend.py)"}
+                               "+ Guidance -> hot path -> D2H of pred4 + prob_volume2.  kernel_front_end: every stride-1 conv of the "
+                               "front end on dca_conv2d_tc* (frontend.py), the five strided convs on cuDNN; torch_front_end: "
+                               "the same modules entirely on cuDNN; both in true fp32 (TF32 off)"}
             for tag, on in (("kernel_front_end", True), ("torch_front_end", False)):
                 d.frontend.Options.enabled = on
                 for fn, key in ((img_steps, "pairs_per_s"), (fe_steps, "front_end_ms")):
