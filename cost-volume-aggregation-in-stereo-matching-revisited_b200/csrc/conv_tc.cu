@@ -2081,7 +2081,7 @@ static int launch_deconv_pair(const TcMaps& maps, const TcParams& p, const Up2Pa
 static int g_use_deconv_pair = 1;
 static int g_use_pool_march = 1;
 static int g_up2_side_slots = 2;   // (4 was measured: 91.2 us either way -- the stream is not ring-depth bound)
-static int g_pool_ctas_per_sm = 4;   // measured at KITTI: 2: 50 us, 4: 44 us, 8: 47 us (thread-per-output kernel: 66 us)
+static int g_pool_ctas_per_sm = 3;   // measured at KITTI (r2f kernel: ld.shared + predicate barrier): 2: 38.7 us, 3: 38.0, 4: 39.1, 5-6: 47.2, 8: 40.4, 12: 40.9 (thread-per-output kernel: 66 us)
 
 }  // namespace dca
 
