@@ -534,7 +534,7 @@ def main():
             ach = fl / (conv_ms * 1e-3) / 1e12
             kernel_name = "conv3d_tc" if (E.Options.use_tc and pc.w_tc is not None and E.tc_supported(E.K3S1, 32, 32)) \
                 else "conv_direct_kernel<32,16> (CUDA-core fp32)"
-            tr = ncu_traffic("conv_tc_march_kernel<32, %d" % P) if kernel_name == "conv3d_tc" else None
+            tr = ncu_traffic("conv_tc_march_kernel<32, %d, 0" % P) if kernel_name == "conv3d_tc" else None
             issued = 3.0 if (P == 2 and kernel_name == "conv3d_tc") else 1.0
             roof = {"kernel": f"{kernel_name} (conv_tc_march_kernel, tcgen05) k3 s1 32->32 @ {maxdisp // 4}x{H4}x{W4}", "bound": "tensor",
                     "achieved": ach, "peak": tf_sust, "unit": "TFLOP/s", "frac": ach / tf_sust,
