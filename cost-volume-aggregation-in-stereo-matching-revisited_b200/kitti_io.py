@@ -85,3 +85,121 @@ def predict_files(model, leftname, rightname, savename=None, crop_height=384, cr
     if savename is not None:
         save_disparity_png(savename, disp)
     return disp
+
+
+class ImagePipeline:
+    """The loop of my_img.py (`main()` :112-125 calling `my()` :91-110 once per pair, everything serial: decode,
+    `.cuda()`, forward, `.cpu()`, PNG write) as a batched pinned-memory pipeline:
+
+      loader threads   decode + standardise + fit (`load_pair`, `fit_to_crop`) the NEXT pairs while the device works
+      slot ring        `depth` pinned host input buffers [6, crop_h, crop_w] and pinned output buffers [crop_h, crop_w];
+                       H2D of pair i+1 on a copy stream overlaps the kernels of pair i, D2H is asynchronous too
+      writer thread    waits for a slot's D2H event, crops the prediction back and writes the KITTI 16-bit PNG
+
+    Results are identical to `predict_files` pair by pair (same functions, same order of operations).  With a CPU model
+    (tests) the same code runs without pinned memory and streams."""
+
+    def __init__(self, model, crop_height=384, crop_width=1248, depth=3, workers=2):
+        self.model = model
+        self.ch, self.cw, self.depth, self.workers = crop_height, crop_width, max(2, depth), max(1, workers)
+        try:
+            self.dev = next(model.parameters()).device
+        except (StopIteration, AttributeError):
+            self.dev = torch.device("cpu")
+        self.cuda = self.dev.type == "cuda"
+        mk = (lambda *s: torch.empty(s, dtype=torch.float32).pin_memory()) if self.cuda else \
+            (lambda *s: torch.empty(s, dtype=torch.float32))
+        self.in_host = [mk(6, crop_height, crop_width) for _ in range(self.depth)]
+        self.out_host = [mk(crop_height, crop_width) for _ in range(self.depth)]
+        self.in_dev = [torch.empty((6, crop_height, crop_width), dtype=torch.float32, device=self.dev)
+                       for _ in range(self.depth)] if self.cuda else self.in_host
+        if self.cuda:
+            self.copy_stream = torch.cuda.Stream(device=self.dev)
+            self.compute_stream = torch.cuda.Stream(device=self.dev)
+            self.h2d = [torch.cuda.Event() for _ in range(self.depth)]
+            self.done = [torch.cuda.Event() for _ in range(self.depth)]
+            self.free = [torch.cuda.Event() for _ in range(self.depth)]
+
+    def _load(self, left, right):
+        pair = load_pair(left, right)
+        _, h, w = pair.shape
+        if h <= self.ch and w <= self.cw:
+            fitted = np.zeros((6, self.ch, self.cw), np.float32)
+            fitted[:, self.ch - h:, :w] = pair
+        else:
+            start_y = int((h - self.ch) / 2)
+            fitted = np.ascontiguousarray(pair[:, start_y:start_y + self.ch, :self.cw], dtype=np.float32)
+        return fitted, h, w
+
+    def _forward(self, slot):
+        x = self.in_dev[slot]
+        out = self.model(x[None, 0:3], x[None, 3:6])
+        pred = out[0] if isinstance(out, (tuple, list)) else out
+        return pred.reshape(self.ch, self.cw).float()
+
+    def run(self, triples):
+        """triples: iterable of (leftname, rightname, savename or None).  Returns the list of cropped disparity maps
+        (float32 numpy [h, w]) in input order; PNGs are written by the writer thread as results arrive."""
+        import queue
+        import threading
+        from concurrent.futures import ThreadPoolExecutor
+        triples = list(triples)
+        results = [None] * len(triples)
+        slot_sem = threading.Semaphore(self.depth)          # a slot is reusable once the writer has consumed its output
+        q = queue.Queue()
+        err = []
+
+        def writer():
+            while True:
+                item = q.get()
+                if item is None:
+                    return
+                i, slot, h, w, savename = item
+                try:
+                    if self.cuda:
+                        self.done[slot].synchronize()
+                    disp = crop_prediction(self.out_host[slot].numpy(), h, w, self.ch, self.cw).copy()
+                    if savename is not None:
+                        save_disparity_png(savename, disp)
+                    results[i] = disp
+                except Exception as e:          # surfaced by run()
+                    err.append(e)
+                finally:
+                    slot_sem.release()
+
+        wt = threading.Thread(target=writer, daemon=True)
+        wt.start()
+        was_training = getattr(self.model, "training", False)
+        if hasattr(self.model, "eval"):
+            self.model.eval()
+        try:
+            with ThreadPoolExecutor(self.workers) as pool, torch.no_grad():
+                futs = [pool.submit(self._load, l, r) for l, r, _ in triples]
+                for i, (fut, (_, _, savename)) in enumerate(zip(futs, triples)):
+                    fitted, h, w = fut.result()
+                    slot_sem.acquire()
+                    slot = i % self.depth
+                    np.copyto(self.in_host[slot].numpy(), fitted)
+                    if self.cuda:
+                        with torch.cuda.stream(self.copy_stream):
+                            if i >= self.depth:
+                                self.copy_stream.wait_event(self.free[slot])     # kernels of the slot's previous pair
+                            self.in_dev[slot].copy_(self.in_host[slot], non_blocking=True)
+                            self.h2d[slot].record(self.copy_stream)
+                        with torch.cuda.stream(self.compute_stream):
+                            self.compute_stream.wait_event(self.h2d[slot])
+                            pred = self._forward(slot)
+                            self.free[slot].record(self.compute_stream)
+                            self.out_host[slot].copy_(pred, non_blocking=True)
+                            self.done[slot].record(self.compute_stream)
+                    else:
+                        self.out_host[slot].copy_(self._forward(slot))
+                    q.put((i, slot, h, w, savename))
+        finally:
+            q.put(None)
+            wt.join()
+            if was_training and hasattr(self.model, "train"):
+                self.model.train()
+        if err:
+            raise err[0]
+        return results

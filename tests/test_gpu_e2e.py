@@ -183,3 +183,23 @@ def test_graphed_forward_is_bit_identical_to_the_launch_sequence():
         net.invalidate()
         g3 = net.hot_path_graphed(*fb)
         assert net._graphed.replays == 1 and all(torch.equal(x, y) for x, y in zip(eb, g3))
+
+
+def test_image_pipeline_on_the_device_equals_predict_files(tmp_path):
+    """kitti_io.ImagePipeline (pinned slot ring, copy / compute streams, writer thread) with the real model: the same
+    disparities and PNGs as the serial `predict_files` (my_img.py:91-110), more pairs than slots, padded and exact sizes."""
+    import dcanet_b200 as d
+    import workloads
+    from PIL import Image
+    net = workloads.init_bench_weights_(d.GwcNet(48), 0).cuda().eval()
+    rng = np.random.default_rng(0)
+    triples, ref = [], []
+    for i, (h, w) in enumerate([(64, 128), (50, 100), (64, 128), (60, 128), (64, 90)]):
+        for side in "lr":
+            Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)).save(tmp_path / f"{side}{i}.png")
+        triples.append((str(tmp_path / f"l{i}.png"), str(tmp_path / f"r{i}.png"), str(tmp_path / f"p{i}.png")))
+        ref.append(d.kitti_io.predict_files(net, triples[-1][0], triples[-1][1], str(tmp_path / f"q{i}.png"), 64, 128))
+    got = d.kitti_io.ImagePipeline(net, 64, 128, depth=2, workers=2).run(triples)
+    for i, (g, r) in enumerate(zip(got, ref)):
+        assert g.shape == r.shape and np.array_equal(g, r), i
+        assert np.array_equal(np.asarray(Image.open(tmp_path / f"p{i}.png")), np.asarray(Image.open(tmp_path / f"q{i}.png")))

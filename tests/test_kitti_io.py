@@ -94,3 +94,45 @@ def test_against_the_references_own_load_and_transform():
         assert [h, w] == z[f"{tag}:hw"].tolist()
         np.testing.assert_array_equal(left.numpy(), z[f"{tag}:left"])
         np.testing.assert_array_equal(right.numpy(), z[f"{tag}:right"])
+
+
+class _FakeStereo(torch.nn.Module):
+    """A stand-in model with GwcNet's call signature and return shapes: 'disparity' = a fixed function of both images."""
+
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.tensor([0.5, 1.5, 2.5]))
+
+    def forward(self, left, right, disp_true=None):
+        d = (left * self.w.view(1, 3, 1, 1)).sum(1, keepdim=True).abs() + right.mean(1, keepdim=True).abs()
+        return d, d[:, :, ::8, ::8]
+
+
+def test_image_pipeline_equals_the_serial_driver(tmp_path):
+    """ImagePipeline (loader threads + slot ring + writer thread) = predict_files pair by pair, PNG bytes included; more
+    pairs than slots, mixed sizes (padded, exact, cropped)."""
+    sizes = [(37, 53), (48, 64), (60, 70), (20, 64), (48, 30), (37, 53), (52, 80)]
+    triples, ref = [], []
+    model = _FakeStereo()
+    for i, (h, w) in enumerate(sizes):
+        Image.fromarray(_rgb(10 + i, h, w)).save(tmp_path / f"l{i}.png")
+        Image.fromarray(_rgb(50 + i, h, w)).save(tmp_path / f"r{i}.png")
+        triples.append((str(tmp_path / f"l{i}.png"), str(tmp_path / f"r{i}.png"), str(tmp_path / f"p{i}.png")))
+        ref.append(io.predict_files(model, triples[-1][0], triples[-1][1], str(tmp_path / f"q{i}.png"), 48, 64))
+    pipe = io.ImagePipeline(model, crop_height=48, crop_width=64, depth=2, workers=3)
+    got = pipe.run(triples)
+    assert len(got) == len(sizes)
+    for i, (g, r) in enumerate(zip(got, ref)):
+        assert g.shape == r.shape and np.array_equal(g, r), i
+        assert np.array_equal(np.asarray(Image.open(tmp_path / f"p{i}.png")), np.asarray(Image.open(tmp_path / f"q{i}.png")))
+    again = pipe.run(triples[:3])                       # the ring is reusable
+    assert all(np.array_equal(a, b) for a, b in zip(again, ref[:3]))
+
+
+def test_image_pipeline_surfaces_loader_errors(tmp_path):
+    import pytest
+    Image.fromarray(_rgb(1, 20, 30)).save(tmp_path / "l.png")
+    Image.fromarray(_rgb(2, 21, 30)).save(tmp_path / "r.png")          # sizes differ -> load_pair raises
+    pipe = io.ImagePipeline(_FakeStereo(), 32, 32)
+    with pytest.raises(ValueError):
+        pipe.run([(str(tmp_path / "l.png"), str(tmp_path / "r.png"), None)])
