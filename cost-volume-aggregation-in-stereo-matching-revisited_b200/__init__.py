@@ -1,5 +1,5 @@
 """B200-native DCANet cost-volume hot path (feature maps -> disparity) behind the reference's module API."""
-from . import _lib, engine, frontend, hshard, kitti_io, pipeline
+from . import _lib, engine, frontend, gwcnet, hshard, kitti_io, pipeline
 from . import gwcnet_dca0_g, gwcnet_dca1_g, gwcnet_dca2_g, gwcnet_dca4_g
 from .cva import Multi_Aggregation, cva
 from .gwcnet_dca_g import GwcNet, feature_extraction, hourglass

@@ -1766,12 +1766,7 @@ static int launch_tc_march(const TcMaps& maps, const TcParams& p, cudaStream_t s
   using Cfg = MarchCfg<CIN, PLANES>;
   static_assert(Cfg::A_SLOTS >= 2 && Cfg::W_SLOTS >= 1, "smem plan");
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "smem plan");
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
+  g_num_sms = dca_num_sms();
   cudaFuncSetAttribute(conv_tc_march_kernel<CIN, PLANES, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   const int total = p.B * p.Dt * p.tiles_h * p.tiles_w;
   const int grid = total < g_num_sms ? total : g_num_sms;
@@ -1851,12 +1846,7 @@ template <int CIN, int COUT, int PLANES>
 static int launch_tc(const TcMaps& maps, const TcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<CIN, COUT, PLANES>;
   static_assert(Cfg::STAGES >= 2, "pipeline too shallow");
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
+  g_num_sms = dca_num_sms();
   cudaFuncSetAttribute(conv_tc_kernel<CIN, COUT, PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        Cfg::SMEM_BYTES);
   const int total = p.B * p.Dt * p.tiles_h * p.tiles_w * p.ncls;
@@ -1873,12 +1863,7 @@ template <int PLANES>
 static int launch_tc_s2slab(const TcMaps& maps, const TcParams& p, cudaStream_t st) {
   using Cfg = S2Cfg<PLANES>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "smem plan");
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
+  g_num_sms = dca_num_sms();
   cudaFuncSetAttribute(conv_tc_s2slab_kernel<PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   const int total = p.B * p.Dt * p.tiles_h * p.tiles_w;
   const int grid = total < g_num_sms ? total : g_num_sms;
@@ -1895,12 +1880,7 @@ static int launch_tc_halo(const TcMaps& maps, const TcParams& p, cudaStream_t st
   using Cfg = HaloCfg<CIN, COUT, PLANES>;
   static_assert(Cfg::A_SLOTS >= 2 && Cfg::W_SLOTS >= 1, "smem plan");
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "smem plan");
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
+  g_num_sms = dca_num_sms();
   cudaFuncSetAttribute(conv_tc_halo_kernel<CIN, COUT, PLANES, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        Cfg::SMEM_BYTES);
   const int total = p.B * p.Dt * p.tiles_h * p.tiles_w;
@@ -1936,12 +1916,7 @@ template <int CIN, int PLANES, int NSLAB, int NSIDE = 2>
 static int launch_up2(const TcMaps& maps, const TcParams& p, const Up2Params& u, cudaStream_t st) {
   using Cfg = Up2Cfg<CIN, PLANES, NSLAB, NSIDE>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "smem plan");
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
+  g_num_sms = dca_num_sms();
   cudaFuncSetAttribute(conv_tc_up2_kernel<CIN, PLANES, NSLAB, NSIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   const int total = p.B * p.Dt * p.tiles_h * p.tiles_w;
   const int grid = total < g_num_sms ? total : g_num_sms;
@@ -2062,12 +2037,7 @@ static int launch_deconv_pair(const TcMaps& maps, const TcParams& p, const Up2Pa
   static_assert(Cfg::W_SLOTS >= 3, "weight ring too shallow");
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "smem plan");
   static_assert(Cfg::TMEM_COLS <= 512 && (Cfg::TMEM_COLS & (Cfg::TMEM_COLS - 1)) == 0, "TMEM plan");
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
+  g_num_sms = dca_num_sms();
   cudaFuncSetAttribute(conv_tc_deconv_pair_kernel<PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   const int total = p.B * p.Dt * p.tiles_h * p.tiles_w;
   const int grid = total < g_num_sms ? total : g_num_sms;
@@ -2685,12 +2655,7 @@ extern "C" int dca_avgpool3d(const void* x, void* y, int planes, int B, int C, i
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return dca_avgpool3d_simple(x, y, planes, B, C, Di, Hi, Wi, stream);     // (tensors smaller than one box)
   }
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
+  g_num_sms = dca_num_sms();
   const int tiles_w = (Wo + AP_TW - 1) / AP_TW, tiles_h = (Ho + AP_TH - 1) / AP_TH;
   const long long cols = (long long)B * tiles_w * tiles_h;
   int nsplit = (int)(((long long)g_pool_ctas_per_sm * g_num_sms + cols - 1) / cols);   // CTAs per SM so that loads and sums overlap

@@ -34,6 +34,19 @@ extern "C" int dca_pdl_enabled(void);
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// SM count of the CURRENT device (cached per device ordinal; grids of the persistent kernels are sized from it)
+static inline int dca_num_sms() {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cache[dev]) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev] = n > 0 ? n : 148;
+  }
+  return cache[dev];
+}
+
 template <typename... Exp, typename... Act>
 static inline cudaError_t dca_launch(void (*kern)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                      Act&&... args) {

@@ -1069,7 +1069,8 @@ static int launch_planes_to_nchw(const void* x, int planes, float* y, int B, int
     planes_to_nchw_tiled_kernel<<<grid, 256, smem, st>>>((const __nv_bfloat16*)x, planes, y, B, C, Cp, V, ybs);
   } else {
     const size_t nb = (total + 255) / 256;
-    planes_to_ncdhw_kernel<<<(unsigned)(nb < 148 * 16 ? (nb ? nb : 1) : 148 * 16), 256, 0, st>>>((const __nv_bfloat16*)x, planes, y, B, C, Cp, V, ybs);
+    const size_t cap = (size_t)dca_num_sms() * 16;
+    planes_to_ncdhw_kernel<<<(unsigned)(nb < cap ? (nb ? nb : 1) : cap), 256, 0, st>>>((const __nv_bfloat16*)x, planes, y, B, C, Cp, V, ybs);
   }
   return 0;
 }
@@ -1210,7 +1211,7 @@ tap_gather_softmax_regress_kernel(const float* __restrict__ P, float* __restrict
 
 static inline int grid_for(size_t total, int threads) {
   size_t g = (total + threads - 1) / threads;
-  const size_t cap = 148 * 32;
+  const size_t cap = (size_t)dca_num_sms() * 32;
   return (int)(g < cap ? (g ? g : 1) : cap);
 }
 
@@ -1271,7 +1272,7 @@ static int attention_launch(const void* x, const int* cls, const float* e, const
   const size_t smem = wbytes + warps * per_warp;
   const int HW = H * W;
   int grid = (B * HW + warps - 1) / warps;
-  if (grid > 148) grid = 148;            // persistent: one CTA per SM pays the weight-staging prologue once
+  if (grid > dca_num_sms()) grid = dca_num_sms();            // persistent: one CTA per SM pays the weight-staging prologue once
   cudaStream_t st = (cudaStream_t)stream;
 #define DCA_AT_LAUNCH2(P_, MT_, DT_, WPP_, CORE_)                                                                      \
   do {                                                                                                           \
@@ -1319,7 +1320,8 @@ extern "C" int dca_upsample_fuse(const void* t, const void* cost, const float* W
   if (!t || !cost || !WcT || !scale || !shift || !y || planes < 1 || planes > 2 || B <= 0) return DCA_ERR_ARG;
   if (C != AT_C) return DCA_ERR_UNSUPPORTED;
   const long long nblocks = (long long)B * (Dl + 1) * (Hl + 1) * (Wl + 1);
-  int grid = (int)((nblocks + 7) / 8 < 148 * 12 ? (nblocks + 7) / 8 : 148 * 12);
+  const size_t gcap = (size_t)dca_num_sms() * 12;
+  int grid = (int)((nblocks + 7) / 8 < gcap ? (nblocks + 7) / 8 : gcap);
   cudaStream_t st = (cudaStream_t)stream;
   if (planes == 2)
     upsample_fuse_kernel<2><<<grid, 256, 0, st>>>((const __nv_bfloat16*)t, (const __nv_bfloat16*)cost, WcT, scale,
@@ -1434,6 +1436,37 @@ extern "C" int dca_fold_bn(const float* gamma, const float* beta, const float* m
   if (!gamma || !beta || !mean || !var || !scale || !shift || C <= 0 || Cpad < C) return DCA_ERR_ARG;
   fold_bn_kernel<<<(Cpad + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, mean, var, eps, scale, shift, C,
                                                                        Cpad);
+  DCA_RETURN_IF_LAUNCH_FAILED();
+  return DCA_OK;
+}
+
+// F.adaptive_avg_pool3d of the rows [h0, H) of an fp32 [B][D][H][W] tensor to [B][Do][Ho][Wo] (torch's windows:
+// [floor(i*In/Out), ceil((i+1)*In/Out)) per axis) -- the visualisation head of the plain-GwcNet baseline,
+// models/gwcnet.py:186-190.  thread = output element.
+__global__ void __launch_bounds__(256)
+adaptive_avgpool3d_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int D, int H, int W, int h0, int Do,
+                          int Ho, int Wo) {
+  const size_t total = (size_t)B * Do * Ho * Wo;
+  const int Hi = H - h0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ow = (int)(i % Wo), oh = (int)((i / Wo) % Ho), od = (int)((i / ((size_t)Wo * Ho)) % Do);
+    const int b = (int)(i / ((size_t)Wo * Ho * Do));
+    const int d0 = (int)(((long long)od * D) / Do), d1 = (int)(((long long)(od + 1) * D + Do - 1) / Do);
+    const int a0 = (int)(((long long)oh * Hi) / Ho), a1 = (int)(((long long)(oh + 1) * Hi + Ho - 1) / Ho);
+    const int w0 = (int)(((long long)ow * W) / Wo), w1 = (int)(((long long)(ow + 1) * W + Wo - 1) / Wo);
+    float s = 0.f;
+    for (int d = d0; d < d1; ++d)
+      for (int h = a0; h < a1; ++h)
+        for (int w = w0; w < w1; ++w) s += x[(((size_t)b * D + d) * H + h0 + h) * W + w];
+    y[i] = s / (float)((d1 - d0) * (a1 - a0) * (w1 - w0));
+  }
+}
+
+extern "C" int dca_adaptive_avgpool3d_rows(const float* x, float* y, int B, int D, int H, int W, int h0, int Do, int Ho,
+                                           int Wo, void* stream) {
+  if (!x || !y || B <= 0 || D <= 0 || H <= 0 || W <= 0 || h0 < 0 || h0 >= H || Do <= 0 || Ho <= 0 || Wo <= 0) return DCA_ERR_ARG;
+  const size_t total = (size_t)B * Do * Ho * Wo;
+  adaptive_avgpool3d_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, B, D, H, W, h0, Do, Ho, Wo);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }

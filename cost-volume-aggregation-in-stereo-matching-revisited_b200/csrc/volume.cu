@@ -476,12 +476,7 @@ static int launch_volume3(const float* gl, const float* gr, const float* cl, con
   static_assert(G % 2 == 0 && G / 2 + CC <= 32 && CV >= G + 2 * CC && CV <= 64 && Cfg::SMEM_BYTES <= 227 * 1024 &&
                 Cfg::R_BYTES % 128 == 0 && Cfg::L_BYTES % 128 == 0 && Cfg::CR_BYTES % 128 == 0 && Cfg::CL_BYTES % 128 == 0,
                 "shape");
-  if (!g_vol_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_vol_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_vol_sms <= 0) g_vol_sms = 148;
-  }
+  g_vol_sms = dca_num_sms();
   VolMaps maps;
   if (!vol_feature_map(&maps.r, gr, B, G, CPG, H, W, V2_UW / 8) || !vol_feature_map(&maps.l, gl, B, G, CPG, H, W, V2_TW / 8) ||
       !vol_concat_map(&maps.cr, cr, B, CC, H, W, V2_UW) || !vol_concat_map(&maps.cl, cl, B, CC, H, W, V2_TW))
@@ -619,7 +614,8 @@ extern "C" int dca_build_concat_volume_f32(const float* l, const float* r, float
                                            void* stream) {
   if (!l || !r || !vol || B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return DCA_ERR_ARG;
   size_t total = (size_t)B * 2 * C * D * H * W;
-  int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  const size_t cap = (size_t)dca_num_sms() * 16;
+  int blocks = (int)((total + 255) / 256 < cap ? (total + 255) / 256 : cap);
   concat_volume_ncdhw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(l, r, vol, B, C, D, H, W);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;

@@ -89,7 +89,12 @@ class hourglass(nn.Module):
         E._require_cuda(x)
         P = self.precision_planes
         pk = E.cached_pack(self, ("hourglass", P), lambda: self._pack(P))
-        xp = E.Planes.from_ncdhw(x, P)
+        return self.forward_planes(E.Planes.from_ncdhw(x, P), pk).to_ncdhw()
+
+    @staticmethod
+    def forward_planes(xp, pk):
+        """The same on cost planes (used by the plain-GwcNet baseline, gwcnet.py, which chains three of these)."""
+        E = engine
         c1 = E.conv(xp, pk["conv1"], E.K3S2, E.ACT_RELU)
         c2 = E.conv(c1, pk["conv2"], E.K3S1, E.ACT_RELU)
         c3 = E.conv(c2, pk["conv3"], E.K3S2, E.ACT_RELU)
@@ -97,8 +102,7 @@ class hourglass(nn.Module):
         r2 = E.conv(c2, pk["redir2"], E.K1, E.ACT_NONE)
         c5 = E.conv(c4, pk["conv5"], E.T3S2, E.ACT_RELU, res_pre=r2)
         r1 = E.conv(xp, pk["redir1"], E.K1, E.ACT_NONE)
-        c6 = E.conv(c5, pk["conv6"], E.T3S2, E.ACT_RELU, res_pre=r1)
-        return c6.to_ncdhw()
+        return E.conv(c5, pk["conv6"], E.T3S2, E.ACT_RELU, res_pre=r1)
 
 
 class GwcNet(nn.Module):

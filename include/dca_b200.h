@@ -232,6 +232,11 @@ int dca_pool_conv(const void* x, void* pooled, const void* w_tc, const float* sc
 int dca_softmax_regress_upsample(const float* logits, const float* mask, float* pred_q, float* out, int B, int D, int H,
                                  int W, void* stream);
 
+/* F.adaptive_avg_pool3d(x[:, :, h0:, :], (Do, Ho, Wo)) of an fp32 [B][D][H][W] tensor: the `vis_tsne1` head of the
+ * plain-GwcNet baseline (models/gwcnet.py:186-190). */
+int dca_adaptive_avgpool3d_rows(const float* x, float* y, int B, int D, int H, int W, int h0, int Do, int Ho, int Wo,
+                                void* stream);
+
 /* layout + parameter preparation ---------------------------------------------------------------- */
 int dca_planes_from_ncdhw(const float* x, void* y, int planes, int B, int C, int Cp, int D, int H, int W,
                           void* stream);

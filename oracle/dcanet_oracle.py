@@ -293,6 +293,78 @@ def hot_path(sd, gwc_l, gwc_r, cat_l, cat_r, g, maxdisp, num_groups=40, operand_
 
 
 # --------------------------------------------------------------------------------------------
+# the plain-GwcNet baseline models/gwcnet.py
+# --------------------------------------------------------------------------------------------
+def hourglass_forward(ctx: _Ctx, prefix, x):
+    """Full hourglass, gwcnet.py:67-103: two stride-2 stages down, two transposed convs up, 1x1x1 shortcuts."""
+    c1 = ctx.convbn3d(x, prefix + ".conv1.0", 2, 1, "relu")
+    c2 = ctx.convbn3d(c1, prefix + ".conv2.0", 1, 1, "relu")
+    c3 = ctx.convbn3d(c2, prefix + ".conv3.0", 2, 1, "relu")
+    c4 = ctx.convbn3d(c3, prefix + ".conv4.0", 1, 1, "relu")
+    c5 = F.relu(ctx.bn(ctx.deconv3d(c4, prefix + ".conv5.0.weight"), prefix + ".conv5.1")
+                + ctx.convbn3d(c2, prefix + ".redir2", 1, 0))
+    return F.relu(ctx.bn(ctx.deconv3d(c5, prefix + ".conv6.0.weight"), prefix + ".conv6.1")
+                  + ctx.convbn3d(x, prefix + ".redir1", 1, 0))
+
+
+def baseline_hot_path(sd, gwc_l, gwc_r, cat_l, cat_r, maxdisp, num_groups=40, calibrate=False, collect=None,
+                      vis_size=(24, 67, 120)):
+    """models/gwcnet.py GwcNet.forward in eval mode, from the feature maps on (gwcnet.py:199-216, 236-244): volume ->
+    dres0 -> dres1 (+) -> dres2 -> dres3 -> vis_tsne1: classif2 logits, rows from 2 on, adaptive average pooling to the
+    hard-coded (48//2, 134//2, 240//2) grid (gwcnet.py:186-190).  (dres4 / classif3 are computed by the reference's
+    eval branch too, but nothing reads them.)  -> [B, 24, 67, 120]."""
+    ctx = _Ctx(sd, None, calibrate)
+    D4 = maxdisp // 4
+    vol = build_gwc_volume(gwc_l, gwc_r, D4, num_groups)
+    if cat_l is not None:
+        vol = torch.cat([vol, build_concat_volume(cat_l, cat_r, D4)], dim=1)
+    c = ctx.convbn3d(vol, "dres0.0", 1, 1, "relu")
+    c = ctx.convbn3d(c, "dres0.2", 1, 1, "relu")
+    r = ctx.convbn3d(c, "dres1.0", 1, 1, "relu")
+    cost0 = ctx.convbn3d(r, "dres1.2", 1, 1, None) + c
+    out1 = hourglass_forward(ctx, "dres2", cost0)
+    out2 = hourglass_forward(ctx, "dres3", out1)
+    h = ctx.convbn3d(out2, "classif2.0", 1, 1, "relu")
+    logits = ctx.conv3d(h, "classif2.2.weight", 1, 1)
+    vis = F.adaptive_avg_pool3d(logits[:, :, :, 2:, :], vis_size).squeeze(1)
+    if collect is not None:
+        collect.update(volume=vol, cost0=cost0, out1=out1, out2=out2, classif2_logits=logits.squeeze(1))
+    return vis
+
+
+def synth_state_dict_from_keys(keyfile, seed, skip=("feature_extraction.", "guidance.")):
+    """Seeded weights for every key of a `key shape` listing (tests/golden/state_dict_keys_*.txt) outside the front end:
+    conv weights ~ N(0, 2/fan_in) (ConvTranspose3d [Cin,Cout,k,k,k]: fan_in = Cin*27/8), BN weight ~ U(.75, 1.25), bias ~
+    N(0, .1), running statistics 0 / 1 (to be calibrated).  Lets a fixture store the calibrated BN statistics only."""
+    import ast
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for line in open(keyfile):
+        k, shp = line.strip().split(" ", 1)
+        if k.startswith(tuple(skip)):
+            continue
+        shape = ast.literal_eval(shp)
+        if k.endswith("num_batches_tracked"):
+            sd[k] = torch.zeros((), dtype=torch.long)
+        elif k.endswith("running_mean"):
+            sd[k] = torch.zeros(shape)
+        elif k.endswith("running_var"):
+            sd[k] = torch.ones(shape)
+        elif len(shape) == 1 and k.endswith(".weight"):
+            sd[k] = torch.rand(shape, generator=g) * 0.5 + 0.75
+        elif len(shape) == 1:
+            sd[k] = torch.randn(shape, generator=g) * 0.1
+        else:
+            taps = 1
+            for d in shape[2:]:
+                taps *= d
+            transposed = ".conv5.0." in k or ".conv6.0." in k or ".conv3.0.weight" in k and len(shape) == 5 and shape[0] > shape[1]
+            fan_in = shape[0] * taps / 8.0 if transposed else shape[1] * taps
+            sd[k] = torch.randn(shape, generator=g) * (2.0 / fan_in) ** 0.5
+    return sd
+
+
+# --------------------------------------------------------------------------------------------
 # synthetic, calibrated hot-path checkpoint (SURVEY section 8c) -- reference-independent
 # --------------------------------------------------------------------------------------------
 def hot_path_param_shapes(num_groups=40, concat_channels=12, num_cva=3):
