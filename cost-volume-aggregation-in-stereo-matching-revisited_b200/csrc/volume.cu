@@ -251,12 +251,18 @@ struct Vol3Cfg {
   static constexpr int SMEM_BYTES = 2 * BUF_BYTES + 128 + 1024;      // + barriers/counters + alignment slack
 };
 
-template <int PLANES, int G, int CPG, int CC, int CV>
+// KS (1, 2 or 4) lanes share one group pair, each summing CPG / KS of its channels (xor-butterfly at the end).  8 groups
+// (40 channels each) run with KS = 4: 4 x 4 + 12 = 28 busy lanes instead of 16, 328 -> 191 us at KITTI size.  20 groups
+// stay at KS = 1 (measured: KS = 2 is 8 % SLOWER, 152 vs 141 us -- the kernel is bound by its 32-bit store instructions,
+// one 2 x CV-byte row per warp instruction, not by the lanes' FMA work).
+template <int PLANES, int G, int CPG, int CC, int CV, int KS = 1>
 __global__ void __launch_bounds__(V3_THREADS, 1)
 volume_fused3_kernel(const __grid_constant__ VolMaps maps, __nv_bfloat16* __restrict__ vol, int B, int D, int H, int W,
                      int dbg) {
   using Cfg = Vol3Cfg<G, CPG, CC>;
   constexpr int HG = Cfg::HG, LW4 = Cfg::LW4, UW4 = Cfg::UW4, LW8 = Cfg::LW8, UW8 = Cfg::UW8;
+  constexpr int HGK = HG * KS, CPK = CPG / KS;      // lanes doing correlation work, channels per such lane
+  static_assert((KS == 1 || KS == 2 || KS == 4) && CPG % KS == 0 && HGK + CC <= 32, "lane plan");
   static_assert(G % 4 == 0, "a 128-byte smem row holds 4 slots: the swap bit is ((slot >> 2) + octet * G / 4) & 1");
   extern __shared__ __align__(1024) uint8_t smem_v3[];
   uint8_t* base = smem_v3;                 // (kept a shared-space pointer: no generic loads in the inner loop)
@@ -301,7 +307,9 @@ volume_fused3_kernel(const __grid_constant__ VolMaps maps, __nv_bfloat16* __rest
   }
   __syncthreads();
 
-  const float lane_scale = lane < HG ? 1.0f / (float)CPG : 1.0f;
+  const float lane_scale = lane < HGK ? 1.0f / (float)CPG : 1.0f;
+  const int gl = lane < HGK ? lane / KS : lane - HGK + HG;     // "virtual lane": owner of output channels (2 gl, 2 gl + 1)
+  const int ks = lane < HGK ? lane % KS : 0;
   const size_t plane_stride = (size_t)B * D * H * W * CV;
   for (int s = warp; s < my_items * V3_SLOTS; s += V3_WARPS) {
     const int k = s / V3_SLOTS, t = s - k * V3_SLOTS;
@@ -322,7 +330,7 @@ volume_fused3_kernel(const __grid_constant__ VolMaps maps, __nv_bfloat16* __rest
       // window index of (w0+wt+i, d0+dt+j) = wt + i - dt - j + 48 = ub + (i - j + 8),  ub = wt - dt + 40 (multiple of 4)
       const int ub = wt - dt + V2_DC - 8;
       float acc[2][8][4];
-      if (lane < HG) {
+      if (lane < HGK) {
 #pragma unroll
         for (int q = 0; q < 2; ++q)
 #pragma unroll
@@ -338,7 +346,7 @@ volume_fused3_kernel(const __grid_constant__ VolMaps maps, __nv_bfloat16* __rest
         for (int q = 0; q < 2; ++q) {
           // SWIZZLE_32B swaps the two float4 of a unit in odd 128-byte rows; row = unit / 4 = (octet * G + slot) / 4, so
           // with G % 8 == 0 the bit is a per-lane constant and with G % 8 == 4 (20 groups) it flips with the octet
-          const int slot = lane + q * HG, sw = (slot >> 2) & 1;
+          const int slot = gl + q * HG, sw = (slot >> 2) & 1;
           constexpr int OSW = (G >> 2) & 1;
           lo_[q] = (uint32_t)((((wq >> 1) * G + slot) << 5) + (((wq & 1) ^ sw ^ (OSW & (wq >> 1))) << 4));
 #pragma unroll
@@ -347,7 +355,8 @@ volume_fused3_kernel(const __grid_constant__ VolMaps maps, __nv_bfloat16* __rest
                                     ((((ub4 + kk) & 1) ^ sw ^ (OSW & ((ub4 + kk) >> 1))) << 4));
         }
 #pragma unroll
-        for (int c = 0; c < CPG; ++c) {
+        for (int cc_ = 0; cc_ < CPK; ++cc_) {
+          const int c = ks * CPK + cc_;
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             const float4 l4 = *reinterpret_cast<const float4*>(Lb + c * (LW8 * G * 32) + lo_[q]);
@@ -362,11 +371,25 @@ volume_fused3_kernel(const __grid_constant__ VolMaps maps, __nv_bfloat16* __rest
               for (int i = 0; i < 4; ++i) acc[q][j][i] = fmaf(l[i], r[i - j + 8], acc[q][j][i]);
           }
         }
+        if (KS > 1) {                                   // sum the KS partial channel sums of a group pair
+          constexpr unsigned m = HGK == 32 ? 0xffffffffu : ((1u << HGK) - 1u);
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float v = acc[q][j][i];
+                v += __shfl_xor_sync(m, v, 1);
+                if (KS == 4) v += __shfl_xor_sync(m, v, 2);
+                acc[q][j][i] = v;
+              }
+        }
       } else {
         // concat lanes, same product form: left copy = cl[w] * [w - d >= 0], right copy = 1 * cr[w - d]
-        const bool left = lane < HG + CC / 2;
-        const int cc = 2 * (lane - HG - (left ? 0 : CC / 2));
-        const bool live = lane < HG + CC;
+        const bool left = lane < HGK + CC / 2;
+        const int cc = 2 * (lane - HGK - (left ? 0 : CC / 2));
+        const bool live = lane < HGK + CC;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           float l[4] = {1.f, 1.f, 1.f, 1.f}, r[12];
@@ -388,8 +411,12 @@ volume_fused3_kernel(const __grid_constant__ VolMaps maps, __nv_bfloat16* __rest
             for (int i = 0; i < 4; ++i) acc[q][j][i] = l[i] * r[i - j + 8];
         }
       }
-      if (2 * lane < CV) {
-        __nv_bfloat16* rowp = vol + ((((size_t)b * D + d0 + dt) * H + h) * W + (w0 + wt)) * CV + 2 * lane;
+      if (2 * gl < CV && ks == 0) {
+        __nv_bfloat16* rowp = vol + ((((size_t)b * D + d0 + dt) * H + h) * W + (w0 + wt)) * CV + 2 * gl;
+        // the 32 lanes own 2 * NVL channels; zero-pad channels beyond that (KS > 1 uses lanes up) fall to the last lane
+        constexpr int NVL = 32 - HGK + HG;
+        constexpr int NPAD = CV > 2 * NVL ? (CV - 2 * NVL) / 2 : 0;
+        const bool pads = NPAD > 0 && gl == NVL - 1;
         const size_t dstep = HW * CV;
         const int nj = min(8, dcount - dt);
 #pragma unroll
@@ -401,6 +428,13 @@ volume_fused3_kernel(const __grid_constant__ VolMaps maps, __nv_bfloat16* __rest
               vol_split2b(acc[0][j][i] * lane_scale, acc[1][j][i] * lane_scale, hw, lw);
               *reinterpret_cast<uint32_t*>(rowp + i * CV) = hw;
               if (PLANES == 2) *reinterpret_cast<uint32_t*>(rowp + plane_stride + i * CV) = lw;
+              if (pads) {
+#pragma unroll
+                for (int z = 1; z <= NPAD; ++z) {
+                  *reinterpret_cast<uint32_t*>(rowp + i * CV + 2 * z) = 0u;
+                  if (PLANES == 2) *reinterpret_cast<uint32_t*>(rowp + plane_stride + i * CV + 2 * z) = 0u;
+                }
+              }
             }
           }
           rowp += dstep;
@@ -469,11 +503,11 @@ static bool vol_concat_map(CUtensorMap* m, const float* p, int B, int CC, int H,
 
 static int g_vol_sms = 0;
 static int g_volume_v2 = 1;   // bit0: use the TMA-staged kernel; bits 1..2: timing probes (skip compute / skip staging)
-template <int G, int CPG, int CC, int CV>
+template <int G, int CPG, int CC, int CV, int KS = 1>
 static int launch_volume3(const float* gl, const float* gr, const float* cl, const float* cr, void* vol, int B, int D,
                           int H, int W, int planes, cudaStream_t st) {
   using Cfg = Vol3Cfg<G, CPG, CC>;
-  static_assert(G % 2 == 0 && G / 2 + CC <= 32 && CV >= G + 2 * CC && CV <= 64 && Cfg::SMEM_BYTES <= 227 * 1024 &&
+  static_assert(G % 2 == 0 && (G / 2) * KS + CC <= 32 && CV >= G + 2 * CC && CV <= 64 && Cfg::SMEM_BYTES <= 227 * 1024 &&
                 Cfg::R_BYTES % 128 == 0 && Cfg::L_BYTES % 128 == 0 && Cfg::CR_BYTES % 128 == 0 && Cfg::CL_BYTES % 128 == 0,
                 "shape");
   g_vol_sms = dca_num_sms();
@@ -486,11 +520,11 @@ static int launch_volume3(const float* gl, const float* gr, const float* cl, con
   if (items * V3_SLOTS >= (1ll << 31)) return DCA_ERR_UNSUPPORTED;
   const int grid = (int)(items < g_vol_sms ? items : g_vol_sms);
   if (planes == 2) {
-    auto kern = volume_fused3_kernel<2, G, CPG, CC, CV>;
+    auto kern = volume_fused3_kernel<2, G, CPG, CC, CV, KS>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     dca_launch(kern, grid, V3_THREADS, Cfg::SMEM_BYTES, st, maps, (__nv_bfloat16*)vol, B, D, H, W, g_volume_v2 >> 1);
   } else {
-    auto kern = volume_fused3_kernel<1, G, CPG, CC, CV>;
+    auto kern = volume_fused3_kernel<1, G, CPG, CC, CV, KS>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     dca_launch(kern, grid, V3_THREADS, Cfg::SMEM_BYTES, st, maps, (__nv_bfloat16*)vol, B, D, H, W, g_volume_v2 >> 1);
   }
@@ -567,10 +601,12 @@ extern "C" int dca_volume_gwc_concat(const float* gwc_l, const float* gwc_r, con
   if (C % G != 0 || (Cc > 0 && (!cat_l || !cat_r)) || Cc < 0) return DCA_ERR_ARG;
   if (Cv < G + 2 * Cc || Cv > 64 || (Cv % 8) != 0 || (planes != 1 && planes != 2)) return DCA_ERR_ARG;
   const int cpg = C / G, gp = G + 1, UW = VOL_TW + VOL_DC - 1;
-  if ((W % 8) == 0 && Cc == 12 && C == 320 && (g_volume_v2 & 1)) {      // DCANet's shape and the 20-group point of config 4's sweep (8 groups x 40 channels does not fit two buffers)
+  if ((W % 8) == 0 && Cc == 12 && C == 320 && (g_volume_v2 & 1)) {      // DCANet's shape (40 groups) and the 20- and 8-group points of config 4's sweep
     if (G == 40 && Cv == 64) return launch_volume3<40, 8, 12, 64>(gwc_l, gwc_r, cat_l, cat_r, vol, B, D, H, W, planes, (cudaStream_t)stream);
     if (G == 20 && Cv == 64) return launch_volume3<20, 16, 12, 64>(gwc_l, gwc_r, cat_l, cat_r, vol, B, D, H, W, planes, (cudaStream_t)stream);
     if (G == 20 && Cv == 48) return launch_volume3<20, 16, 12, 48>(gwc_l, gwc_r, cat_l, cat_r, vol, B, D, H, W, planes, (cudaStream_t)stream);
+    if (G == 8 && Cv == 32) return launch_volume3<8, 40, 12, 32, 4>(gwc_l, gwc_r, cat_l, cat_r, vol, B, D, H, W, planes, (cudaStream_t)stream);
+    if (G == 8 && Cv == 64) return launch_volume3<8, 40, 12, 64, 4>(gwc_l, gwc_r, cat_l, cat_r, vol, B, D, H, W, planes, (cudaStream_t)stream);
   }
   size_t smem = ((size_t)cpg * (VOL_TW + UW) * gp + (size_t)Cc * (VOL_TW + UW)) * sizeof(float);
   if (smem > 220 * 1024) return DCA_ERR_UNSUPPORTED;

@@ -36,7 +36,9 @@ def rnd(*shape, seed=0):
     (2, 320, 40, 12, 3, 40, 52, 2), (1, 320, 40, 12, 2, 72, 48, 1), (1, 320, 8, 12, 2, 36, 24, 2),
     (1, 320, 20, 12, 2, 28, 96, 2),
     # 20 groups on the TMA-staged kernel (W % 8 == 0; Cv = 48: the swap bit of SWIZZLE_32B flips with the column octet)
-    (1, 320, 20, 12, 2, 40, 52, 2), (2, 320, 20, 12, 3, 72, 24, 1), (1, 320, 20, 12, 2, 64, 100, 2)])
+    (1, 320, 20, 12, 2, 40, 52, 2), (2, 320, 20, 12, 3, 72, 24, 1), (1, 320, 20, 12, 2, 64, 100, 2),
+    # 8 groups x 40 channels on the TMA-staged kernel (four lanes per group pair)
+    (1, 320, 8, 12, 2, 40, 52, 2), (2, 320, 8, 12, 3, 72, 24, 1), (1, 320, 8, 12, 2, 64, 100, 2)])
 def test_fused_volume(B, C, G, Cc, H, W, D, planes):
     d, E, O = _mods()
     L, R = rnd(B, C, H, W, seed=1), rnd(B, C, H, W, seed=2)
@@ -51,6 +53,24 @@ def test_fused_volume(B, C, G, Cc, H, W, D, planes):
     close(got[:, :G + 2 * Cc], ref, 2e-5 if planes == 2 else 5e-3, "volume")
     if vol.C > G + 2 * Cc:
         assert float(got[:, G + 2 * Cc:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("G", [8, 20])
+def test_fused_volume_wide_zero_pad(G):
+    """8 / 20 groups written into 64-channel plane rows (the tcgen05 convs take 32 or 64 input channels): the lanes left over
+    by the lane-split group pairs do not cover the pad, the last lane writes it."""
+    d, E, O = _mods()
+    B, C, Cc, H, W, D = 1, 320, 12, 3, 48, 20
+    L, R = rnd(B, C, H, W, seed=5), rnd(B, C, H, W, seed=6)
+    cl, cr = rnd(B, Cc, H, W, seed=7), rnd(B, Cc, H, W, seed=8)
+    ref = torch.cat([O.build_gwc_volume(L, R, D, G), O.build_concat_volume(cl, cr, D)], 1)
+    dev = [t.cuda() for t in (L, R, cl, cr)]
+    vol = E.Planes(B, D, H, W, 64, 2, "cuda")
+    vol.t.fill_(float("nan"))                       # every element, pad included, must be written
+    d._lib.call("dca_volume_gwc_concat", *[t.data_ptr() for t in dev], vol.ptr, B, C, G, Cc, D, H, W, 64, 2, E._stream())
+    got = vol.to_ncdhw()
+    close(got[:, :G + 2 * Cc], ref, 2e-5, "volume")
+    assert float(got[:, G + 2 * Cc:].abs().max()) == 0.0
 
 
 def test_volume_api_matches_reference_golden():
