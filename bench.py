@@ -442,7 +442,7 @@ def main():
                         net.feature_extraction(torch.cat((ld, r.to(dev, non_blocking=True)), 0))
                         net.guidance(ld)
 
-            img_rec = {"h2d_bytes_per_step": 2 * B * 3 * H * W * 4, "d2h_bytes_per_step": d2h,
+            img_rec = {"h2d_bytes_per_step": 2 * B * 3 * H * W * 4, "d2h_bytes_per_step": d2h, "n_gpus": world,
                        "what": "GwcNet(left, right): pinned host images -> H2D -> feature_extraction (left+right as one batch) "
                                "+ Guidance -> hot path -> D2H of pred4 + prob_volume2.  kernel_front_end: every stride-1 conv of the "
                                "front end on dca_conv2d_tc* (frontend.py), the five strided convs on cuDNN; torch_front_end: "
@@ -458,7 +458,7 @@ def main():
                     b__.record()
                     barrier()
                     ms_ = a_.elapsed_time(b__) / K
-                    img_rec.setdefault(tag, {})[key] = (B / (ms_ * 1e-3)) if key == "pairs_per_s" else ms_
+                    img_rec.setdefault(tag, {})[key] = (world * B / (ms_ * 1e-3)) if key == "pairs_per_s" else ms_
             d.frontend.Options.enabled = True
 
         # ---------------- latency distribution (20 warm-up + 200 timed), extra key only ----------

@@ -26,7 +26,7 @@ class feature_extraction(nn.Module):
             self.lastconv = nn.Sequential(convbn(320, 128, 3, 1, 1, 1), nn.ReLU(inplace=True),
                                           nn.Conv2d(128, concat_feature_channel, kernel_size=1, padding=0, stride=1,
                                                     bias=False))
-        self.precision_planes = 2
+        self.frontend_planes = 2        # the front end always runs hi+lo planes (GwcNet.set_precision governs the hot path only)
 
     def _make_layer(self, block, planes, blocks, stride, pad, dilation):
         downsample = None
@@ -43,7 +43,7 @@ class feature_extraction(nn.Module):
         from . import frontend
         if frontend.use_kernels(self, x) and x.shape[2] % 8 == 0 and x.shape[3] % 8 == 0:
             # CUDA + eval: the 1/4-resolution layers (layer2[1:], layer3, layer4, lastconv) on the tcgen05 2-D conv kernel
-            return frontend.feature_extraction_forward(self, x, self.precision_planes)
+            return frontend.feature_extraction_forward(self, x, self.frontend_planes)
         x = self.layer1(self.firstconv(x))
         l2 = self.layer2(x)
         l3 = self.layer3(l2)

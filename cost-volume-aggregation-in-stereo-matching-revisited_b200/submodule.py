@@ -177,7 +177,7 @@ class Guidance(nn.Module):
         self.conv_g0 = nn.Sequential(BasicConv(64, 64, kernel_size=3, padding=1),
                                      BasicConv(64, 64, kernel_size=3, padding=1))
         self.guidance = nn.Conv2d(64, output_dim, kernel_size=(3, 3), stride=(1, 1), padding=(1, 1), bias=False)
-        self.precision_planes = 2
+        self.frontend_planes = 2
 
     def _make_layer(self, dim, stride=1):
         layers = (ResidualBlock(self.in_planes, dim, self.norm_fn, stride=stride),
@@ -189,7 +189,7 @@ class Guidance(nn.Module):
         from . import frontend
         if frontend.use_kernels(self, x) and self.norm_fn == "batch":
             # CUDA + eval: layer2[1], conv_g0 and the output conv (all 64 -> 64 at 1/4 res) on the tcgen05 2-D conv kernel
-            return frontend.guidance_forward(self, x, self.precision_planes)
+            return frontend.guidance_forward(self, x, self.frontend_planes)
         x = self.layer2(self.layer1(self.conv_start(x)))
         return {"g": self.guidance(self.conv_g0(x))}
 
