@@ -444,9 +444,9 @@ def main():
 
             img_rec = {"h2d_bytes_per_step": 2 * B * 3 * H * W * 4, "d2h_bytes_per_step": d2h, "n_gpus": world,
                        "what": "GwcNet(left, right): pinned host images -> H2D -> feature_extraction (left+right as one batch) "
-                               "+ Guidance -> hot path -> D2H of pred4 + prob_volume2.  kernel_front_end: every stride-1 conv of the "
-                               "front end on dca_conv2d_tc* (frontend.py), the five strided convs on cuDNN; torch_front_end: "
-                               "the same modules entirely on cuDNN; both in true fp32 (TF32 off)"}
+                               "+ Guidance -> hot path -> D2H of pred4 + prob_volume2.  kernel_front_end: every conv of the front end "
+                               "on this repo's kernels (frontend.py); torch_front_end: the same modules on cuDNN in true "
+                               "fp32 (TF32 off)"}
             for tag, on in (("kernel_front_end", True), ("torch_front_end", False)):
                 d.frontend.Options.enabled = on
                 for fn, key in ((img_steps, "pairs_per_s"), (fe_steps, "front_end_ms")):

@@ -37,6 +37,7 @@ SIGNATURES = {
     "dca_tap_gather3d": [_vp, _vp] + [_c_int] * 4 + [_vp],
     "dca_conv2d_tc": [_vp, _c_int, _vp, _vp, _vp, _vp, _c_int, _c_int] + [_c_int] * 5 + [_vp],
     "dca_conv2d_tc_ex": [_vp, _c_int, _vp, _vp, _vp, _vp, _c_int, _vp, _c_int, _c_int] + [_c_int] * 6 + [_vp],
+    "dca_conv2d_stem": [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int] + [_c_int] * 4 + [_vp],
     "dca_conv2d_tc_cat": [_vp, _c_int, _vp, _c_int, _vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _c_int, _c_int]
                          + [_c_int] * 4 + [_vp],
     "dca_planes_to_nchw_slice": [_vp, _c_int, _vp] + [_c_int] * 5 + [_ll, _vp],

@@ -1209,6 +1209,66 @@ tap_gather_softmax_regress_kernel(const float* __restrict__ P, float* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The two 3-channel stems of the front end: Conv2d(3 -> 32, K x K, stride 2, pad K/2) (+ bias) + BN + ReLU --
+// feature_extraction.firstconv[0] (3x3, gwcnet_dca_g.py:19) and Guidance.conv_start (7x7, submodule.py:413-414).
+// Too few input channels for the tensor-core family and only 0.2 / 0.6 GMAC: thread = output pixel with all 32 output
+// channels in registers, weights transposed to [tap][ci][co] in shared memory (every lane reads the same address:
+// broadcast float4 loads), fp32 NCHW image in, cost planes [P][B][1][Ho][Wo][32] out (no layout pass in between).
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(128)
+conv2d_stem_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
+                   const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, int planes, int B, int H, int W, int Ho,
+                   int Wo, int act) {
+  __shared__ __align__(16) float sw[K * K * 3 * 32];
+  __shared__ float ssc[32], ssh[32];
+  for (int i = threadIdx.x; i < K * K * 3 * 32; i += blockDim.x) {
+    const int co = i & 31, t = i >> 5, ci = t % 3, kk = t / 3;
+    sw[i] = w[(co * 3 + ci) * K * K + kk];
+  }
+  if (threadIdx.x < 32) {
+    ssc[threadIdx.x] = scale ? scale[threadIdx.x] : 1.f;
+    ssh[threadIdx.x] = shift ? shift[threadIdx.x] : 0.f;
+  }
+  __syncthreads();
+  const size_t npix = (size_t)B * Ho * Wo;
+  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((size_t)Wo * Ho));
+  float acc[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+  const float* xb = x + (size_t)b * 3 * H * W;
+  for (int kh = 0; kh < K; ++kh) {
+    const int iy = 2 * oy + kh - K / 2;
+    if (iy < 0 || iy >= H) continue;
+    for (int kw = 0; kw < K; ++kw) {
+      const int ix = 2 * ox + kw - K / 2;
+      if (ix < 0 || ix >= W) continue;
+      const float* wp = sw + (kh * K + kw) * 3 * 32;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float v = __ldg(xb + ((size_t)ci * H + iy) * W + ix);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 ww = *reinterpret_cast<const float4*>(wp + ci * 32 + 4 * c4);
+          acc[4 * c4 + 0] = fmaf(v, ww.x, acc[4 * c4 + 0]); acc[4 * c4 + 1] = fmaf(v, ww.y, acc[4 * c4 + 1]);
+          acc[4 * c4 + 2] = fmaf(v, ww.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(v, ww.w, acc[4 * c4 + 3]);
+        }
+      }
+    }
+  }
+  const size_t plane = npix * 32;
+#pragma unroll
+  for (int c8 = 0; c8 < 4; ++c8) {
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = apply_act(fmaf(acc[8 * c8 + k], ssc[8 * c8 + k], ssh[8 * c8 + k]), act);
+    store8_rt(y, plane, planes, pix * 32 + 8 * c8, o);
+  }
+}
+
 static inline int grid_for(size_t total, int threads) {
   size_t g = (total + threads - 1) / threads;
   const size_t cap = (size_t)dca_num_sms() * 32;
@@ -1436,6 +1496,22 @@ extern "C" int dca_fold_bn(const float* gamma, const float* beta, const float* m
   if (!gamma || !beta || !mean || !var || !scale || !shift || C <= 0 || Cpad < C) return DCA_ERR_ARG;
   fold_bn_kernel<<<(Cpad + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, mean, var, eps, scale, shift, C,
                                                                        Cpad);
+  DCA_RETURN_IF_LAUNCH_FAILED();
+  return DCA_OK;
+}
+
+extern "C" int dca_conv2d_stem(const float* x, const float* w, const float* scale, const float* shift, void* y, int planes,
+                               int act, int B, int H, int W, int K, void* stream) {
+  if (!x || !w || !y || planes < 1 || planes > 2 || B <= 0 || H <= 0 || W <= 0) return DCA_ERR_ARG;
+  if (K != 3 && K != 7) return DCA_ERR_UNSUPPORTED;
+  const int Ho = (H + 2 * (K / 2) - K) / 2 + 1, Wo = (W + 2 * (K / 2) - K) / 2 + 1;
+  const size_t npix = (size_t)B * Ho * Wo;
+  const unsigned grid = (unsigned)((npix + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (K == 3)
+    conv2d_stem_kernel<3><<<grid, 128, 0, st>>>(x, w, scale, shift, (__nv_bfloat16*)y, planes, B, H, W, Ho, Wo, act);
+  else
+    conv2d_stem_kernel<7><<<grid, 128, 0, st>>>(x, w, scale, shift, (__nv_bfloat16*)y, planes, B, H, W, Ho, Wo, act);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }

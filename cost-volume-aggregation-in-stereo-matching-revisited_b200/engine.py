@@ -263,6 +263,66 @@ def conv2d_tc(x: Planes, pc: PackedConv2dTc, act=ACT_NONE, out_fp32=False, out=N
     return y
 
 
+class PackedStem:
+    """Conv2d(3 -> 32, K x K, stride 2) (+ bias) + eval-mode BN for dca_conv2d_stem: fp32 weights in torch layout, BN and bias
+    folded to scale/shift."""
+
+    def __init__(self, conv, bn):
+        w = conv.weight.detach().contiguous().float()
+        if w.shape[0] != 32 or w.shape[1] != 3 or w.shape[2] not in (3, 7) or conv.stride != (2, 2):
+            raise _lib.DcaError("dca_conv2d_stem: Conv2d(3 -> 32, 3x3 or 7x7, stride 2) only")
+        self.w, self.k = w, int(w.shape[2])
+        dev = w.device
+        self.scale = torch.ones(32, dtype=torch.float32, device=dev)
+        self.shift = torch.zeros(32, dtype=torch.float32, device=dev)
+        if bn is not None:
+            g, b = bn.weight.detach().float().contiguous(), bn.bias.detach().float().contiguous()
+            m, v = bn.running_mean.detach().float().contiguous(), bn.running_var.detach().float().contiguous()
+            _lib.call("dca_fold_bn", g.data_ptr(), b.data_ptr(), m.data_ptr(), v.data_ptr(), float(bn.eps),
+                      self.scale.data_ptr(), self.shift.data_ptr(), 32, 32, _stream())
+        if conv.bias is not None:
+            self.shift += self.scale * conv.bias.detach().float()
+        torch.cuda.current_stream().synchronize()
+
+
+def conv2d_stem(x, ps: PackedStem, planes, act=ACT_RELU):
+    """fp32 NCHW image [B,3,H,W] -> cost planes [P][B][1][H/2][W/2][32]."""
+    _require_cuda(x)
+    x = x.contiguous().float()
+    B, C, H, W = x.shape
+    assert C == 3
+    k = ps.k
+    y = Planes(B, 1, (H + 2 * (k // 2) - k) // 2 + 1, (W + 2 * (k // 2) - k) // 2 + 1, 32, planes, x.device)
+    _lib.call("dca_conv2d_stem", x.data_ptr(), ps.w.data_ptr(), ps.scale.data_ptr(), ps.shift.data_ptr(), y.ptr, planes, act,
+              B, H, W, k, _stream())
+    return y
+
+
+def pack_conv2d_s2(conv, bn, planes):
+    """A stride-2 Conv2d(32 -> 64) (3x3 pad 1, or 1x1) as the middle depth slice of a 3x3x3 stride-2 Conv3d on a depth-1
+    volume: the w-pair slab kernel of Multi_Aggregation.conv1 (K3S2) then IS the 2-D conv (its two outer depth taps read
+    the zero padding).  Bias folded into the BN shift."""
+    w = conv.weight.detach().float()
+    co, ci, k = w.shape[0], w.shape[1], w.shape[2]
+    w3 = torch.zeros((co, ci, 3, 3, 3), dtype=torch.float32, device=w.device)
+    if k == 3:
+        w3[:, :, 1] = w
+    elif k == 1:
+        w3[:, :, 1, 1, 1] = w[:, :, 0, 0]
+    else:
+        raise _lib.DcaError("pack_conv2d_s2: 3x3 or 1x1 kernels")
+    pc = PackedConv(w3, bn)
+    if conv.bias is not None:
+        if pc.scale is None:
+            pc.scale = torch.ones(pc.cout_pad, dtype=torch.float32, device=w.device)
+            pc.shift = torch.zeros(pc.cout_pad, dtype=torch.float32, device=w.device)
+        pc.shift[:co] += pc.scale[:co] * conv.bias.detach().float()
+    if not pc.pack_tc(planes) or not tc_supported(K3S2, ci, co):
+        raise _lib.DcaError("pack_conv2d_s2: the stride-2 tensor-core kernel takes 32 -> 64 channels")
+    torch.cuda.current_stream().synchronize()
+    return pc
+
+
 def conv2d_tc_cat(xs, pc: PackedConv2dTc, act=ACT_NONE):
     """conv3x3 over the channel concatenation of up to three plane tensors, without materialising it."""
     x0 = xs[0]

@@ -17,10 +17,13 @@ BN (eval) and conv biases are folded into the epilogue's fp32 scale/shift; resid
 submodule.py:272; `relu(x + y)`, ResidualBlock :347) are epilogue terms; the channel concat is never materialised in
 the plane layout (the 320-channel conv reads its five 64-channel slabs through three tensor maps) and is written once,
 as fp32 NCHW, for the volume kernel.  The 32-channel stride-1 layers of the 1/2-resolution stem (firstconv[2], firstconv[4],
-feature_extraction.layer1, Guidance.layer1) run on the same kernel with a 32-channel tile.  What stays on torch/cuDNN (true
-fp32, TF32 switched off) are the five strided convs: the 3-channel stems (3x3 s2, 7x7 s2) and the two stride-2 blocks.
+feature_extraction.layer1, Guidance.layer1) run on the same kernel with a 32-channel tile; the stride-2 convs of the two
+down-sampling blocks (3x3 32 -> 64 and the 1x1 shortcut) run on the 3-D stride-2 slab kernel at depth 1
+(`engine.pack_conv2d_s2`); the two 3-channel stems (3x3 s2, 7x7 s2) on a small CUDA-core kernel (`dca_conv2d_stem`) that
+reads the image and writes planes.  With CUDA inputs in eval mode no layer of the front end runs on torch / cuDNN.
 
-torch here: device memory, the stem modules, and load-time parameter folding.  No arithmetic of the layers listed above.
+torch here: device memory and load-time parameter folding.  (CPU inputs, training mode, odd sizes and
+`Options.enabled = False` take the plain torch modules, in true fp32.)
 """
 import torch
 
@@ -81,9 +84,45 @@ def _planes_to_nchw(p, channels=None):
     return out
 
 
+class _BlockS2:
+    """The stride-2 BasicBlock feature_extraction.layer2[0] (32 -> 64; 1x1 stride-2 downsample on the shortcut): both strided
+    convs on the 3-D stride-2 slab kernel at depth 1 (engine.pack_conv2d_s2), conv2 + the add on the 2-D kernel."""
+
+    def __init__(self, blk, planes):
+        c1, b1 = _conv_bn(blk.conv1[0])
+        c2, b2 = _conv_bn(blk.conv2)
+        self.c1 = E.pack_conv2d_s2(c1, b1, planes)
+        self.ds = E.pack_conv2d_s2(blk.downsample[0], blk.downsample[1], planes)
+        self.c2 = E.PackedConv2dTc(c2.weight, b2, planes)
+
+    def __call__(self, x):
+        h = E.conv(x, self.c1, E.K3S2, E.ACT_RELU)
+        r = E.conv(x, self.ds, E.K3S2, E.ACT_NONE)
+        return E.conv2d_tc(h, self.c2, E.ACT_NONE, res=r)
+
+
+class _ResBlockS2:
+    """The stride-2 ResidualBlock Guidance.layer2[0] (submodule.py:305-347): relu(norm3(down(x)) + relu(bn2(conv2(relu(bn1(conv1 x))))))."""
+
+    def __init__(self, rb, planes):
+        for n in (rb.norm1, rb.norm2, rb.norm3):
+            if not isinstance(n, torch.nn.BatchNorm2d):
+                raise _lib.DcaError("Guidance on the tcgen05 kernels needs norm_fn='batch'")
+        self.c1 = E.pack_conv2d_s2(rb.conv1, rb.norm1, planes)
+        self.ds = E.pack_conv2d_s2(rb.downsample[0], rb.norm3, planes)
+        self.c2 = E.PackedConv2dTc(rb.conv2.weight, rb.norm2, planes, bias=rb.conv2.bias)
+
+    def __call__(self, x):
+        y = E.conv(x, self.c1, E.K3S2, E.ACT_RELU)
+        r = E.conv(x, self.ds, E.K3S2, E.ACT_NONE)
+        return E.conv2d_tc(y, self.c2, E.ACT_RELU, res=r, act_post=E.ACT_RELU)
+
+
 class PackedFeatureExtraction:
     def __init__(self, fe, planes):
         self.planes = planes
+        self.stem = E.PackedStem(fe.firstconv[0][0], fe.firstconv[0][1])       # 3 -> 32, 3x3 stride 2 (+BN+ReLU)
+        self.down = _BlockS2(fe.layer2[0], planes)
         # 1/2-resolution stem: firstconv's two 32 -> 32 convs and layer1 (3 BasicBlocks) on the 32-channel tile
         self.first = [E.PackedConv2dTc(fe.firstconv[i][0].weight, fe.firstconv[i][1], planes) for i in (2, 4)]
         self.layer1 = [_Block(b, planes) for b in fe.layer1]
@@ -113,16 +152,12 @@ class _no_tf32:
 def feature_extraction_forward(fe, x, planes=2):
     """feature_extraction.forward (gwcnet_dca_g.py:53-66) for a CUDA batch in eval mode."""
     pk = E.cached_pack(fe, ("frontend", planes), lambda: PackedFeatureExtraction(fe, planes))
-    with _no_tf32():
-        s = fe.firstconv[1](fe.firstconv[0](x))               # 3 -> 32, stride 2 (+BN+ReLU): cuDNN, true fp32
-    p = E.Planes.from_ncdhw(s, planes=planes)
+    p = E.conv2d_stem(x, pk.stem, planes, E.ACT_RELU)         # image -> 32-channel planes at 1/2 resolution
     for pc in pk.first:
         p = E.conv2d_tc(p, pc, E.ACT_RELU)
     for blk in pk.layer1:
         p = blk(p)
-    with _no_tf32():
-        s = fe.layer2[0](_planes_to_nchw(p))                  # the stride-2 block (32 -> 64, 1x1 s2 downsample): cuDNN
-    p = E.Planes.from_ncdhw(s, planes=planes)
+    p = pk.down(p)                                            # the stride-2 block: 64 channels at 1/4 resolution
     for blk in pk.layer2:
         p = blk(p)
     l2 = p
@@ -148,7 +183,11 @@ def feature_extraction_forward(fe, x, planes=2):
 
 class PackedGuidance:
     def __init__(self, g, planes):
+        if not isinstance(g.conv_start[1], torch.nn.BatchNorm2d):
+            raise _lib.DcaError("Guidance on the tcgen05 kernels needs norm_fn='batch'")
+        self.stem = E.PackedStem(g.conv_start[0], g.conv_start[1])        # 3 -> 32, 7x7 stride 2 (+bias+BN+ReLU)
         self.layer1 = [_ResBlock(rb, planes) for rb in g.layer1]          # 32 channels at 1/2 resolution
+        self.down = _ResBlockS2(g.layer2[0], planes)
         self.rb = _ResBlock(g.layer2[1], planes)
         self.g0 = E.PackedConv2dTc(g.conv_g0[0].conv.weight, g.conv_g0[0].bn, planes)
         self.g1 = E.PackedConv2dTc(g.conv_g0[1].conv.weight, g.conv_g0[1].bn, planes)
@@ -159,14 +198,10 @@ class PackedGuidance:
 def guidance_forward(g, x, planes=2):
     """Guidance.forward (submodule.py:452-460) for a CUDA batch in eval mode -> {'g': [B,64,H/4,W/4]}."""
     pk = E.cached_pack(g, ("frontend", planes), lambda: PackedGuidance(g, planes))
-    with _no_tf32():
-        s = g.conv_start(x)                                   # 7x7 stride-2 stem (+BN+ReLU): cuDNN, true fp32
-    p = E.Planes.from_ncdhw(s, planes=planes)
+    p = E.conv2d_stem(x, pk.stem, planes, E.ACT_RELU)
     for rb in pk.layer1:
         p = rb(p)
-    with _no_tf32():
-        s = g.layer2[0](_planes_to_nchw(p))                   # the stride-2 ResidualBlock: cuDNN
-    p = pk.rb(E.Planes.from_ncdhw(s, planes=planes))
+    p = pk.rb(pk.down(p))
     p = E.conv2d_tc(p, pk.g0, E.ACT_RELU)
     p = E.conv2d_tc(p, pk.g1, E.ACT_RELU)
     p = E.conv2d_tc(p, pk.out, E.ACT_NONE)

@@ -131,6 +131,11 @@ long long dca_pack_weights_tc2d_bytes(int Co, int Ci, int planes);
 int dca_conv2d_tc_ex(const void* x, int planes, const void* w_tc2d, const float* scale, const float* shift,
                      const void* res, int act_post, void* y, int out_f32, int act, int B, int Cin, int Cout, int H, int W,
                      int dil, void* stream);
+/* The two 3-channel stems of the front end: Conv2d(3 -> 32, K x K, stride 2, pad K/2) (+ bias) + BN + act, K in {3, 7}
+ * (feature_extraction.firstconv[0] gwcnet_dca_g.py:19; Guidance.conv_start submodule.py:413-414).  x fp32 NCHW [B,3,H,W],
+ * w fp32 [32][3][K][K] (torch layout), scale/shift = folded BN (+ bias); y cost planes [planes][B][1][Ho][Wo][32]. */
+int dca_conv2d_stem(const float* x, const float* w, const float* scale, const float* shift, void* y, int planes, int act,
+                    int B, int H, int W, int K, void* stream);
 /* The same conv over the channel concatenation cat(x0, x1, x2) (each a multiple of 64 channels, <= 320 in total; unused
  * sources NULL) without materialising it: feature_extraction.lastconv on cat(l2, l3, l4) (gwcnet_dca_g.py:60-65). */
 int dca_conv2d_tc_cat(const void* x0, int C0, const void* x1, int C1, const void* x2, int C2, int planes,

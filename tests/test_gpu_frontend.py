@@ -1,5 +1,5 @@
-"""The 1/4-resolution part of the 2-D front end on the tcgen05 2-D conv kernel (frontend.py) against the
-same torch modules on cuDNN in true fp32 (TF32 off) and against torch on the CPU (op level)."""
+"""The 2-D front end (feature_extraction, Guidance) on this repo's kernels (frontend.py) against the same
+torch modules on cuDNN in true fp32 (TF32 off), against an fp64 run, and against torch on the CPU (op level)."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -82,6 +82,45 @@ def test_conv2d_tc_cat_and_1x1_match_torch():
     assert float(out[:, :5].abs().max()) == 0.0 and float(out[:, 17:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("K,bias,H,W", [(3, False, 36, 52), (7, True, 40, 64), (7, True, 33, 47), (3, False, 31, 45)])
+def test_conv2d_stem_matches_torch(K, bias, H, W):
+    """Conv2d(3 -> 32, K x K, stride 2, pad K/2) (+bias) + BN + ReLU: firstconv[0] (3x3) and Guidance.conv_start (7x7)."""
+    d, E = _mods()
+    g = torch.Generator().manual_seed(K)
+    conv = torch.nn.Conv2d(3, 32, K, 2, K // 2, bias=bias)
+    conv.weight.data.normal_(0, (2.0 / (3 * K * K)) ** 0.5, generator=g)
+    bn = torch.nn.BatchNorm2d(32).eval()
+    bn.weight.data.uniform_(0.8, 1.2, generator=g); bn.bias.data.normal_(0, 0.1, generator=g)
+    bn.running_mean.normal_(0, 0.1, generator=g); bn.running_var.uniform_(0.5, 1.5, generator=g)
+    x = torch.randn(2, 3, H, W, generator=g)
+    with torch.no_grad():
+        ref = torch.relu(bn(conv(x)))
+    y = E.conv2d_stem(x.cuda(), E.PackedStem(conv.cuda(), bn.cuda()), 2, E.ACT_RELU)
+    got = _planes_to_nchw(E, y).cpu()
+    assert got.shape == ref.shape
+    assert float((got - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("k,bias,H,W", [(3, False, 24, 40), (1, False, 24, 40), (3, True, 18, 36), (1, True, 30, 28)])
+def test_stride2_conv2d_on_the_3d_slab_kernel_matches_torch(k, bias, H, W):
+    """Conv2d(32 -> 64, 3x3 pad 1 or 1x1, stride 2) + BN as the middle depth slice of a K3S2 Conv3d on a depth-1 volume."""
+    d, E = _mods()
+    g = torch.Generator().manual_seed(10 + k)
+    conv = torch.nn.Conv2d(32, 64, k, 2, k // 2, bias=bias)
+    conv.weight.data.normal_(0, (2.0 / (32 * k * k)) ** 0.5, generator=g)
+    bn = torch.nn.BatchNorm2d(64).eval()
+    bn.weight.data.uniform_(0.8, 1.2, generator=g); bn.bias.data.normal_(0, 0.1, generator=g)
+    bn.running_mean.normal_(0, 0.1, generator=g); bn.running_var.uniform_(0.5, 1.5, generator=g)
+    x = torch.randn(2, 32, H, W, generator=g)
+    with torch.no_grad():
+        ref = torch.relu(bn(conv(x)))
+    pc = E.pack_conv2d_s2(conv.cuda(), bn.cuda(), 2)
+    y = E.conv(E.Planes.from_ncdhw(x.cuda(), 2), pc, E.K3S2, E.ACT_RELU)
+    got = _planes_to_nchw(E, y).cpu()
+    assert got.shape == ref.shape
+    assert float((got - ref).abs().max()) <= 3e-5 * max(1.0, float(ref.abs().max()))
+
+
 def _net(maxdisp=48, seed=0):
     import dcanet_b200 as d
     import workloads
@@ -118,8 +157,13 @@ def test_front_end_kernels_match_the_torch_modules(B, H, W):
         finally:
             d.frontend.Options.enabled = True
         n0 = d._lib.LAUNCHES
-        got = net.feature_extraction(left)
-        gotg = net.guidance(left)["g"]
+        real = torch.nn.Conv2d.forward
+        try:                                      # CUDA + eval: NO layer of the front end may run on torch / cuDNN
+            torch.nn.Conv2d.forward = lambda self, x: (_ for _ in ()).throw(AssertionError("a torch Conv2d ran"))
+            got = net.feature_extraction(left)
+            gotg = net.guidance(left)["g"]
+        finally:
+            torch.nn.Conv2d.forward = real
     assert d._lib.LAUNCHES - n0 > 60, "the kernel path did not run"
     for name, a, b in (("gwc_feature", got["gwc_feature"], ref["gwc_feature"]),
                        ("concat_feature", got["concat_feature"], ref["concat_feature"]), ("g", gotg, refg)):
