@@ -549,6 +549,29 @@ def main():
                     "note": ("parity precision issues 3 16-bit (kind::f16, same rate as bf16) MMAs per algorithmic MAC (hi*Whi, hi*Wlo, lo*Whi); "
                              "`achieved` counts algorithmic FLOPs only") if issued > 1 else "",
                     "ncu": tr}
+            # the same kernel with single-plane operands (precision="fast": ONE MMA per MAC), to separate the tensor-core
+            # efficiency of the kernel from the 3x MMA cost of the parity format
+            try:
+                x1 = E.Planes(B, maxdisp // 4, H4, W4, 32, 1, dev)
+                x1.t.normal_()
+                pc1 = E.pack_convbn(net.dres0[2])
+                pc1.pack_tc(1)
+                for _ in range(3):
+                    E.conv(x1, pc1, E.K3S1, E.ACT_RELU)
+                torch.cuda.synchronize()
+                a.record()
+                for _ in range(n_it):
+                    E.conv(x1, pc1, E.K3S1, E.ACT_RELU)
+                b_.record()
+                torch.cuda.synchronize()
+                f_ms = a.elapsed_time(b_) / n_it
+                extra["roofline_fast_mode"] = {"kernel": "conv_tc_march_kernel<32,1> (single fp16 plane, one MMA per MAC)",
+                                               "bound": "tensor", "achieved": fl / (f_ms * 1e-3) / 1e12, "peak": tf_sust,
+                                               "unit": "TFLOP/s", "frac": fl / (f_ms * 1e-3) / 1e12 / tf_sust,
+                                               "ms_per_launch": f_ms, "note": "not the parity configuration; context only"}
+                del x1, pc1
+            except Exception as e:          # context record only
+                extra["roofline_fast_mode"] = {"error": str(e)}
             # volume kernel (HBM bound)
             fs = dev_sets[0]
             for _ in range(3):
