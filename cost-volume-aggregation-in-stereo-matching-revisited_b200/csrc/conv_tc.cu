@@ -60,6 +60,8 @@ struct TcParams {
   const __nv_bfloat16* up; int planes_up;   // optional half-resolution tensor added (trilinear x2) before BN
   int nslab; int slab_c0[5]; int slab_dz[5];   // halo kernel: slabs per tile (3 depth slabs, or up to 5 64-channel slabs in 2-D)
   int slab_map[5];                 // ... and the input view (TcMaps::a index) each slab is read from (2-D channel concat)
+  int par2d;                       // 2-D dilation-2 conv: the tile-space depth index td in [0, 4) is the (row, column) PARITY of a
+                                   // sub-image: input view maps.a[td], output pixel (2 ty + (td >> 1), 2 tx + (td & 1)), depth 0
   int act_post;                    // activation applied once more AFTER res_post (ResidualBlock: relu(x + relu(bn(conv))))
   int ldc, co_base, cout_valid, out_f32;        // output row pitch / first channel / valid channels / fp32 output
   float inv_tiles_w, inv_tiles_h, inv_Dt, inv_ncls;   // reciprocals for the epilogue's tile decode (fast_divmod)
@@ -315,6 +317,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, int total_tiles, 
     int oz = mn ? td * mn + mj : td * (p.out_stride_d ? p.out_stride_d : p.out_stride) + p.cls_off[cls][0],
         oy = ty * p.out_stride + p.cls_off[cls][1],
         ox = tx * p.out_stride + p.cls_off[cls][2];
+    if (p.par2d) { oz = 0; oy += td >> 1; ox += td & 1; }
     const bool valid = (ty < p.Ht) && (tx < p.Wt) && (oz < p.Do) && (oy < p.Ho) && (ox < p.Wo);
     const size_t vox = (((size_t)b * p.Do + oz) * p.Ho + oy) * p.Wo + ox;
     int bb = b, uD = p.Do, uH = p.Ho, uW = p.Wo;
@@ -831,8 +834,9 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
           mbar_expect_tx(&afull[sa], PLANES * Cfg::SLAB_BYTES);
 #pragma unroll
           for (int pl = 0; pl < PLANES; ++pl)
-            tma_load_5d(a_base + sa * Cfg::A_SLOT + pl * Cfg::SLAB_PITCH, &maps.a[p.slab_map[kd]], &afull[sa], p.slab_c0[kd],
-                        tw * TC_TW - 1, th * TC_TH - 1, td + p.slab_dz[kd], pl * p.B + b);
+            tma_load_5d(a_base + sa * Cfg::A_SLOT + pl * Cfg::SLAB_PITCH, &maps.a[p.slab_map[kd] + (p.par2d ? td : 0)],
+                        &afull[sa], p.slab_c0[kd], tw * TC_TW - 1, th * TC_TH - 1, (p.par2d ? 0 : td) + p.slab_dz[kd],
+                        pl * p.B + b);
           if (++sa == Cfg::A_SLOTS) { sa = 0; pa ^= 1; }
           if (!Cfg::WRES) {
             for (int kh = 0; kh < 3; ++kh) {
@@ -2430,17 +2434,26 @@ static int conv2d_tc_run_t(const void* const* xs, const int* cs, int nsrc, int p
                            int act, int B, int Cin, int Cout, int H, int W, int dil, cudaStream_t st) {
   const int P = planes, nslab = Cin / T, nchunk = (Cout + T - 1) / T;
   const int Hs = H / dil, Ws = W / dil;                       // sub-image extent (dil == 1: the image itself)
-  for (int par = 0; par < dil * dil; ++par) {
-    const int pa = par / dil, pb = par % dil;                 // row / column parity of this sub-image
+  // dilation 2 with ONE source: the four parity sub-images ride the tile-space depth index of a single launch (par2d);
+  // with several sources (never needed so far) they are four launches
+  const bool batched = dil == 2 && nsrc == 1;
+  const int npass = batched ? 1 : dil * dil;
+  for (int pass = 0; pass < npass; ++pass) {
     TcMaps maps;
-    for (int i = 0; i < nsrc; ++i) {
-      const int C = cs[i];
-      const __nv_bfloat16* xb = (const __nv_bfloat16*)xs[i] + ((size_t)pa * W + pb) * C;
-      if (!make_act_map(&maps.a[i], xb, C, Ws, Hs, 1, P * B, (size_t)dil * C, (size_t)dil * W * C, (size_t)H * W * C,
-                        (size_t)H * W * C, HB_W, HB_H, T))
-        return DCA_ERR_LAUNCH;
+    const int npar = batched ? 4 : 1;
+    for (int q = 0; q < npar; ++q) {
+      const int par = batched ? q : pass;
+      const int pa = par / dil, pb = par % dil;               // row / column parity of this sub-image
+      for (int i = 0; i < nsrc; ++i) {
+        const int C = cs[i];
+        const __nv_bfloat16* xb = (const __nv_bfloat16*)xs[i] + ((size_t)pa * W + pb) * C;
+        if (!make_act_map(&maps.a[batched ? q : i], xb, C, Ws, Hs, 1, P * B, (size_t)dil * C, (size_t)dil * W * C,
+                          (size_t)H * W * C, (size_t)H * W * C, HB_W, HB_H, T))
+          return DCA_ERR_LAUNCH;
+      }
     }
-    for (int i = nsrc; i < 9; ++i) maps.a[i] = maps.a[0];
+    for (int i = batched ? 4 : nsrc; i < 9; ++i) maps.a[i] = maps.a[0];
+    const int pa = pass / dil, pb = pass % dil;
     for (int j = 0; j < nchunk; ++j) {
       TcParams p;
       memset(&p, 0, sizeof(p));
@@ -2452,9 +2465,11 @@ static int conv2d_tc_run_t(const void* const* xs, const int* cs, int nsrc, int p
       p.ldc = Cout; p.co_base = j * T; p.cout_valid = Cout; p.out_f32 = out_f32;
       p.nslab = nslab;
       for (int i = 0, sl = 0; i < nsrc; ++i)
-        for (int c0 = 0; c0 < cs[i]; c0 += T, ++sl) { p.slab_map[sl] = i; p.slab_c0[sl] = c0; p.slab_dz[sl] = 0; }
-      p.Dt = 1; p.Ht = Hs; p.Wt = Ws; p.out_stride = dil; p.out_stride_d = 1; p.ntaps = 9 * nslab; p.ncls = 1;
-      p.cls_off[0][0] = 0; p.cls_off[0][1] = (signed char)pa; p.cls_off[0][2] = (signed char)pb;
+        for (int c0 = 0; c0 < cs[i]; c0 += T, ++sl) { p.slab_map[sl] = batched ? 0 : i; p.slab_c0[sl] = c0; p.slab_dz[sl] = 0; }
+      p.par2d = batched ? 1 : 0;
+      p.Dt = batched ? 4 : 1; p.Ht = Hs; p.Wt = Ws; p.out_stride = dil; p.out_stride_d = 1; p.ntaps = 9 * nslab; p.ncls = 1;
+      p.cls_off[0][0] = 0;
+      p.cls_off[0][1] = (signed char)(batched ? 0 : pa); p.cls_off[0][2] = (signed char)(batched ? 0 : pb);
       p.cls_tap0[0] = 0; p.cls_tap0[1] = (unsigned char)(9 * nslab);
       p.tiles_w = (Ws + TC_TW - 1) / TC_TW; p.tiles_h = (Hs + TC_TH - 1) / TC_TH;
       const __nv_bfloat16* wj = (const __nv_bfloat16*)w_tc2d + (size_t)j * nslab * 9 * P * T * T;
