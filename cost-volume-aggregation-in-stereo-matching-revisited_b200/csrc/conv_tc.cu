@@ -2576,6 +2576,26 @@ extern "C" int dca_pack_weights_tc_march(const float* w, int Ci, void* out, int 
 
 // Conv3d k3 s1 p1, Cout = 32, depth-marching kernel (kd folded into N).  Same epilogue contract as dca_conv3d_tc:
 //   y = act(scale * conv(x, w) + shift + res_pre) + res_post ;  w_march from dca_pack_weights_tc_march.
+// Planes per work item of the depth-marching kernel.  An item of n planes costs n + 2 slab steps (one per input plane
+// of its halo'd depth range) and the persistent grid runs ceil(items / SMs) items per CTA, so n trades the halo overhead
+// against the fill of the last wave: KITTI 1/4 res (234 tile columns x 48 planes): n = 8 (1404 items, 10 x 10 steps);
+// 1/8 res (60 columns x 24 planes): n = 6 (240 items, 2 x 8 = 16 steps) instead of n = 8 (180 items, 2 x 10 = 20).
+static int g_march_n = 0;          // > 0: forced (timing experiments)
+extern "C" int dca_tc_set_march_n(int n) { g_march_n = n > 0 ? n : 0; return DCA_OK; }
+static int choose_march_n(int B, int D, int H, int W, int nmax) {
+  if (g_march_n > 0) return g_march_n < nmax ? (g_march_n < D ? g_march_n : D) : (nmax < D ? nmax : D);
+  const long long cols = (long long)B * ((H + TC_TH - 1) / TC_TH) * ((W + TC_TW - 1) / TC_TW);
+  const int sms = dca_num_sms();
+  int best = D < nmax ? D : nmax;
+  long long best_cost = -1;
+  for (int n = (D < nmax ? D : nmax); n >= 2; --n) {
+    const long long items = cols * ((D + n - 1) / n);
+    const long long cost = ((items + sms - 1) / sms) * (n + 2);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = n; }
+  }
+  return best;
+}
+
 extern "C" int dca_conv3d_tc_march(const void* x, int planes, const void* w_march, const float* scale, const float* shift,
                                    const void* res_pre, const void* res_post, int planes_res, void* y, int act, int B,
                                    int Cin, int D, int H, int W, void* stream) {
@@ -2594,7 +2614,7 @@ extern "C" int dca_conv3d_tc_march(const void* x, int planes, const void* w_marc
   p.dbg = g_dbg;
   p.ldc = Cout; p.cout_valid = Cout;
   const int nmax = P == 2 ? 8 : 16;            // planes per work item (TMEM: 512 columns)
-  const int n = D < nmax ? D : nmax;
+  const int n = choose_march_n(B, D, H, W, nmax);
   p.march_n = n;
   p.Dt = (D + n - 1) / n;                      // depth chunks
   p.Ht = H; p.Wt = W; p.out_stride = 1; p.ncls = 1;
@@ -2637,7 +2657,7 @@ extern "C" int dca_conv3d_tc_taps27(const void* x, int planes, const void* w, in
   for (int i = 1; i < 9; ++i) maps.a[i] = maps.a[0];
   if (use_march) {
     const int nmax = Pn == 2 ? 8 : 16;
-    const int n = D < nmax ? D : nmax;
+    const int n = choose_march_n(B, D, H, W, nmax);
     p.march_n = n;
     p.Dt = (D + n - 1) / n;
     if (!make_w_map(&maps.w, w, Cin, 9 * Pn * 3 * Cout, Pn * 3 * Cout)) return DCA_ERR_LAUNCH;

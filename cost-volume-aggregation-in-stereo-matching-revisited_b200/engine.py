@@ -136,7 +136,8 @@ class Options:
     fuse_upsample_in_conv = True  # cva fuse stage: fold the trilinear upsample into the 1x1x1 conv's epilogue
     fuse_redir_in_deconv = True   # Multi_Aggregation: conv3 (transposed) + redir (1x1x1) as one GEMM
     use_march = True              # k3 s1 Cout=32 convs: depth-marching kernel (kd folded into the GEMM N)
-    march_min_items = 296         # ... when there are at least 2 work items per SM
+    march_min_items = 1184        # ... when there are at least this many (tile column, plane) pairs: 8 per SM.  The kernel
+                                  # picks the planes per work item itself (KITTI 1/8 res: 6, 36 -> 31 us vs the halo kernel)
     cout1_on_tc = True            # 32->1 convs: tensor-core per-tap GEMM + shifted sum instead of the CUDA-core kernel
     prop_on_tc = True             # the two 3x3 Conv2d of PropgationNet_4x on the halo-slab tcgen05 kernel
     up2_bilinear = True           # fuse stage: depth interpolation in the attention store, bilinear 4-class GEMM
@@ -174,7 +175,7 @@ def conv(x: Planes, pc: PackedConv, mode=K3S1, act=ACT_NONE, res_pre: Planes = N
         yptr = y.ptr
     if (Options.use_tc and Options.use_march and mode == K3S1 and not out_fp32 and up is None and side is None
             and pc.w_march is not None and pc.tc_planes == x.planes and planes_out == x.planes
-            and x.B * ((x.D + 15) // 16) * ((x.H + 15) // 16) * ((x.W + 7) // 8) >= Options.march_min_items):
+            and x.B * x.D * ((x.H + 15) // 16) * ((x.W + 7) // 8) >= Options.march_min_items):
         # depth-marching kernel: enough (tile column x depth chunk) work items to fill the SMs
         _lib.call("dca_conv3d_tc_march", x.ptr, x.planes, pc.w_march.data_ptr(), _ptr(pc.scale), _ptr(pc.shift),
                   res_pre.ptr if res_pre is not None else 0, res_post.ptr if res_post is not None else 0, planes_res,
@@ -397,7 +398,7 @@ def conv_taps27(x: Planes, pc: PackedConv, pc1: "PackedCout1", act=ACT_RELU):
             and pc.tc_planes == x.planes and pc1.host.shape == (27, 32)):
         return None
     march = (Options.use_march and pc.w_march is not None
-             and x.B * ((x.D + 15) // 16) * ((x.H + 15) // 16) * ((x.W + 7) // 8) >= Options.march_min_items)
+             and x.B * x.D * ((x.H + 15) // 16) * ((x.W + 7) // 8) >= Options.march_min_items)
     w = pc.w_march if march else pc.w_tc
     if w is None:
         return None

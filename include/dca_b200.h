@@ -141,6 +141,9 @@ int dca_conv2d_stem(const float* x, const float* w, const float* scale, const fl
 int dca_conv2d_tc_cat(const void* x0, int C0, const void* x1, int C1, const void* x2, int C2, int planes,
                       const void* w_tc2d, const float* scale, const float* shift, void* y, int out_f32, int act, int B,
                       int Cout, int H, int W, void* stream);
+/* planes per work item of the depth-marching kernel: 0 (default) = chosen per shape (halo overhead vs fill of the last
+ * wave), n > 0 = forced (timing experiments). */
+int dca_tc_set_march_n(int n);
 /* k3 s1 main loop selector: 1 = halo'd slab reuse (default), 0 = one TMA box per tap. */
 int dca_tc_set_halo(int on);
 /* 1 (default): DCANet-shaped volumes (C=320, Cc=12, G in {8,20,40}, W % 4 == 0) use the 16-byte-staged group-pair
