@@ -511,6 +511,29 @@ def main():
                 g50, g90, _ = p50_of(lambda i: tnet.hot_path_graphed(*tf), 100, 10, torch.cuda.synchronize)
                 graph_rec["tiny_64x128"] = {"eager_p50_ms": e50, "eager_p90_ms": e90, "graph_p50_ms": g50, "graph_p90_ms": g90}
                 del tnet, tf
+        # ---------------- independent pairs in flight on two streams (throughput only), extra key ----------
+        ms_rec = None
+        if n_lat and not args.no_graph:
+            sts = [torch.cuda.Stream(device=dev) for _ in range(2)]
+            for i in range(4):
+                with torch.cuda.stream(sts[i % 2]):
+                    net.hot_path(*dev_sets[i % nsets])
+            barrier()
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record()
+            for st_ in sts:
+                st_.wait_event(m0)
+            for i in range(n_lat):
+                with torch.cuda.stream(sts[i % 2]):
+                    net.hot_path(*dev_sets[i % nsets])
+            for st_ in sts:
+                torch.cuda.current_stream().wait_stream(st_)
+            m1.record()
+            barrier()
+            ms_rec = {"streams": 2, "steps": n_lat, "pairs_per_s_per_gpu": n_lat * B / (m0.elapsed_time(m1) * 1e-3),
+                      "what": "the same forwards issued alternately on two CUDA streams: a pair's kernels take the SMs that "
+                              "the tail of the other pair's single-wave persistent kernel leaves idle (compare with "
+                              "latency.pairs_per_s, the one-stream rate over the same number of steps)"}
         gc.enable()
 
         # ---------------- roofline of the dominant kernel: conv3d k3 s1 32->32 at 1/4 res ----------------
@@ -648,6 +671,8 @@ def main():
             line["graph"] = graph_rec
         if img_rec is not None:
             line["e2e_images"] = img_rec
+        if ms_rec is not None:
+            line["multi_stream"] = ms_rec
         if hrec is not None:
             line["hshard"] = hrec
         line["host"] = {"numa_node_bound": numa, "cpus": len(os.sched_getaffinity(0)) if affinity0 is not None else None}
