@@ -763,8 +763,8 @@ def _prop_mask_start(pk, g, P):
     if not Options.prop_side_stream:
         return (None, pk, g, P)
     main = torch.cuda.current_stream()
-    dev = g.device.index
-    side = _SIDE_STREAMS.get(dev)
+    dev = (g.device.index, main.cuda_stream)   # one side stream AND one buffer set per calling stream: forwards issued
+    side = _SIDE_STREAMS.get(dev)              # concurrently on several streams must not share the mask buffers
     if side is None:
         side = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=g.device)
     side.wait_stream(main)                 # g is ready, and the previous forward no longer reads the buffers below
@@ -773,7 +773,7 @@ def _prop_mask_start(pk, g, P):
     # persistent buffers per shape: no caching-allocator traffic on the side stream (cross-stream frees made single
     # steps stall for 8-100 ms in 2 of 10 bench runs)
     B, Cg, H, W = g.shape
-    key = (g.device.index, B, Cg, H, W, P)
+    key = (g.device.index, main.cuda_stream, B, Cg, H, W, P)
     bufs = pk.__dict__.setdefault("_side_bufs", {}).get(key)
     if bufs is None and Options.use_tc and Options.prop_on_tc:
         gp = Planes(B, 1, H, W, (Cg + 7) // 8 * 8, P, g.device)

@@ -203,3 +203,25 @@ def test_image_pipeline_on_the_device_equals_predict_files(tmp_path):
     for i, (g, r) in enumerate(zip(got, ref)):
         assert g.shape == r.shape and np.array_equal(g, r), i
         assert np.array_equal(np.asarray(Image.open(tmp_path / f"p{i}.png")), np.asarray(Image.open(tmp_path / f"q{i}.png")))
+
+
+def test_forwards_on_two_streams_do_not_share_state():
+    """Independent pairs issued concurrently on two CUDA streams (throughput mode): each stream gets its own side stream and
+    mask buffers, results equal the one-stream forwards bit for bit."""
+    import dcanet_b200 as d
+    import workloads
+    net = workloads.init_bench_weights_(d.GwcNet(96), 0).cuda().eval()
+    fs = [[t.cuda() for t in workloads.feature_maps(s, 1, 32, 64)] for s in (1, 2, 3, 4)]
+    with torch.no_grad():
+        ref = [net.hot_path(*f) for f in fs]
+        torch.cuda.synchronize()
+        sts = [torch.cuda.Stream(), torch.cuda.Stream()]
+        for rep in range(5):
+            outs = []
+            for i, f in enumerate(fs):
+                sts[i % 2].wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(sts[i % 2]):
+                    outs.append(net.hot_path(*f))
+            torch.cuda.synchronize()
+            for (p, v), (rp, rv) in zip(outs, ref):
+                assert torch.equal(p, rp) and torch.equal(v, rv)
