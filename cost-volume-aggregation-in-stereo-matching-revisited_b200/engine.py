@@ -768,14 +768,16 @@ def _prop_mask_start(pk, g, P):
     if side is None:
         side = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=g.device)
     side.wait_stream(main)                 # g is ready, and the previous forward no longer reads the buffers below
-    if not torch.cuda.is_current_stream_capturing():
+    capturing = torch.cuda.is_current_stream_capturing()
+    if not capturing:
         g.record_stream(side)
     # persistent buffers per shape: no caching-allocator traffic on the side stream (cross-stream frees made single
     # steps stall for 8-100 ms in 2 of 10 bench runs)
     B, Cg, H, W = g.shape
     key = (g.device.index, main.cuda_stream, B, Cg, H, W, P)
-    bufs = pk.__dict__.setdefault("_side_bufs", {}).get(key)
-    if bufs is None and Options.use_tc and Options.prop_on_tc:
+    # (under CUDA-graph capture the buffers come from the graph's own pool instead: every graph bakes in its own set)
+    bufs = None if capturing else pk.__dict__.setdefault("_side_bufs", {}).get(key)
+    if bufs is None and not capturing and Options.use_tc and Options.prop_on_tc:
         gp = Planes(B, 1, H, W, (Cg + 7) // 8 * 8, P, g.device)
         m1 = Planes(B, 1, H, W, pk.prop0_tc.cout, P, g.device)
         mask = torch.empty((B, 1, H, W, pk.prop2_tc.cout), dtype=torch.float32, device=g.device)
@@ -797,7 +799,7 @@ def _prop_mask_wait(job):
         return _prop_mask(pk, g, P)
     side, mask, main, bufs = job
     main.wait_stream(side)
-    if bufs is None:
+    if bufs is None and not torch.cuda.is_current_stream_capturing():
         mask.record_stream(main)
     return mask
 

@@ -185,11 +185,21 @@ class GwcNet(nn.Module):
 
     def hot_path_graphed(self, gwc_l, gwc_r, cat_l, cat_r, g):
         """`hot_path` as one CUDA graph per set of input buffers (captured on first use, replayed afterwards; the inputs
-        are read in place, results are returned as copies).  Same kernels, same results, one launch."""
+        are read in place, results are returned as copies).  Same kernels, same results, one launch.  Graphs (and their
+        shared activation pool) are kept per CALLING stream, so forwards replayed concurrently on several streams do not
+        share buffers."""
+        return self.graphed()(gwc_l, gwc_r, cat_l, cat_r, g)
+
+    def graphed(self):
+        """The `engine.GraphedHotPath` of the current stream (created on first use; dropped with the packed parameters)."""
         pk = self.packed()
-        if self._graphed is None or self._graphed.pk is not pk:
-            self._graphed = engine.GraphedHotPath(pk)
-        return self._graphed(gwc_l, gwc_r, cat_l, cat_r, g)
+        if self._graphed is None or self._graphed[0] is not pk:
+            self._graphed = (pk, {})
+        sid = torch.cuda.current_stream().cuda_stream
+        gh = self._graphed[1].get(sid)
+        if gh is None:
+            gh = self._graphed[1][sid] = engine.GraphedHotPath(pk)
+        return gh
 
     def hot_path_hsharded(self, gwc_l, gwc_r, cat_l, cat_r, g, rank, world, group=None, transport="nccl"):
         """One rank of the H-sharded single-pair mode (BASELINE configs[4]): this rank's OWNED 1/4-res rows of the

@@ -174,7 +174,7 @@ def test_graphed_forward_is_bit_identical_to_the_launch_sequence():
         for t, u in zip(fa, fb):                            # same buffers, new contents -> replay of graph A
             t.copy_(u)
         ga2 = net.hot_path_graphed(*fa)
-        assert net._graphed.replays == 3 and len(net._graphed.graphs) == 2
+        assert net.graphed().replays == 3 and len(net.graphed().graphs) == 2
         assert all(torch.equal(x, y) for x, y in zip(eb, ga2))
         pipe = d.HotPathPipeline(net, depth=2, graph=True)  # streaming API on graphs
         hs = [[t.cpu().pin_memory() for t in fb] for _ in range(3)]
@@ -182,7 +182,7 @@ def test_graphed_forward_is_bit_identical_to_the_launch_sequence():
         assert torch.equal(out[0], eb[0].cpu()) and torch.equal(out[1], eb[1].cpu())
         net.invalidate()
         g3 = net.hot_path_graphed(*fb)
-        assert net._graphed.replays == 1 and all(torch.equal(x, y) for x, y in zip(eb, g3))
+        assert net.graphed().replays == 1 and all(torch.equal(x, y) for x, y in zip(eb, g3))
 
 
 def test_image_pipeline_on_the_device_equals_predict_files(tmp_path):
