@@ -118,13 +118,15 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
-def common_config(cfg, n_gpus, batch=0):
+def common_config(cfg, n_gpus, batch=0, sub_batch=4):
     """The workload description shared, key for key, by both arms (the driver compares the dicts)."""
     H, W, maxdisp, B = workloads.CONFIGS[cfg]
     if batch:
         z = common_config(cfg, n_gpus)
+        z["batch_per_gpu"] = batch // n_gpus
         z["batch_total"] = batch
-        z["parallelism"] = f"{batch} pairs per step, {batch // n_gpus} per GPU over {n_gpus} GPU(s), no collective"
+        z["parallelism"] = (f"{batch} pairs per step, {batch // n_gpus} per GPU over {n_gpus} GPU(s) in forwards of up to "
+                            f"{sub_batch} pairs, no collective")
         return z
     return {"workload": cfg, "H": H, "W": W, "maxdisp": maxdisp, "batch_per_gpu": B, "groups": 40,
             "precision": "parity (|d disp| <= 0.05 px of the fp32 torch forward)",
@@ -286,6 +288,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0,
                     help="configs[2] mode: a step is BATCH pairs in total, split BATCH/N per GPU (each rank runs its share "
                          "as consecutive single-pair forwards); 0 (default) = one pair per GPU per step")
+    ap.add_argument("--sub-batch", type=int, default=4,
+                    help="--batch mode: pairs per forward call (a rank's share is processed in forwards of this many pairs)")
     ap.add_argument("--latency-steps", type=int, default=200,
                     help="extra latency loop after the K timed steps (p50/p90 in the `latency` key; 0 = skip)")
     ap.add_argument("--no-images", action="store_true", help="skip the images -> disparity record (`e2e_images` key)")
@@ -312,7 +316,7 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
                 "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": common_config(args.config, args.gpus, args.batch),
+                "config": common_config(args.config, args.gpus, args.batch, args.sub_batch),
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -337,6 +341,14 @@ def main():
     if args.batch and args.batch % world:
         raise SystemExit(f"--batch {args.batch} does not split over {world} ranks")
     ppr = args.batch // world if args.batch else 1          # pairs per rank and step
+    if args.batch:
+        # configs[2]: a rank's share of the batch runs as forwards over `sub_batch` pairs each: the kernels' grids scale with
+        # the batch, which fills the last wave of every single-wave persistent kernel (KITTI: +3 % at 2, +5.5 % at 4 pairs
+        # per forward, results bit-identical per pair: benchmarks/batch_probe.py)
+        sb = max(1, min(args.sub_batch, ppr))
+        while ppr % sb:
+            sb -= 1
+        B, ppr = sb, ppr // sb
     net = workloads.init_bench_weights_(d.GwcNet(maxdisp, precision=args.precision), 0).to(dev).eval()
     H4, W4 = H // 4, W // 4
 
@@ -656,7 +668,7 @@ def main():
                 "dtype": "f16x2 split operands (hi+lo fp16 planes, 22-bit significand), fp32 accumulate" if args.precision == "parity"
                 else "f16 operands, fp32 accumulate",
                 "data": "synthetic",
-                "config": common_config(args.config, world, args.batch),
+                "config": common_config(args.config, world, args.batch, args.sub_batch),
                 "precision_mode": args.precision,
                 "clocks": sampler.summary(),
                 "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * ppr,
