@@ -146,8 +146,8 @@ int dca_conv2d_tc_cat(const void* x0, int C0, const void* x1, int C1, const void
 int dca_tc_set_march_n(int n);
 /* k3 s1 main loop selector: 1 = halo'd slab reuse (default), 0 = one TMA box per tap. */
 int dca_tc_set_halo(int on);
-/* 1 (default): DCANet-shaped volumes (C=320, Cc=12, G in {8,20,40}, W % 4 == 0) use the 16-byte-staged group-pair
-   kernel; 0: the generic kernel everywhere (A/B timing and tests). */
+/* bit 0 (default 1): volumes with C = 320, Cc = 12, G in {8, 20, 40} and W % 8 == 0 use the TMA-staged group-pair kernel
+   (DCANet's shape is G = 40); 0: the generic kernel everywhere (A/B timing and tests).  Bits 1-2: timing probes. */
 int dca_volume_set_v2(int on);
 /* dca_disp_attention at D/8 == 24: 1 (default) two warps per pixel + mma.sync attention core, 2 two warps + fp32 FMA
  * core, 0 one warp per pixel (A/B timing). */
