@@ -48,6 +48,7 @@ SIGNATURES = {
     "dca_pdl_enabled": [],
     "dca_tc_set_deconv_pair": [_c_int],
     "dca_tc_set_march_n": [_c_int],
+    "dca_tap_gather_set_groups": [_c_int],
     "dca_tc_set_up2_side_slots": [_c_int],
     "dca_volume_set_v2": [_c_int],
     "dca_attention_set_team": [_c_int],

@@ -1144,7 +1144,7 @@ tap_gather3d_kernel(const float* __restrict__ P, float* __restrict__ out, int B,
 // softmax (running max / sum / weighted sum), the DG partial states of a pixel are merged through shared memory.
 // Every load is coalesced along w.  logits_out (optional): the summed logits [B,D,H,W] (stage-count variants with no
 // cva stage return them).
-constexpr int TG_DG = 16;
+template <int TG_DG>
 __global__ void __launch_bounds__(32 * TG_DG)
 tap_gather_softmax_regress_kernel(const float* __restrict__ P, float* __restrict__ pred, float* __restrict__ logits_out,
                                   int B, int D, int H, int W) {
@@ -1437,13 +1437,26 @@ extern "C" int dca_tap_gather3d(const float* P, float* out, int B, int D, int H,
   return DCA_OK;
 }
 
+static int g_tg_dg = 16;
+extern "C" int dca_tap_gather_set_groups(int n) { g_tg_dg = n; return DCA_OK; }
 // P fp32 tap-major [27][B*D*H*W] (dca_conv3d_tc_taps27 / dca_conv1_taps_tc) -> pred [B,H,W] = sum_d d softmax_d(logits),
 // logits = 27-tap shifted sum of P; logits_out optional ([B,D,H,W]).  Replaces tap_gather3d + softmax_regress.
 extern "C" int dca_tap_gather_softmax_regress(const float* P, float* pred, float* logits_out, int B, int D, int H, int W,
                                               void* stream) {
   if (!P || !pred || B <= 0 || D <= 0 || H <= 0 || W <= 0 || H > 65535 || B > 65535) return DCA_ERR_ARG;
-  dca_launch(tap_gather_softmax_regress_kernel, dim3((W + 31) / 32, H, B), 32 * TG_DG, 0, (cudaStream_t)stream, P, pred,
-             logits_out, B, D, H, W);
+  // disparity groups per block (threads = 32 x groups; each thread walks D / groups disparities with 27 loads in flight).
+  // Measured at KITTI (benchmarks/one_tail.py): 4: 43.5 us, 6: 69.8, 8: 55.4, 16: 39.7 (default; 155 MB -> 3.9 TB/s = 0.60 of
+  // measured HBM), 24 / 32: 76.8 -- the stride pattern of the 27 x D plane reads, not the thread count, decides
+  const dim3 grid((W + 31) / 32, H, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (g_tg_dg) {
+    case 8: dca_launch(tap_gather_softmax_regress_kernel<8>, grid, 32 * 8, 0, st, P, pred, logits_out, B, D, H, W); break;
+    case 4: dca_launch(tap_gather_softmax_regress_kernel<4>, grid, 32 * 4, 0, st, P, pred, logits_out, B, D, H, W); break;
+    case 6: dca_launch(tap_gather_softmax_regress_kernel<6>, grid, 32 * 6, 0, st, P, pred, logits_out, B, D, H, W); break;
+    case 24: dca_launch(tap_gather_softmax_regress_kernel<24>, grid, 32 * 24, 0, st, P, pred, logits_out, B, D, H, W); break;
+    case 32: dca_launch(tap_gather_softmax_regress_kernel<32>, grid, 32 * 32, 0, st, P, pred, logits_out, B, D, H, W); break;
+    default: dca_launch(tap_gather_softmax_regress_kernel<16>, grid, 32 * 16, 0, st, P, pred, logits_out, B, D, H, W); break;
+  }
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }

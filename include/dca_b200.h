@@ -141,6 +141,8 @@ int dca_conv2d_stem(const float* x, const float* w, const float* scale, const fl
 int dca_conv2d_tc_cat(const void* x0, int C0, const void* x1, int C1, const void* x2, int C2, int planes,
                       const void* w_tc2d, const float* scale, const float* shift, void* y, int out_f32, int act, int B,
                       int Cout, int H, int W, void* stream);
+/* disparity groups per block of dca_tap_gather_softmax_regress (16 / 8 / 6 (default) / 4; timing experiments). */
+int dca_tap_gather_set_groups(int n);
 /* planes per work item of the depth-marching kernel: 0 (default) = chosen per shape (halo overhead vs fill of the last
  * wave), n > 0 = forced (timing experiments). */
 int dca_tc_set_march_n(int n);
