@@ -60,3 +60,24 @@ def test_state_dict_layout_matches_reference():
     # DataParallel-prefixed checkpoint wrapper loads (main_dca.py:277-281)
     m = d.GwcNet(192)
     m.load_state_dict({"epoch": 1, "state_dict": {"module." + k: v for k, v in sd.items()}})
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """include/dca_b200.h compiles as C99 (no C++ / CUDA / torch types in any signature), and a C program that references an
+    entry point links against the shared library with gcc alone."""
+    import subprocess
+    from dcanet_b200 import _lib
+    src = tmp_path / "probe.c"
+    src.write_text('#include "dca_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) { printf("%d %d\\n", dca_version(), dca_plane_format()); '
+                   'return dca_build_gwc_volume_f32(0, 0, 0, 1, 8, 4, 2, 2, 4, 0) == DCA_ERR_ARG ? 0 : 1; }\n')
+    exe = tmp_path / "probe"
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", inc, str(src)])
+    subprocess.check_call(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-l:libdca_b200.so",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    # version / plane format need no GPU; the NULL-pointer call must come back as DCA_ERR_ARG without touching the device
+    assert out.returncode == 0, out
+    assert out.stdout.split()[0] == str(_lib.load().dca_version())
