@@ -148,6 +148,9 @@ class Options:
     fp32_stages = frozenset()     # diagnostics: stages whose convs run on the fp32 CUDA-core kernel: {'dres', 'cva', 'cls3'}
     use_up2 = True                # class-wise halo-slab kernel for the transposed conv and the trilinear fuse stage
     fuse_tail = True              # conv(32ch)+BN+ReLU -> Conv3d(32->1): per-tap products from the first conv's epilogue
+    fuse_gather_stats = False     # the shifted sum + class statistics of a cva stage as ONE kernel (dca_tap_gather_class_stats):
+                                  # bit-identical, but measured SLOWER (36 us vs 9.3 + 16.7 us under ncu at KITTI: 768-thread
+                                  # blocks at one per SM, 23 warps waiting at the barrier for the one that runs the statistics)
 
 
 def conv(x: Planes, pc: PackedConv, mode=K3S1, act=ACT_NONE, res_pre: Planes = None, res_post: Planes = None,
@@ -414,6 +417,21 @@ def tap_gather(P):
     y = torch.empty((B, D, H, W), dtype=torch.float32, device=P.device)
     _lib.call("dca_tap_gather3d", P.data_ptr(), y.data_ptr(), B, D, H, W, _stream())
     return y
+
+
+def tap_gather_class_stats(P):
+    """P [27,B,D,H,W] -> (logits [B,D,H,W], cls [B,H,W] int32, e [B,H,W], S [B,D]): the shifted sum of the 32 -> 1 conv and the
+    class statistics on its result in one launch."""
+    _, B, D, H, W = P.shape
+    dev = P.device
+    logits = torch.empty((B, D, H, W), dtype=torch.float32, device=dev)
+    cls = torch.empty((B, H, W), dtype=torch.int32, device=dev)
+    e = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    S = torch.empty((B, D), dtype=torch.float32, device=dev)
+    scratch = torch.empty(B * D + 1, dtype=torch.int64, device=dev)
+    _lib.call("dca_tap_gather_class_stats", P.data_ptr(), logits.data_ptr(), cls.data_ptr(), e.data_ptr(), S.data_ptr(),
+              scratch.data_ptr(), B, D, H, W, _stream())
+    return logits, cls, e, S
 
 
 def tap_gather_softmax_regress(P, want_logits=False):
@@ -692,12 +710,15 @@ def cva_forward(pk: PackedCva, cost: Planes, res_post: Planes = None, keep=None)
     pooled = avgpool(cost)
     cost_down = conv(pooled, pk.down, K3S1, ACT_RELU)
     P27 = conv_taps27(cost_down, pk.cls0, pk.cls2)
-    if P27 is not None:
-        logits = tap_gather(P27)
+    if P27 is not None and Options.fuse_gather_stats:
+        logits, cls, e, S = tap_gather_class_stats(P27)
     else:
-        h = conv(cost_down, pk.cls0, K3S1, ACT_RELU)
-        logits = conv_cout1_any(h, pk.cls2)
-    cls, e, S = class_stats(logits)
+        if P27 is not None:
+            logits = tap_gather(P27)
+        else:
+            h = conv(cost_down, pk.cls0, K3S1, ACT_RELU)
+            logits = conv_cout1_any(h, pk.cls2)
+        cls, e, S = class_stats(logits)
     use_up2 = Options.use_tc and Options.use_up2 and pk.attn.has_wa
     bil = use_up2 and Options.up2_bilinear
     t = disp_attention(cost_down, cls, e, S, pk.attn.buf, pk.attn.has_wa, pad=(2 if bil else (1 if use_up2 else 0)))
