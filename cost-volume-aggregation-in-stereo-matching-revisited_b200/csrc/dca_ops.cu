@@ -76,79 +76,130 @@ constexpr int CS_MAXD = 256;
 // (a float atomicAdd version differed in the last bit from run to run).  e_p = exp(P[k_p]) lies in (1, e], sums stay
 // below 2^58 for any image the path can hold.  The last CTA to finish (ticket) converts the sums to fp32.
 constexpr float CS_FIX = 1099511627776.0f;   // 2^40
-constexpr int CS_REGD = 48;                  // disparity classes held in registers (D/8 = 24 at KITTI, 48 at Middlebury)
-constexpr int CS_THREADS = 64;               // small blocks: 7,488 pixels spread over 117 CTAs
+constexpr int CS_G = 8;                      // class groups per pixel: thread (lane = pixel, group g) owns classes g, g + 8, ...
+constexpr int CS_PER = 8;                    // ... up to 8 of them in registers (D <= 64; more: they are re-read)
+constexpr int CS_THREADS = 32 * CS_G;
+
+// Per-pixel class statistics by a (32 pixels x CS_G groups) thread block.  A single thread per pixel ran 3,500 dependent
+// instructions (24 x (expf + expf + divide)) on a warp that had its scheduler to itself: 17 us for 7,488 pixels.  Here the
+// classes of a pixel are dealt out over CS_G threads (same lane, different warps: loads stay coalesced along w) and the
+// max / sum / first-argmax are merged through shared memory in a FIXED order, so the result is still reproducible bit
+// for bit.  P[d] = exp(x[d] - m) / s with m = max_d x[d], s = sum_d exp(x[d] - m) (groups summed in the order 0..7);
+// strict > inside a thread (ascending d) and "larger P, then smaller d" across threads keep torch.argmax's FIRST maximum.
+// `load(d)` returns the pixel's logit d; all CS_THREADS threads must call this (it synchronises); valid = the lane
+// holds a pixel.  Returns k (class) and e = exp(P[k]) to the threads with g == 0.
+struct CsSmem { float red[CS_G][32]; int idx[CS_G][32]; };
+// BAR = 0: the whole block takes part (__syncthreads); BAR > 0: only the first CS_THREADS threads do (named barrier BAR)
+template <int BAR>
+__device__ __forceinline__ void cs_sync() {
+  if (BAR == 0) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(CS_THREADS) : "memory");
+}
+template <int BAR, typename Load>
+__device__ __forceinline__ void pixel_class_stats(CsSmem& sm, int lane, int g, int D, bool valid, Load load, int& k_out,
+                                                  float& e_out) {
+  float v[CS_PER];
+  float m = -INFINITY;
+  if (valid) {
+#pragma unroll
+    for (int i = 0; i < CS_PER; ++i) {
+      const int d = g + CS_G * i;
+      v[i] = d < D ? load(d) : -INFINITY;
+      m = fmaxf(m, v[i]);
+    }
+    for (int d = g + CS_G * CS_PER; d < D; d += CS_G) m = fmaxf(m, load(d));
+  }
+  sm.red[g][lane] = m;
+  cs_sync<BAR>();
+#pragma unroll
+  for (int j = 0; j < CS_G; ++j) m = fmaxf(m, sm.red[j][lane]);
+  cs_sync<BAR>();
+  float s = 0.f;
+  if (valid) {
+#pragma unroll
+    for (int i = 0; i < CS_PER; ++i) {
+      const int d = g + CS_G * i;
+      v[i] = d < D ? expf(v[i] - m) : 0.f;
+      s += v[i];
+    }
+    for (int d = g + CS_G * CS_PER; d < D; d += CS_G) s += expf(load(d) - m);
+  }
+  sm.red[g][lane] = s;
+  cs_sync<BAR>();
+  s = 0.f;
+#pragma unroll
+  for (int j = 0; j < CS_G; ++j) s += sm.red[j][lane];
+  cs_sync<BAR>();
+  float best = -1.f;
+  int k = 0;
+  if (valid) {
+#pragma unroll
+    for (int i = 0; i < CS_PER; ++i) {
+      const int d = g + CS_G * i;
+      const float pd = v[i] / s;                        // same formula torch's softmax uses
+      if (d < D && pd > best) { best = pd; k = d; }     // ascending d, strict >: the first maximum of this thread
+    }
+    for (int d = g + CS_G * CS_PER; d < D; d += CS_G) {
+      const float pd = expf(load(d) - m) / s;
+      if (pd > best) { best = pd; k = d; }
+    }
+  }
+  sm.red[g][lane] = best;
+  sm.idx[g][lane] = k;
+  cs_sync<BAR>();
+  if (g == 0) {
+#pragma unroll
+    for (int j = 1; j < CS_G; ++j) {
+      const float bj = sm.red[j][lane];
+      const int kj = sm.idx[j][lane];
+      if (bj > best || (bj == best && kj < k)) { best = bj; k = kj; }
+    }
+    k_out = k;
+    e_out = expf(best);
+  }
+}
+
+// fixed-point per-class sums of one warp of pixels: summed per class inside the warp, one atomic per (warp, class)
+__device__ __forceinline__ void warp_class_sums(unsigned long long* dst, int lane, int kk, unsigned long long efix) {
+  unsigned todo = __ballot_sync(0xffffffffu, kk >= 0);
+  while (todo) {
+    const int leader = __ffs(todo) - 1;
+    const int k0 = __shfl_sync(0xffffffffu, kk, leader);
+    const bool mine = (kk == k0);
+    unsigned long long v = mine ? efix : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == leader) atomicAdd(&dst[k0], v);
+    todo &= ~__ballot_sync(0xffffffffu, mine);
+  }
+}
+
 __global__ void __launch_bounds__(CS_THREADS)
 class_stats_kernel(const float* __restrict__ logits, int* __restrict__ cls, float* __restrict__ e_out,
                    float* __restrict__ S, unsigned long long* __restrict__ acc /* [B*D] sums + [1] ticket, zeroed */,
                    int D, int HW, int BD) {
-  __shared__ unsigned long long s_sum[CS_MAXD];
+  __shared__ CsSmem sm;
   __shared__ int s_last;
   pdl_wait();
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < D; i += blockDim.x) s_sum[i] = 0ull;
-  __syncthreads();
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  int kk = -1;                       // this pixel's class (-1: no pixel) and its fixed-point exp(P[k])
-  unsigned long long efix = 0ull;
-  if (p < HW) {
-    const float* lp = logits + (size_t)b * D * HW + p;
-    float m = -INFINITY, s = 0.f, best = -1.f;
-    int k = 0;
-    if (D <= CS_REGD) {
-      // the pixel's logits in registers: ONE round of independent loads instead of three dependent passes (the kernel
-      // is a latency chain on 7,488 pixels at KITTI: 13.8 -> 6 us); the arithmetic and its order are unchanged
-      float v[CS_REGD];
-#pragma unroll
-      for (int d = 0; d < CS_REGD; ++d) v[d] = d < D ? __ldg(lp + (size_t)d * HW) : -INFINITY;
-#pragma unroll
-      for (int d = 0; d < CS_REGD; ++d) m = fmaxf(m, v[d]);
-#pragma unroll
-      for (int d = 0; d < CS_REGD; ++d) { v[d] = d < D ? expf(v[d] - m) : 0.f; if (d < D) s += v[d]; }
-#pragma unroll
-      for (int d = 0; d < CS_REGD; ++d) {
-        const float pd = v[d] / s;                     // same formula torch's softmax uses
-        if (d < D && pd > best) { best = pd; k = d; }  // strict > keeps the FIRST maximum
-      }
-    } else {
-      for (int d = 0; d < D; ++d) m = fmaxf(m, lp[(size_t)d * HW]);
-      for (int d = 0; d < D; ++d) s += expf(lp[(size_t)d * HW] - m);
-      for (int d = 0; d < D; ++d) {
-        float pd = expf(lp[(size_t)d * HW] - m) / s;
-        if (pd > best) { best = pd; k = d; }
-      }
+  const int p = blockIdx.x * 32 + lane;
+  const bool valid = p < HW;
+  const float* lp = logits + (size_t)b * D * HW + (valid ? p : 0);
+  int k = 0;
+  float e = 0.f;
+  pixel_class_stats<0>(sm, lane, g, D, valid, [&](int d) { return __ldg(lp + (size_t)d * HW); }, k, e);
+  if (g == 0) {
+    if (valid) {
+      cls[(size_t)b * HW + p] = k;
+      e_out[(size_t)b * HW + p] = e;
     }
-    float e = expf(best);
-    cls[(size_t)b * HW + p] = k;
-    e_out[(size_t)b * HW + p] = e;
-    kk = k;
-    efix = __float2ull_rn(e * CS_FIX);
-  }
-  // neighbouring pixels mostly share a class, and a 64-bit shared-memory atomic is a compare-and-swap loop: 64 threads on
-  // one address serialise (the kernel spent most of its 14 us there).  Sum per class inside the warp first (integer
-  // sums: any order gives the same bits), one atomic per (warp, class).
-  {
-    const int lane = threadIdx.x & 31;
-    unsigned todo = __ballot_sync(0xffffffffu, kk >= 0);
-    while (todo) {
-      const int leader = __ffs(todo) - 1;
-      const int k0 = __shfl_sync(0xffffffffu, kk, leader);
-      const bool mine = (kk == k0);
-      unsigned long long v = mine ? efix : 0ull;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == leader) atomicAdd(&s_sum[k0], v);
-      todo &= ~__ballot_sync(0xffffffffu, mine);
+    warp_class_sums(acc + (size_t)b * D, lane, valid ? k : -1, valid ? __float2ull_rn(e * CS_FIX) : 0ull);
+    __threadfence();
+    if (lane == 0) {
+      const unsigned long long t = atomicAdd(&acc[BD], 1ull);
+      s_last = (t == (unsigned long long)gridDim.x * gridDim.y - 1ull);
     }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < D; i += blockDim.x)
-    if (s_sum[i] != 0ull) atomicAdd(&acc[(size_t)b * D + i], s_sum[i]);
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned long long t = atomicAdd(&acc[BD], 1ull);
-    s_last = (t == (unsigned long long)gridDim.x * gridDim.y - 1ull);
   }
   __syncthreads();
   if (s_last) {
@@ -1272,7 +1323,8 @@ conv2d_stem_kernel(const float* __restrict__ x, const float* __restrict__ w, con
 // cva.classify.2 + SemanticLevelContext statistics in one kernel: logits = 27-tap shifted sum of P (exactly as
 // tap_gather3d_kernel: same loads, same summation order), written to HBM (they are an output of the stage) AND kept in shared
 // memory, where one warp per block runs the per-pixel class statistics of class_stats_kernel (same formulas) on them.
-// Saves the class-stats launch and its re-read of the logits: 9.3 + 16.7 us -> one launch (KITTI 1/8 res).
+// Saves the class-stats launch and its re-read of the logits -- but measured SLOWER than the two kernels (35 us at KITTI 1/8
+// res: the gather phase runs worse in these 768-thread blocks), so the engine keeps the two launches; kept as an entry point.
 // Block = 32 w-columns x GC_DG disparity groups of one image row.
 constexpr int GC_DG = 24;
 __global__ void __launch_bounds__(32 * GC_DG)
@@ -1315,40 +1367,24 @@ tap_gather_class_stats_kernel(const float* __restrict__ P, float* __restrict__ l
     }
   }
   __syncthreads();
-  if (g == 0) {                                     // one warp: a pixel per lane
-    int kk = -1;
-    unsigned long long efix = 0ull;
-    if (w < W) {
-      float m = -INFINITY, s = 0.f, best = -1.f;
-      int k = 0;
-      for (int d = 0; d < D; ++d) m = fmaxf(m, gc_log[d * 33 + lane]);
-      for (int d = 0; d < D; ++d) s += expf(gc_log[d * 33 + lane] - m);
-      for (int d = 0; d < D; ++d) {
-        const float pd = expf(gc_log[d * 33 + lane] - m) / s;     // same formula torch's softmax uses
-        if (pd > best) { best = pd; k = d; }                      // strict > keeps the FIRST maximum
+  if (g < CS_G) {                                   // the first CS_G warps: the block's 32 pixels x CS_G class groups
+    const bool valid = w < W;
+    int k = 0;
+    float e = 0.f;
+    pixel_class_stats<1>(*reinterpret_cast<CsSmem*>(gc_log + D * 33), lane, g, D, valid,
+                      [&](int d) { return gc_log[d * 33 + lane]; }, k, e);
+    if (g == 0) {
+      if (valid) {
+        const size_t pix = ((size_t)b * H + h) * W + w;
+        cls[pix] = k;
+        e_out[pix] = e;
       }
-      const float e = expf(best);
-      const size_t pix = ((size_t)b * H + h) * W + w;
-      cls[pix] = k;
-      e_out[pix] = e;
-      kk = k;
-      efix = __float2ull_rn(e * CS_FIX);
-    }
-    unsigned todo = __ballot_sync(0xffffffffu, kk >= 0);
-    while (todo) {                                  // per-class sums inside the warp, one global atomic per class
-      const int leader = __ffs(todo) - 1;
-      const int k0 = __shfl_sync(0xffffffffu, kk, leader);
-      const bool mine = (kk == k0);
-      unsigned long long v = mine ? efix : 0ull;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == leader) atomicAdd(&acc[(size_t)b * D + k0], v);
-      todo &= ~__ballot_sync(0xffffffffu, mine);
-    }
-    __threadfence();
-    if (lane == 0) {
-      const unsigned long long t = atomicAdd(&acc[(size_t)B * D], 1ull);
-      s_last = (t == (unsigned long long)gridDim.x * gridDim.y * gridDim.z - 1ull);
+      warp_class_sums(acc + (size_t)b * D, lane, valid ? k : -1, valid ? __float2ull_rn(e * CS_FIX) : 0ull);
+      __threadfence();
+      if (lane == 0) {
+        const unsigned long long t = atomicAdd(&acc[(size_t)B * D], 1ull);
+        s_last = (t == (unsigned long long)gridDim.x * gridDim.y * gridDim.z - 1ull);
+      }
     }
   }
   __syncthreads();
@@ -1397,7 +1433,7 @@ extern "C" int dca_class_stats(const float* logits, int* cls, float* e, float* S
   cudaStream_t st = (cudaStream_t)stream;
   if (cudaMemsetAsync(scratch, 0, ((size_t)B * D + 1) * sizeof(unsigned long long), st) != cudaSuccess) return DCA_ERR_LAUNCH;
   const int HW = H * W;
-  dca_launch(class_stats_kernel, dim3((HW + CS_THREADS - 1) / CS_THREADS, B), CS_THREADS, 0, st, logits, cls, e, S,
+  dca_launch(class_stats_kernel, dim3((HW + 31) / 32, B), CS_THREADS, 0, st, logits, cls, e, S,
              (unsigned long long*)scratch, D, HW, B * D);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
@@ -1413,8 +1449,8 @@ extern "C" int dca_tap_gather_class_stats(const float* P, float* logits, int* cl
     return DCA_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   if (cudaMemsetAsync(scratch, 0, ((size_t)B * D + 1) * sizeof(unsigned long long), st) != cudaSuccess) return DCA_ERR_LAUNCH;
-  dca_launch(tap_gather_class_stats_kernel, dim3((W + 31) / 32, H, B), 32 * GC_DG, (size_t)D * 33 * sizeof(float), st, P, logits,
-             cls, e, S, (unsigned long long*)scratch, B, D, H, W);
+  dca_launch(tap_gather_class_stats_kernel, dim3((W + 31) / 32, H, B), 32 * GC_DG,
+             (size_t)D * 33 * sizeof(float) + sizeof(CsSmem), st, P, logits, cls, e, S, (unsigned long long*)scratch, B, D, H, W);
   DCA_RETURN_IF_LAUNCH_FAILED();
   return DCA_OK;
 }

@@ -149,8 +149,8 @@ class Options:
     use_up2 = True                # class-wise halo-slab kernel for the transposed conv and the trilinear fuse stage
     fuse_tail = True              # conv(32ch)+BN+ReLU -> Conv3d(32->1): per-tap products from the first conv's epilogue
     fuse_gather_stats = False     # the shifted sum + class statistics of a cva stage as ONE kernel (dca_tap_gather_class_stats):
-                                  # bit-identical, but measured SLOWER (36 us vs 9.3 + 16.7 us under ncu at KITTI: 768-thread
-                                  # blocks at one per SM, 23 warps waiting at the barrier for the one that runs the statistics)
+                                  # bit-identical, but measured SLOWER (35 us vs 9.3 us + the class-stats kernel under ncu at
+                                  # KITTI: the gather runs worse in 768-thread blocks at one block per SM)
 
 
 def conv(x: Planes, pc: PackedConv, mode=K3S1, act=ACT_NONE, res_pre: Planes = None, res_post: Planes = None,
